@@ -1,0 +1,326 @@
+// TEST INFRASTRUCTURE — not product code.
+//
+// C-ABI shim over the UNMODIFIED reference (denniskb/spice2 @ f5e57eb), compiled from the
+// sources where they lie under $(REF) (= /root/reference) by oracle/Makefile into
+// oracle/_ref/libspice_ref_{fast,strict}.so.  Nothing from the reference is copied into this
+// repository: this file only calls the reference's public API (spice/snn.h, spice/topology.h,
+// spice/util/random.h, spice/util/numeric.h) and textually includes the reference's sample
+// model definitions (samples/brunel.cpp, samples/brunel+.cpp, samples/vogels.cpp) in place,
+// inside namespaces, so that the oracle runs the reference's own functors.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's reference / cpu_baseline leg may load
+// the resulting library.
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <initializer_list>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <span>
+#include <string>
+#include <vector>
+
+#include "spice/snn.h"
+#include "spice/topology.h"
+#include "spice/util/numeric.h"
+#include "spice/util/random.h"
+#include "spice/util/range.h"
+
+#include "matplot.h" // reference samples/matplot.h (declarations only; the shim defines the sink)
+
+// The samples call pause() and stream into spike_output_stream; the shim never runs their
+// main(), but the symbols must resolve.  (The reference's own sink is samples/matplot.cpp,
+// which the sample executables built by the Makefile link instead.)
+#ifndef REF_SHIM_NO_SINK
+void pause(double) {}
+struct spike_output_stream::impl {};
+spike_output_stream::spike_output_stream(std::string const&, bool) {}
+spike_output_stream::~spike_output_stream() = default;
+spike_output_stream& spike_output_stream::operator<<(spice::detail::NeuronPopulation const*) {
+	return *this;
+}
+spike_output_stream& spike_output_stream::operator<<(char const) { return *this; }
+#endif
+
+// The reference's own model definitions, in place.  All headers they include are already
+// included above at global scope (every one is `#pragma once`), so inside the namespace the
+// include directives are no-ops and only the sample's own declarations land here.
+namespace ref_brunel {
+#include "brunel.cpp"
+}
+namespace ref_brunel_plus {
+#include "brunel+.cpp"
+}
+namespace ref_vogels {
+#include "vogels.cpp"
+}
+
+namespace {
+using clk = std::chrono::steady_clock;
+
+double seconds(clk::time_point a, clk::time_point b) {
+	return std::chrono::duration<double>(b - a).count();
+}
+
+spice::util::seed_seq make_seed(std::uint32_t const* il, int n, int increments) {
+	// seed_seq only takes an initializer_list; build one per supported arity.
+	spice::util::seed_seq s = [&]() -> spice::util::seed_seq {
+		switch (n) {
+			case 1: return {il[0]};
+			case 2: return {il[0], il[1]};
+			case 3: return {il[0], il[1], il[2]};
+			case 4: return {il[0], il[1], il[2], il[3]};
+			default: return {il[0], il[1], il[2], il[3], il[4]};
+		}
+	}();
+	for (int i = 0; i < increments; i++)
+		s++;
+	return s;
+}
+
+struct raster {
+	std::int32_t* ids;     // flat spike ids, population-local
+	std::int64_t capacity; // capacity of ids
+	std::int64_t* counts;  // [steps * npop]
+	std::int64_t used = 0;
+	bool overflow     = false;
+
+	void push(std::span<std::int32_t const> s, std::int64_t slot) {
+		counts[slot] = static_cast<std::int64_t>(s.size());
+		if (used + static_cast<std::int64_t>(s.size()) > capacity) {
+			overflow = true;
+			return;
+		}
+		std::copy(s.begin(), s.end(), ids + used);
+		used += static_cast<std::int64_t>(s.size());
+	}
+};
+}
+
+extern "C" {
+
+// ---- seeds / rng (random.h:143-175, 222-234) -------------------------------------------------
+void ref_seed(std::uint32_t const* il, int n, int increments, std::uint64_t out[2]) {
+	auto const s = make_seed(il, n, increments).seed();
+	out[0]       = s.lo;
+	out[1]       = s.hi;
+}
+
+void ref_xoroshiro(std::uint32_t const* il, int n, int increments, std::int64_t count,
+                   std::uint64_t* out) {
+	spice::util::xoroshiro64_128p rng(make_seed(il, n, increments));
+	for (std::int64_t i = 0; i < count; i++)
+		out[i] = rng();
+}
+
+// generate_canonical<float>(rng) and exponential_distribution<double>(scale)(rng) on the same
+// stream, so tests can pin the u -> value maps (random.h:236-247, 264-276).
+void ref_canonical_float(std::uint32_t const* il, int n, int increments, std::int64_t count,
+                         float* out) {
+	spice::util::xoroshiro64_128p rng(make_seed(il, n, increments));
+	for (std::int64_t i = 0; i < count; i++)
+		out[i] = spice::util::generate_canonical<float>(rng);
+}
+
+void ref_exponential(std::uint32_t const* il, int n, int increments, double scale,
+                     std::int64_t count, double* out) {
+	spice::util::xoroshiro64_128p rng(make_seed(il, n, increments));
+	spice::util::exponential_distribution<double> d(scale);
+	for (std::int64_t i = 0; i < count; i++)
+		out[i] = d(rng);
+}
+
+// ---- kahan-compensated dt exactly as snn::step() produces it (snn.cpp:8-10) -------------------
+void ref_kahan_dt(float dt, std::int64_t steps, float* out) {
+	spice::util::kahan_sum<float> simtime;
+	for (std::int64_t i = 0; i < steps; i++) {
+		float const d = simtime += dt;
+		if (simtime >= 1)
+			simtime.reset();
+		out[i] = d;
+	}
+}
+
+// ---- fixed_probability (topology.cpp:75-112) ---------------------------------------------------
+std::int64_t ref_fixed_probability_size(std::int64_t src, std::int64_t dst, double p) {
+	spice::fixed_probability fp(p);
+	fp(src, dst);
+	return fp.size();
+}
+
+// offsets: src+1 entries, neighbors: >= size() entries.  Returns the edge count.
+std::int64_t ref_fixed_probability_generate(std::int64_t src, std::int64_t dst, double p,
+                                            std::uint32_t const* il, int n, int increments,
+                                            std::int64_t* offsets, std::int32_t* neighbors,
+                                            double* seconds_out) {
+	spice::fixed_probability fp(p);
+	fp(src, dst);
+	auto const t0 = clk::now();
+	fp.generate(std::span<Int>(reinterpret_cast<Int*>(offsets), static_cast<std::size_t>(src + 1)),
+	            std::span<Int32>(neighbors, static_cast<std::size_t>(fp.size())),
+	            make_seed(il, n, increments));
+	auto const t1 = clk::now();
+	if (seconds_out)
+		*seconds_out = seconds(t0, t1);
+	return (src > 0 && dst > 0 && p > 0) ? offsets[src] : 0;
+}
+
+// ---- Brunel (samples/brunel.cpp:78-103), parametrised -----------------------------------------
+// Populations in add order P (poisson, N/2), E (lif, 4N/10), I (lif, N/10); six connections in
+// the sample's order.  Raster slots are step*3 + {0:P,1:E,2:I}.  state_E/state_I receive the
+// final lif::neuron arrays ({float V; int Twait} = 8 bytes each) when non-null.
+int ref_brunel_run(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay,
+                   std::uint32_t seed, std::int64_t steps, std::int32_t* ids,
+                   std::int64_t capacity, std::int64_t* counts, void* state_E, void* state_I,
+                   double* build_seconds, double* sim_seconds, std::int64_t* synaptic_events) {
+	using namespace ref_brunel;
+	auto const t0 = clk::now();
+	spice::snn net(dt, delay, {seed});
+	auto P = net.add_population<poisson>(N / 2);
+	auto E = net.add_population<lif>(N * 4 / 10);
+	auto I = net.add_population<lif>(N / 10);
+	net.connect<fixed_weight>(P, E, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(P, I, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(E, E, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(E, I, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(I, E, spice::fixed_probability(p), delay, {w_inh});
+	net.connect<fixed_weight>(I, I, spice::fixed_probability(p), delay, {w_inh});
+	auto const t1 = clk::now();
+
+	raster r{ids, capacity, counts};
+	double sim = 0;
+	for (std::int64_t s = 0; s < steps; s++) {
+		auto const a = clk::now();
+		net.step();
+		sim += seconds(a, clk::now());
+		if (counts) {
+			r.push(P->spikes(0), s * 3 + 0);
+			r.push(E->spikes(0), s * 3 + 1);
+			r.push(I->spikes(0), s * 3 + 2);
+		}
+	}
+	if (state_E)
+		std::memcpy(state_E, E->get_neurons().data(), E->size() * sizeof(lif::neuron));
+	if (state_I)
+		std::memcpy(state_I, I->get_neurons().data(), I->size() * sizeof(lif::neuron));
+	if (build_seconds)
+		*build_seconds = seconds(t0, t1);
+	if (sim_seconds)
+		*sim_seconds = sim;
+	(void)synaptic_events;
+	return r.overflow ? 1 : 0;
+}
+
+// ---- Brunel+ (samples/brunel+.cpp:102-117): E->E plastic -------------------------------------
+int ref_brunel_plus_run(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay,
+                        std::uint32_t seed, std::int64_t steps, std::int32_t* ids,
+                        std::int64_t capacity, std::int64_t* counts, void* state_E, void* state_I,
+                        double* build_seconds, double* sim_seconds) {
+	using namespace ref_brunel_plus;
+	auto const t0 = clk::now();
+	spice::snn net(dt, delay, {seed});
+	auto P = net.add_population<poisson>(N / 2);
+	auto E = net.add_population<lif>(N * 4 / 10);
+	auto I = net.add_population<lif>(N / 10);
+	net.connect<fixed_weight>(P, E, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(P, I, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<plastic>(E, E, spice::fixed_probability(p), delay);
+	net.connect<fixed_weight>(E, I, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<fixed_weight>(I, E, spice::fixed_probability(p), delay, {w_inh});
+	net.connect<fixed_weight>(I, I, spice::fixed_probability(p), delay, {w_inh});
+	auto const t1 = clk::now();
+
+	raster r{ids, capacity, counts};
+	double sim = 0;
+	for (std::int64_t s = 0; s < steps; s++) {
+		auto const a = clk::now();
+		net.step();
+		sim += seconds(a, clk::now());
+		if (counts) {
+			r.push(P->spikes(0), s * 3 + 0);
+			r.push(E->spikes(0), s * 3 + 1);
+			r.push(I->spikes(0), s * 3 + 2);
+		}
+	}
+	if (state_E)
+		std::memcpy(state_E, E->get_neurons().data(), E->size() * sizeof(lif::neuron));
+	if (state_I)
+		std::memcpy(state_I, I->get_neurons().data(), I->size() * sizeof(lif::neuron));
+	if (build_seconds)
+		*build_seconds = seconds(t0, t1);
+	if (sim_seconds)
+		*sim_seconds = sim;
+	return r.overflow ? 1 : 0;
+}
+
+// ---- Vogels (samples/vogels.cpp:62-76): E (8N/10), I (2N/10), static synapses ------------------
+// Raster slots are step*2 + {0:E,1:I}.  lif::neuron = {float V, Gex, Gin; int32 Twait} = 16 B.
+int ref_vogels_run(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay,
+                   std::uint32_t seed, std::int64_t steps, std::int32_t* ids,
+                   std::int64_t capacity, std::int64_t* counts, void* state_E, void* state_I,
+                   double* build_seconds, double* sim_seconds) {
+	using namespace ref_vogels;
+	auto const t0 = clk::now();
+	spice::snn net(dt, delay, {seed});
+	auto E = net.add_population<lif>(N * 8 / 10);
+	auto I = net.add_population<lif>(N * 2 / 10);
+	net.connect<excitatory>(E, E, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<excitatory>(E, I, spice::fixed_probability(p), delay, {w_exc});
+	net.connect<inhibitory>(I, E, spice::fixed_probability(p), delay, {w_inh});
+	net.connect<inhibitory>(I, I, spice::fixed_probability(p), delay, {w_inh});
+	auto const t1 = clk::now();
+
+	raster r{ids, capacity, counts};
+	double sim = 0;
+	for (std::int64_t s = 0; s < steps; s++) {
+		auto const a = clk::now();
+		net.step();
+		sim += seconds(a, clk::now());
+		if (counts) {
+			r.push(E->spikes(0), s * 2 + 0);
+			r.push(I->spikes(0), s * 2 + 1);
+		}
+	}
+	if (state_E)
+		std::memcpy(state_E, E->get_neurons().data(), E->size() * sizeof(lif::neuron));
+	if (state_I)
+		std::memcpy(state_I, I->get_neurons().data(), I->size() * sizeof(lif::neuron));
+	if (build_seconds)
+		*build_seconds = seconds(t0, t1);
+	if (sim_seconds)
+		*sim_seconds = sim;
+	return r.overflow ? 1 : 0;
+}
+
+// libm values at the reference's call sites (random.h:271 -> glibc log; brunel+.cpp:78-79,96-97
+// -> glibc expf / pow), so tests can pin the device restatements against this host's libm.
+// Called through volatile pointers so -ffast-math cannot swap in a libmvec vector variant:
+// the reference's call sites are scalar calls inside serial loops.
+void ref_libm_log(double const* x, std::int64_t n, double* out) {
+	double (*volatile f)(double) = static_cast<double (*)(double)>(&std::log);
+	for (std::int64_t i = 0; i < n; i++)
+		out[i] = f(x[i]);
+}
+void ref_libm_expf(float const* x, std::int64_t n, float* out) {
+	float (*volatile f)(float) = static_cast<float (*)(float)>(&std::exp);
+	for (std::int64_t i = 0; i < n; i++)
+		out[i] = f(x[i]);
+}
+void ref_libm_pow(double const* x, double const* y, std::int64_t n, double* out) {
+	double (*volatile f)(double, double) = static_cast<double (*)(double, double)>(&std::pow);
+	for (std::int64_t i = 0; i < n; i++)
+		out[i] = f(x[i], y[i]);
+}
+
+char const* ref_build_flavour() {
+#ifdef REF_STRICT
+	return "strict (-O2 -fno-fast-math -ffp-contract=off)";
+#else
+	return "reference flags (-O2 -ffast-math ... -march=haswell -mfpmath=sse)";
+#endif
+}
+}
