@@ -1,0 +1,324 @@
+"""spice2_b200 — Python host mirror of the reference's `snn` API over the B200 C ABI.
+
+The product is the CUDA library (spice2_b200/csrc -> libspice_b200.so, C ABI in
+include/spice_b200.h) and the C++20 facade (csrc/include/spice/snn.h).  This module is the
+Python-side mirror used by tests/ and bench.py: same vocabulary as the reference
+(`snn(dt, max_delay, seed)`, `add_population`, `connect(..., fixed_probability(p), delay, ...)`,
+`step()`, `population.spikes(age)`; reference: spice/include/spice/snn.h:16-75), every call
+going straight through ctypes into the C ABI.  There is no CPU fallback: without the CUDA
+library or a CUDA device every computing call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from pathlib import Path
+
+import numpy as np
+
+from .build import build as _build
+
+__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "seed_seq",
+           "MODE_DETERMINISTIC", "MODE_FAST"]
+
+MODE_DETERMINISTIC, MODE_FAST = 0, 1
+_ERR = {1: "precondition", 2: "cuda", 3: "unsupported", 4: "internal", 5: "no device"}
+
+
+class SpiceError(RuntimeError):
+    """Non-zero status from the C ABI.  Violated preconditions carry the reference's message form
+    'Assertion failed (file:line): cond' (spice/src/util/assert.cpp:8-15)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"[{_ERR.get(code, code)}] {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The CUDA library; built in-tree on first use.  Raises if it cannot be had — never falls
+    back to a CPU path."""
+    global _lib
+    if _lib is None:
+        path = _build()
+        L = C.CDLL(str(path))
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+        sig = {
+            "spice_ctx_create": (i32, [C.POINTER(vp), i32, C.c_float, C.c_float, vp, i32, i32, i32, i32]),
+            "spice_ctx_destroy": (i32, [vp]),
+            "spice_last_error": (C.c_char_p, [vp]),
+            "spice_ctx_set_stream": (i32, [vp, vp]),
+            "spice_add_population": (i32, [vp, vp, i64, vp, C.POINTER(i32)]),
+            "spice_population_size": (i64, [vp, i32]),
+            "spice_population_range": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
+            "spice_connect_fixed_probability": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
+            "spice_connect_adj_list": (i32, [vp, vp, i32, i32, vp, vp, i64, C.c_float, vp, C.POINTER(i32)]),
+            "spice_connection_csr": (i32, [vp, i32, C.POINTER(i64), vp, vp]),
+            "spice_connection_synapses": (i32, [vp, i32, vp, i64]),
+            "spice_run": (i32, [vp, i64]),
+            "spice_sync": (i32, [vp]),
+            "spice_time": (i64, [vp]),
+            "spice_spikes": (i32, [vp, i32, i64, C.POINTER(vp), C.POINTER(i64)]),
+            "spice_neurons": (i32, [vp, i32, vp, i64]),
+            "spice_set_neurons": (i32, [vp, i32, vp, i64]),
+            "spice_raster_enable": (i32, [vp, i32]),
+            "spice_raster_size": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+            "spice_raster_read": (i32, [vp, vp, vp]),
+            "spice_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+            "spice_ctx_finalize": (i32, [vp]),
+            "spice_ctx_peer_handle": (i32, [vp, vp, C.POINTER(i64)]),
+            "spice_ctx_set_peers": (i32, [vp, vp, i64]),
+            "spice_fixed_probability_max_degree": (i64, [i64, C.c_double]),
+            "spice_fixed_probability_generate": (i32, [i32, i64, i64, C.c_double, C.c_uint64, C.c_uint64, i64, i64,
+                                                       C.POINTER(vp)]),
+            "spice_adjacency_edges": (i64, [vp]),
+            "spice_adjacency_offsets_dev": (vp, [vp]),
+            "spice_adjacency_neighbors_dev": (vp, [vp]),
+            "spice_adjacency_copy": (i32, [vp, vp, vp]),
+            "spice_adjacency_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i64)]),
+            "spice_adjacency_destroy": (i32, [vp]),
+            "spice_seed_seq": (None, [vp, i32, vp]),
+            "spice_seed_next": (None, [vp]),
+            "spice_builtin_neuron": (vp, [C.c_char_p]),
+            "spice_builtin_synapse": (vp, [C.c_char_p]),
+            "spice_device_check": (i32, [i32]),
+            "spice_version": (C.c_char_p, []),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---- built-in sample models (the same structs as spice/models/*.h) -----------------------------
+# name -> (functor packer, neuron dtype)
+NEURON_MODELS = {
+    "brunel.poisson": (lambda **kw: b"\0", None),
+    "brunel.lif": (lambda **kw: b"\0", np.dtype([("V", np.float32), ("Twait", np.int32)])),
+    "vogels.lif": (lambda **kw: b"\0", np.dtype([("V", np.float32), ("Gex", np.float32), ("Gin", np.float32),
+                                                 ("Twait", np.int32)])),
+}
+SYNAPSE_MODELS = {
+    "brunel.fixed_weight": lambda weight: struct.pack("<f", np.float32(weight)),
+    "vogels.excitatory": lambda weight: struct.pack("<f", np.float32(weight)),
+    "vogels.inhibitory": lambda weight: struct.pack("<f", np.float32(weight)),
+}
+
+
+class fixed_probability:
+    """spice::fixed_probability (spice/include/spice/topology.h:48-58)."""
+
+    def __init__(self, p: float):
+        self.p = float(p)
+
+
+class adj_list:
+    """spice::adj_list (spice/include/spice/topology.h:37-46)."""
+
+    def __init__(self):
+        self.src, self.dst = [], []
+
+    def connect(self, src: int, dst: int):
+        self.src.append(src)
+        self.dst.append(dst)
+
+
+def seed_seq(words, increments=0):
+    """util::seed_seq{words...} advanced `increments` times -> (lo, hi)  (random.h:143-175)."""
+    w = np.asarray(words, np.uint32)
+    out = np.zeros(2, np.uint64)
+    lib().spice_seed_seq(_ptr(w), len(w), _ptr(out))
+    for _ in range(increments):
+        lib().spice_seed_next(_ptr(out))
+    return int(out[0]), int(out[1])
+
+
+class Population:
+    """Handle returned by snn.add_population (reference: detail::neuron_population<Neur>*)."""
+
+    def __init__(self, net: "snn", index: int, model: str, size: int):
+        self.net, self.index, self.model, self._size = net, index, model, size
+        self.dtype = NEURON_MODELS[model][1]
+
+    def size(self) -> int:
+        return self._size
+
+    def range(self):
+        lo, hi = C.c_int64(), C.c_int64()
+        self.net._check(lib().spice_population_range(self.net._h, self.index, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def spikes(self, age: int = 0) -> np.ndarray:
+        """NeuronPopulation::spikes(age) (neuron_population.h:147-153)."""
+        p, n = C.c_void_p(), C.c_int64()
+        self.net._check(lib().spice_spikes(self.net._h, self.index, age, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
+
+    def get_neurons(self) -> np.ndarray:
+        """neuron_population::get_neurons() (neuron_population.h:142-145); this rank's slice."""
+        if self.dtype is None:
+            raise SpiceError(1, "Can only return collections of stateful neurons.")
+        lo, hi = self.range()
+        out = np.zeros(hi - lo, self.dtype)
+        self.net._check(lib().spice_neurons(self.net._h, self.index, _ptr(out), out.nbytes))
+        return out
+
+    def set_neurons(self, values: np.ndarray):
+        values = np.ascontiguousarray(values, self.dtype)
+        self.net._check(lib().spice_set_neurons(self.net._h, self.index, _ptr(values), values.nbytes))
+
+
+class snn:
+    """spice::snn (spice/include/spice/snn.h:16-75) on one B200 (or one rank of several)."""
+
+    def __init__(self, dt, max_delay, seed=(1337,), device=0, rank=0, world=1, mode=MODE_DETERMINISTIC):
+        L = lib()
+        words = np.asarray(seed, np.uint32)
+        h = C.c_void_p()
+        rc = L.spice_ctx_create(C.byref(h), device, np.float32(dt), np.float32(max_delay), _ptr(words), len(words), rank,
+                                world, mode)
+        if rc != 0:
+            raise SpiceError(rc, L.spice_last_error(None).decode())
+        self._h = h
+        self.populations: list[Population] = []
+        self.connections = []
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().spice_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SpiceError(rc, lib().spice_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(lib().spice_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def add_population(self, model: str, size: int, **params) -> Population:
+        ops = lib().spice_builtin_neuron(model.encode())
+        if not ops:
+            raise SpiceError(3, f"unknown neuron model {model!r}")
+        functor = NEURON_MODELS[model][0](**params)
+        idx = C.c_int()
+        self._check(lib().spice_add_population(self._h, ops, size, functor, C.byref(idx)))
+        pop = Population(self, idx.value, model, size)
+        self.populations.append(pop)
+        return pop
+
+    def connect(self, synapse: str, source: Population, target: Population, topology, delay, **params) -> int:
+        ops = lib().spice_builtin_synapse(synapse.encode())
+        if not ops:
+            raise SpiceError(3, f"unknown synapse model {synapse!r}")
+        functor = SYNAPSE_MODELS[synapse](**params)
+        idx = C.c_int()
+        if isinstance(topology, fixed_probability):
+            self._check(lib().spice_connect_fixed_probability(self._h, ops, source.index, target.index, topology.p,
+                                                              np.float32(delay), functor, C.byref(idx)))
+        elif isinstance(topology, adj_list):
+            s = np.asarray(topology.src, np.int32)
+            d = np.asarray(topology.dst, np.int32)
+            self._check(lib().spice_connect_adj_list(self._h, ops, source.index, target.index, _ptr(s), _ptr(d), len(s),
+                                                     np.float32(delay), functor, C.byref(idx)))
+        else:
+            raise TypeError("topology must be fixed_probability or adj_list")
+        self.connections.append((synapse, source.index, target.index))
+        return idx.value
+
+    def connection_csr(self, conn: int):
+        n = C.c_int64()
+        self._check(lib().spice_connection_csr(self._h, conn, C.byref(n), None, None))
+        src_size = self.populations[self.connections[conn][1]].size()
+        off = np.zeros(src_size + 1, np.int64)
+        nb = np.zeros(max(n.value, 1), np.int32)
+        self._check(lib().spice_connection_csr(self._h, conn, C.byref(n), _ptr(off), _ptr(nb)))
+        return off, nb[: n.value]
+
+    def step(self, n: int = 1):
+        """snn::step() n times (spice/src/snn.cpp:7-28).  Asynchronous; readouts synchronise."""
+        self._check(lib().spice_run(self._h, n))
+
+    def sync(self):
+        self._check(lib().spice_sync(self._h))
+
+    def time(self) -> int:
+        return int(lib().spice_time(self._h))
+
+    def spikes(self, i: int, age: int = 0) -> np.ndarray:
+        """Convenience named by the north star: spikes of the i-th population added."""
+        return self.populations[i].spikes(age)
+
+    def raster_enable(self, on=True):
+        self._check(lib().spice_raster_enable(self._h, int(on)))
+
+    def raster_read(self):
+        """-> (counts[steps, npops], ids concatenated in (step, pop) order); clears the log."""
+        steps, nids = C.c_int64(), C.c_int64()
+        self._check(lib().spice_raster_size(self._h, C.byref(steps), C.byref(nids)))
+        counts = np.zeros((steps.value, len(self.populations)), np.int64)
+        ids = np.zeros(max(nids.value, 1), np.int32)
+        self._check(lib().spice_raster_read(self._h, _ptr(counts), _ptr(ids)))
+        return counts, ids[: nids.value]
+
+    def stats(self):
+        ev, sp, kl = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(lib().spice_stats(self._h, C.byref(ev), C.byref(sp), C.byref(kl)))
+        return dict(synaptic_events=ev.value, spikes_delivered=sp.value, kernel_launches=kl.value)
+
+    # multi-GPU plumbing (one process per GPU; handles are all-gathered by the caller)
+    def finalize(self):
+        self._check(lib().spice_ctx_finalize(self._h))
+
+    def peer_handle(self) -> bytes:
+        n = C.c_int64()
+        self._check(lib().spice_ctx_peer_handle(self._h, None, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(lib().spice_ctx_peer_handle(self._h, buf, C.byref(n)))
+        return buf.raw
+
+    def set_peers(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        self._check(lib().spice_ctx_set_peers(self._h, blob, len(handles[0])))
+
+
+def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True):
+    """fixed_probability::generate on the GPU (spice/src/topology.cpp:80-112) -> dict."""
+    L = lib()
+    lo, hi = seed_seq(seed, increments)
+    col_hi = dst if col_hi is None else col_hi
+    h = C.c_void_p()
+    rc = L.spice_fixed_probability_generate(device, src, dst, p, lo, hi, col_lo, col_hi, C.byref(h))
+    if rc != 0:
+        raise SpiceError(rc, L.spice_last_error(None).decode())
+    try:
+        e = int(L.spice_adjacency_edges(h))
+        total, rows = C.c_float(), C.c_float()
+        draws = C.c_int64()
+        L.spice_adjacency_timing(h, C.byref(total), C.byref(rows), C.byref(draws))
+        out = dict(edges=e, total_ms=total.value, rows_ms=rows.value, draws=draws.value)
+        if copy:
+            off = np.zeros(src + 1, np.int64)
+            nb = np.zeros(max(e, 1), np.int32)
+            rc = L.spice_adjacency_copy(h, _ptr(off), _ptr(nb))
+            if rc != 0:
+                raise SpiceError(rc, "adjacency copy failed")
+            out.update(offsets=off, neighbors=nb[:e])
+        return out
+    finally:
+        L.spice_adjacency_destroy(h)

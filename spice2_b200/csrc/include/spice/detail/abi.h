@@ -1,0 +1,116 @@
+// Internal contract between the model-agnostic runtime (runtime.cu) and the kernel templates
+// instantiated per user model (kernels.cuh / model_ops.cuh).  Plain structs, shared by host and
+// device code.  Not part of the public C ABI (include/spice_b200.h), which only sees the two ops
+// tables as opaque pointers.
+#pragma once
+
+#include <cstdint>
+
+#include "spice/util/platform.h"
+
+namespace spice::detail {
+
+constexpr int kMaxWindow   = 32; // steps per launch window (also bounded by the minimum delay)
+constexpr int kMaxIncoming = 8;  // connections into one population handled by one update launch
+constexpr int kMaxWorld    = 16; // ranks (GPUs of one NVSwitch domain)
+constexpr int kRngChunk    = 32; // consecutive neurons whose draws one thread generates per jump
+
+struct u128 {
+	std::uint64_t lo, hi;
+};
+
+// Device function applying `k` deliveries of one connection's (stateless) synapse functor to a
+// neuron held in registers/local memory: k sequential calls of Syn::deliver, which is what the
+// reference does event by event (synapse_population.h:118-133).
+using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
+
+// One incoming connection as the target population's update kernel sees it.
+struct incoming {
+	std::uint32_t* counts; // [ring][n_local] event counters, slot = consume step % ring
+	float* accum;          // [ring][n_local] float contributions of stateful synapses (or null)
+	apply_fn apply;        // device function pointer (same module as the update kernel)
+	void const* functor;   // device copy of the Syn object
+	std::int32_t ring;
+	std::int32_t accum_word; // neuron word the accumulated float is added to (stateful synapses)
+};
+
+// Per-window random-access tables for the step streams: for every step of the window, the 128
+// basis states T^i s (i < 128) of that step's xoroshiro stream folded into 4-bit lookup groups:
+// nib[step][g][v] = XOR_{b in v} T^(4g+b) s, g < 32, v < 16.
+struct rng_window {
+	u128 const* nib; // [nsteps][32][16]
+};
+
+struct update_args {
+	void* stream;           // cudaStream_t
+	void const* functor;    // device copy of the Neur object
+	std::uint32_t* state;   // word-SoA: word w of local neuron i at state[w * stride + i]
+	std::int64_t n_local;   // neurons owned by this rank
+	std::int64_t lo;        // global index of local neuron 0
+	std::int64_t stride;
+	std::int64_t t0;        // first step of the window (snn::_time)
+	std::int32_t nsteps;
+	float dt[kMaxWindow];   // kahan-compensated dt of each step (snn.cpp:8)
+	// spike ring: ids[(step % ring) * cap + seg_base + j], cnt[(step % ring) * world + rank]
+	std::int32_t* ring_ids[kMaxWorld]; // this rank's copy first ([rank]); peers' copies for direct stores
+	std::uint32_t* ring_cnt;           // local counters only; published to peers after the window
+	std::int64_t ring_cap;             // = global population size
+	std::int32_t ring;
+	std::int32_t rank, world;
+	// plasticity: 64-bit spike history per local neuron (neuron_population.h:126-132) or null
+	std::uint64_t* history;
+	// incoming connections, in connect() order
+	std::int32_t n_in;
+	incoming in[kMaxIncoming];
+	// random access into the step streams
+	rng_window rng;
+	u128 const* jump_poly;  // per chunk of kRngChunk local neurons: x^(offset of chunk start) mod charpoly
+};
+
+struct export_args {
+	void* stream;
+	std::uint32_t const* state;
+	std::int64_t n_local, stride;
+	std::int64_t t_next; // the step whose pending deliveries must be folded in (= snn::_time)
+	std::int32_t n_in;
+	incoming in[kMaxIncoming];
+	void* out_aos; // device buffer, n_local * sizeof(neuron)
+};
+
+struct import_args {
+	void* stream;
+	std::uint32_t* state;
+	std::int64_t n_local, stride;
+	void const* in_aos;
+};
+}
+
+// ---- the two ops tables behind the opaque pointers of include/spice_b200.h ---------------------
+extern "C" {
+struct spice_neuron_ops {
+	std::uint32_t abi_version;
+	char const* name;
+	std::uint32_t neuron_bytes;  // sizeof(Neur::neuron); 0 for stateless neurons
+	std::uint32_t functor_bytes; // sizeof(Neur)
+	std::uint32_t rng_draws;     // engine draws one update() consumes (compile-time constant)
+	std::uint32_t burns_seed;    // stateful adapters consume one seed++ (neuron_population.h:60)
+	// host: fill `out` (n * neuron_bytes) with default-constructed neurons and run the model's
+	// init hook, if any, with an engine seeded by (seed_lo, seed_hi) (neuron_population.h:60-67)
+	void (*init_host)(void const* functor, void* out, std::int64_t n, std::uint64_t seed_lo, std::uint64_t seed_hi);
+	int (*launch_update)(spice::detail::update_args const*);
+	int (*launch_export)(spice::detail::export_args const*);
+	int (*launch_import)(spice::detail::import_args const*);
+};
+
+struct spice_synapse_ops {
+	std::uint32_t abi_version;
+	char const* name;
+	std::uint32_t synapse_bytes; // sizeof(Syn::synapse); 0 for stateless synapses
+	std::uint32_t functor_bytes; // sizeof(Syn)
+	std::uint32_t dst_neuron_bytes;
+	std::uint32_t plastic;         // has update()/skip()
+	std::uint32_t deliver_from_to; // deliver takes the source neuron (unsupported on this path yet)
+	// device function pointer of apply<Syn, DstNeur>, fetched from the module that holds the kernels
+	int (*get_apply)(spice::detail::apply_fn* out);
+};
+}

@@ -1,0 +1,345 @@
+// Kernel templates instantiated per user model, and the type-erased tables (spice_neuron_ops /
+// spice_synapse_ops) that hand them to the model-agnostic runtime.
+//
+// What runs here is the reference's per-neuron loop, neuron_population<Neur>::update
+// (spice/include/spice/detail/neuron_population.h:116-134) with its adapters (:40-45, :72-77),
+// re-designed for the GPU:
+//   * neuron state is word-SoA (word w of neuron i at state[w*stride + i]) so every load/store
+//     of a warp is one coalesced 128-byte line;
+//   * one launch advances a whole WINDOW of steps (<= the minimum synaptic delay): inside a
+//     window a neuron depends only on its own state and on event counters written before the
+//     window began, so a thread keeps its neuron in registers across all steps;
+//   * incoming synaptic events arrive as per-(slot, connection, target) integer counters; the
+//     owner thread applies Syn::deliver that many times, connection by connection in connect()
+//     order — the same sequence of float operations the reference performs
+//     (synapse_population.h:118-133 under snn.cpp:21-25), hence bit-exact;
+//   * spikes are compacted with warp ballots into the step's spike list (and stored straight
+//     into every peer GPU's copy of the list over NVLink when world > 1);
+//   * the step's single xoroshiro stream (snn.cpp:12-15) is entered at arbitrary offsets through
+//     GF(2) jump polynomials (spice/util/random.h), 32 consecutive neurons per jump.
+//
+// Everything in this header must be compiled into ONE device module together with the user's
+// functors (device function pointers are only valid inside the module that defines them).
+// Compile with -fmad=false so the functors' float expressions are evaluated as written.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <span>
+#include <type_traits>
+
+#include "spice/concepts.h"
+#include "spice/detail/abi.h"
+#include "spice/util/random.h"
+
+namespace spice::detail {
+
+// ---- small helpers ------------------------------------------------------------------------------
+template <class T>
+struct words_of {
+	static_assert(std::is_trivially_copyable_v<T>, "neuron / synapse state must be trivially copyable");
+	static_assert(sizeof(T) % 4 == 0, "neuron / synapse state must be a multiple of 4 bytes");
+	static constexpr int value = sizeof(T) / 4;
+};
+
+template <class T>
+__device__ __forceinline__ T load_soa(std::uint32_t const* base, std::int64_t stride, std::int64_t i) {
+	constexpr int W = words_of<T>::value;
+	std::uint32_t w[W];
+#pragma unroll
+	for (int k = 0; k < W; k++)
+		w[k] = base[k * stride + i];
+	T out;
+	memcpy(&out, w, sizeof(T));
+	return out;
+}
+
+template <class T>
+__device__ __forceinline__ void store_soa(std::uint32_t* base, std::int64_t stride, std::int64_t i, T const& v) {
+	constexpr int W = words_of<T>::value;
+	std::uint32_t w[W];
+	memcpy(w, &v, sizeof(T));
+#pragma unroll
+	for (int k = 0; k < W; k++)
+		base[k * stride + i] = w[k];
+}
+
+// engine handed to models that declare no draws: using it is a compile-time error
+struct null_rng {
+	using result_type = UInt;
+	template <class T = void>
+	__host__ __device__ UInt operator()() {
+		static_assert(!std::is_void_v<T>,
+		              "this neuron draws from the rng: declare `static constexpr int rng_draws = <draws per update()>;`");
+		return 0;
+	}
+};
+
+// engine that counts its draws so a model that uses fewer than it declared stays in step
+struct counting_rng {
+	using result_type = UInt;
+	util::xoroshiro64_128p g;
+	int used = 0;
+	__device__ __forceinline__ UInt operator()() {
+		used++;
+		return g();
+	}
+};
+
+// ---- apply: k deliveries of a stateless synapse to one neuron ------------------------------------
+template <class Syn, class DstNeur>
+__device__ void apply_impl(void const* functor, void* neuron, unsigned k) {
+	Syn const& syn = *static_cast<Syn const*>(functor);
+	auto& n        = *static_cast<typename DstNeur::neuron*>(neuron);
+	if constexpr (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+		for (unsigned j = 0; j < k; j++)
+			syn.deliver(n);
+	}
+}
+template <class Syn, class DstNeur>
+__device__ apply_fn apply_ptr = apply_impl<Syn, DstNeur>;
+
+// ---- stateful neurons: one thread per neuron, whole window --------------------------------------
+template <class Neur>
+__global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
+	using N                  = typename Neur::neuron;
+	std::int64_t const i     = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	bool const active        = i < a.n_local;
+	std::int64_t const ii    = active ? i : 0;
+	unsigned const lane_lt   = (1u << (threadIdx.x & 31)) - 1;
+	Neur const neur          = *static_cast<Neur const*>(a.functor);
+	N n                      = load_soa<N>(a.state, a.stride, ii);
+	std::uint64_t hist       = (a.history && active) ? a.history[ii] : 0;
+	std::int32_t const my_id = static_cast<std::int32_t>(a.lo + i);
+	null_rng rng;
+
+	for (int s = 0; s < a.nsteps; s++) {
+		std::int64_t const t = a.t0 + s;
+		// fold in the events whose delivery the reference ran at the end of step t-1
+		for (int c = 0; c < a.n_in; c++) {
+			incoming const& in   = a.in[c];
+			std::int64_t const o = (t % in.ring) * a.n_local + ii;
+			unsigned const k     = active ? in.counts[o] : 0;
+			if (k) {
+				in.counts[o] = 0;
+				in.apply(in.functor, &n, k);
+			}
+		}
+		bool const spiked = active && neur.update(n, a.dt[s], rng);
+		hist              = (hist << 1) | (spiked ? 1u : 0u);
+
+		unsigned const m = __ballot_sync(0xffffffffu, spiked);
+		if (m) {
+			std::int64_t const slot = t % a.ring;
+			unsigned base           = 0;
+			if ((threadIdx.x & 31) == 0)
+				base = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], __popc(m));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (spiked) {
+				std::int64_t const at = slot * a.ring_cap + a.lo + base + __popc(m & lane_lt);
+				for (int r = 0; r < a.world; r++)
+					a.ring_ids[r][at] = my_id;
+			}
+		}
+	}
+	if (active) {
+		store_soa<N>(a.state, a.stride, i, n);
+		if (a.history)
+			a.history[i] = hist;
+	}
+}
+
+// ---- stateless neurons: one thread per (step, 32 consecutive neurons) ----------------------------
+template <class Neur>
+__global__ void __launch_bounds__(256) update_stateless_kernel(update_args a) {
+	constexpr int draws        = rng_draws_v<Neur>;
+	std::int64_t const chunks  = (a.n_local + kRngChunk - 1) / kRngChunk;
+	std::int64_t const item    = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (item >= chunks * a.nsteps)
+		return;
+	int const s              = static_cast<int>(item / chunks);
+	std::int64_t const chunk = item % chunks;
+	std::int64_t const t     = a.t0 + s;
+	Neur const neur          = *static_cast<Neur const*>(a.functor);
+	float const dt           = a.dt[s];
+
+	counting_rng rng;
+	if constexpr (draws > 0) {
+		// state at this chunk's offset in step t's stream: XOR of the basis states selected by
+		// the chunk's jump polynomial, 4 coefficients per lookup
+		u128 const poly = a.jump_poly[chunk];
+		u128 const* nib = a.rng.nib + static_cast<std::int64_t>(s) * 32 * 16;
+		UInt s0 = 0, s1 = 0;
+#pragma unroll 8
+		for (int g = 0; g < 32; g++) {
+			unsigned const v = static_cast<unsigned>(((g < 16 ? poly.lo : poly.hi) >> (4 * (g & 15))) & 15);
+			ulonglong2 const e = __ldg(reinterpret_cast<ulonglong2 const*>(nib + g * 16 + v));
+			s0 ^= e.x;
+			s1 ^= e.y;
+		}
+		rng.g = util::xoroshiro64_128p(s0, s1);
+	}
+
+	std::int64_t const first = chunk * kRngChunk;
+	std::int64_t const slot  = t % a.ring;
+	for (int q = 0; q < kRngChunk; q++) {
+		std::int64_t const i = first + q;
+		if (i >= a.n_local)
+			break;
+		rng.used = 0;
+		bool spiked;
+		if constexpr (draws > 0)
+			spiked = neur.update(dt, rng);
+		else {
+			null_rng none;
+			spiked = neur.update(dt, none);
+		}
+		if constexpr (draws > 0)
+			for (; rng.used < draws; rng.used++)
+				rng.g.advance();
+		if (spiked) {
+			unsigned const pos    = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], 1u);
+			std::int64_t const at = slot * a.ring_cap + a.lo + pos;
+			for (int r = 0; r < a.world; r++)
+				a.ring_ids[r][at] = static_cast<std::int32_t>(a.lo + i);
+		}
+	}
+}
+
+// ---- state export / import (neuron_population::get_neurons, neuron_population.h:142-145) ---------
+// Export folds the pending events of step t_next into a COPY of the state: the reference applies
+// them at the end of the step that was just run, this backend at the start of the next one.
+template <class Neur>
+__global__ void __launch_bounds__(256) export_kernel(export_args a) {
+	using N              = typename Neur::neuron;
+	std::int64_t const i = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= a.n_local)
+		return;
+	N n = load_soa<N>(a.state, a.stride, i);
+	for (int c = 0; c < a.n_in; c++) {
+		incoming const& in = a.in[c];
+		unsigned const k   = in.counts[(a.t_next % in.ring) * a.n_local + i];
+		if (k)
+			in.apply(in.functor, &n, k);
+	}
+	static_cast<N*>(a.out_aos)[i] = n;
+}
+
+template <class Neur>
+__global__ void __launch_bounds__(256) import_kernel(import_args a) {
+	using N              = typename Neur::neuron;
+	std::int64_t const i = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= a.n_local)
+		return;
+	store_soa<N>(a.state, a.stride, i, static_cast<N const*>(a.in_aos)[i]);
+}
+
+inline int grid_for(std::int64_t threads, int block = 256) {
+	return static_cast<int>((threads + block - 1) / block);
+}
+
+// ---- ops tables ----------------------------------------------------------------------------------
+template <Neuron Neur>
+struct neuron_ops_builder {
+	static void init_host(void const* functor, void* out, std::int64_t n, std::uint64_t seed_lo, std::uint64_t seed_hi) {
+		if constexpr (StatefulNeuron<Neur>) {
+			using N = typename Neur::neuron;
+			N* v    = static_cast<N*>(out);
+			for (std::int64_t i = 0; i < n; i++)
+				new (v + i) N();
+			Neur neur = *static_cast<Neur const*>(functor);
+			util::xoroshiro64_128p rng(seed_lo, seed_hi);
+			if constexpr (PerNeuronInit<Neur>) {
+				for (std::int64_t i = 0; i < n; i++)
+					neur.init(v[i], i, rng);
+			} else if constexpr (PerPopulationInit<Neur>) {
+				neur.init(std::span<N>(v, static_cast<std::size_t>(n)), rng);
+			}
+		}
+		(void)functor, (void)out, (void)n, (void)seed_lo, (void)seed_hi;
+	}
+
+	static int launch_update(update_args const* a) {
+		auto stream = static_cast<cudaStream_t>(a->stream);
+		if constexpr (StatefulNeuron<Neur>) {
+			static_assert(rng_draws_v<Neur> == 0, "stateful neurons that draw from the rng are not supported yet");
+			if (a->n_local > 0)
+				update_stateful_kernel<Neur><<<grid_for(a->n_local), 256, 0, stream>>>(*a);
+		} else {
+			std::int64_t const items = ((a->n_local + kRngChunk - 1) / kRngChunk) * a->nsteps;
+			if (items > 0)
+				update_stateless_kernel<Neur><<<grid_for(items), 256, 0, stream>>>(*a);
+		}
+		return static_cast<int>(cudaGetLastError());
+	}
+
+	static int launch_export(export_args const* a) {
+		if constexpr (StatefulNeuron<Neur>) {
+			if (a->n_local > 0)
+				export_kernel<Neur><<<grid_for(a->n_local), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(*a);
+		}
+		return static_cast<int>(cudaGetLastError());
+	}
+
+	static int launch_import(import_args const* a) {
+		if constexpr (StatefulNeuron<Neur>) {
+			if (a->n_local > 0)
+				import_kernel<Neur><<<grid_for(a->n_local), 256, 0, static_cast<cudaStream_t>(a->stream)>>>(*a);
+		}
+		return static_cast<int>(cudaGetLastError());
+	}
+
+	static constexpr std::uint32_t neuron_bytes() {
+		if constexpr (StatefulNeuron<Neur>)
+			return sizeof(typename Neur::neuron);
+		else
+			return 0;
+	}
+};
+
+template <Neuron Neur>
+spice_neuron_ops const* neuron_ops(char const* name = "user") {
+	static_assert(!PerPopulationUpdate<Neur>, "per-population update() neurons are host-fed; not on the GPU path yet");
+	static_assert(std::is_trivially_copyable_v<Neur>, "neuron functors are copied to the device byte-wise");
+	using B = neuron_ops_builder<Neur>;
+	static spice_neuron_ops const ops{1,
+	                                  name,
+	                                  B::neuron_bytes(),
+	                                  static_cast<std::uint32_t>(sizeof(Neur)),
+	                                  static_cast<std::uint32_t>(rng_draws_v<Neur>),
+	                                  StatefulNeuron<Neur> ? 1u : 0u,
+	                                  &B::init_host,
+	                                  &B::launch_update,
+	                                  &B::launch_export,
+	                                  &B::launch_import};
+	return &ops;
+}
+
+template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
+requires Synapse<Syn, SrcNeur, DstNeur>
+spice_synapse_ops const* synapse_ops(char const* name = "user") {
+	static_assert(std::is_trivially_copyable_v<Syn>, "synapse functors are copied to the device byte-wise");
+	struct B {
+		static int get_apply(apply_fn* out) {
+			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_ptr<Syn, DstNeur>, sizeof(apply_fn)));
+		}
+	};
+	constexpr std::uint32_t syn_bytes = [] {
+		if constexpr (StatefulSynapse<Syn>)
+			return static_cast<std::uint32_t>(sizeof(typename Syn::synapse));
+		else
+			return 0u;
+	}();
+	static spice_synapse_ops const ops{1,
+	                                   name,
+	                                   syn_bytes,
+	                                   static_cast<std::uint32_t>(sizeof(Syn)),
+	                                   static_cast<std::uint32_t>(sizeof(typename DstNeur::neuron)),
+	                                   PlasticSynapse<Syn> ? 1u : 0u,
+	                                   DeliverTo<Syn, DstNeur> ? 0u : 1u,
+	                                   &B::get_apply};
+	return &ops;
+}
+}

@@ -1,0 +1,1277 @@
+// Model-agnostic runtime of the B200 backend and the C ABI (include/spice_b200.h).
+//
+// It stands where the reference has `class snn` + the type-erased NeuronPopulation /
+// SynapsePopulation interfaces (spice/include/spice/snn.h:16-75, spice/src/snn.cpp:7-28,
+// spice/include/spice/detail/{neuron_population,synapse_population}.h): it owns the populations,
+// the connections and the seed bookkeeping, and sequences update -> (exchange) -> delivery.
+// Unlike the reference it does so per WINDOW of up to min-delay steps: a spike emitted inside a
+// window cannot be consumed inside it (snn.cpp:21-25: emitted at t, first visible at t+delay),
+// so one launch per population updates all steps of the window and one launch per connection
+// delivers all of the window's spikes into future per-step event counters.
+//
+// The kernels that touch user functors are instantiated elsewhere (spice/detail/model_ops.cuh)
+// and reach this file through the ops tables; the kernels here are functor-free: spike
+// delivery into integer counters, window prologue (per-step RNG jump tables), peer publication /
+// wait for the multi-GPU spike exchange over NVLink, raster packing.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "generator.h"
+#include "spice/detail/abi.h"
+#include "spice/util/numeric.h"
+#include "spice/util/random.h"
+#include "spice_b200.h"
+
+using namespace spice;
+using namespace spice::detail;
+
+namespace {
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// Window prologue: (1) zero this rank's spike counters for the window's steps, (2) for every step
+// build the 4-bit jump tables of that step's xoroshiro stream:
+// nib[s][g][v] = XOR_{b in v} T^(4g+b) seed_s.  One block per step.
+struct prologue_args {
+	u128 seed[kMaxWindow]; // seed of each step's stream (snn.cpp:12: rng(_seed++))
+	u128* nib;             // [nsteps][32][16] or null when no population draws
+	std::uint32_t* const* ring_cnt; // device array: per population, counters [ring][world]
+	int npops;
+	int ring, world, rank;
+	long long t0;
+	int nsteps;
+};
+
+__global__ void __launch_bounds__(512) window_prologue(prologue_args a) {
+	int const s = blockIdx.x;
+	for (int p = threadIdx.x; p < a.npops; p += blockDim.x)
+		a.ring_cnt[p][((a.t0 + s) % a.ring) * a.world + a.rank] = 0;
+	if (!a.nib)
+		return;
+	__shared__ ulonglong2 basis[128];
+	if (threadIdx.x == 0) {
+		unsigned long long s0 = a.seed[s].lo, s1 = a.seed[s].hi;
+		for (int i = 0; i < 128; i++) {
+			basis[i]                   = make_ulonglong2(s0, s1);
+			unsigned long long const t = s0 ^ s1;
+			s0                         = ((s0 << 24) | (s0 >> 40)) ^ t ^ (t << 16);
+			s1                         = (t << 37) | (t >> 27);
+		}
+	}
+	__syncthreads();
+	int const g = threadIdx.x >> 4, v = threadIdx.x & 15;
+	unsigned long long x = 0, y = 0;
+	for (int b = 0; b < 4; b++)
+		if (v & (1 << b)) {
+			x ^= basis[4 * g + b].x;
+			y ^= basis[4 * g + b].y;
+		}
+	a.nib[(static_cast<long long>(s) * 32 + g) * 16 + v] = u128{x, y};
+}
+
+// Spike delivery for connections whose events are integer counts (all stateless synapses):
+// the reference's hot loop B (synapse_population.h:88,99,118-133) — for src in spikes, for dst
+// in row(src): deliver — with `deliver` deferred: one warp per spiking source streams that
+// source's CSR row and bumps counts[slot(step + delay)][dst].
+struct deliver_args {
+	std::int32_t const* ring_ids;  // source population spike ring (this rank's copy)
+	std::uint32_t const* ring_cnt; // [ring][world]
+	long long ring_cap;
+	int ring, world;
+	long long seg_lo[kMaxWorld]; // first neuron of each rank's range in the source population
+	long long const* offsets;    // CSR (rows = all sources, local columns)
+	std::int32_t const* neighbors;
+	std::uint32_t* counts;       // [cring][n_dst_local]
+	long long n_dst_local;
+	int cring;
+	long long delay;
+	long long t0;
+	int nsteps;
+	unsigned long long* stats; // [0] events, [1] spikes
+};
+
+__global__ void __launch_bounds__(256) deliver_counts(deliver_args a) {
+	__shared__ unsigned prefix[kMaxWindow * kMaxWorld + 1];
+	int const nseg = a.nsteps * a.world;
+	if (threadIdx.x == 0) {
+		unsigned run = 0;
+		for (int i = 0; i < nseg; i++) {
+			prefix[i]   = run;
+			int const s = i / a.world, r = i % a.world;
+			run += a.ring_cnt[((a.t0 + s) % a.ring) * a.world + r];
+		}
+		prefix[nseg] = run;
+	}
+	__syncthreads();
+	unsigned const total = prefix[nseg];
+	int const lane       = threadIdx.x & 31;
+	unsigned const warps = gridDim.x * (blockDim.x >> 5);
+	unsigned long long ev = 0, sp = 0;
+	for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < total; item += warps) {
+		// which (step, rank) segment does this spike belong to
+		int lo = 0, hi = nseg - 1;
+		while (lo < hi) {
+			int const mid = (lo + hi + 1) >> 1;
+			if (prefix[mid] <= item)
+				lo = mid;
+			else
+				hi = mid - 1;
+		}
+		int const s = lo / a.world, r = lo % a.world;
+		long long const t   = a.t0 + s;
+		std::int32_t const src = a.ring_ids[(t % a.ring) * a.ring_cap + a.seg_lo[r] + (item - prefix[lo])];
+		long long const beg = a.offsets[src], end = a.offsets[src + 1];
+		std::uint32_t* cnt  = a.counts + ((t + a.delay) % a.cring) * a.n_dst_local;
+		long long e = beg + lane;
+		for (; e + 96 < end; e += 128) {
+			std::int32_t const d0 = a.neighbors[e], d1 = a.neighbors[e + 32], d2 = a.neighbors[e + 64],
+			                   d3 = a.neighbors[e + 96];
+			atomicAdd(cnt + d0, 1u);
+			atomicAdd(cnt + d1, 1u);
+			atomicAdd(cnt + d2, 1u);
+			atomicAdd(cnt + d3, 1u);
+		}
+		for (; e < end; e += 32)
+			atomicAdd(cnt + a.neighbors[e], 1u);
+		ev += static_cast<unsigned long long>(end - beg);
+		sp++;
+	}
+	if (lane == 0 && sp) {
+		atomicAdd(a.stats + 0, ev);
+		atomicAdd(a.stats + 1, sp);
+	}
+}
+
+// Multi-GPU: after this rank's update kernels of window `seq` finished, copy its spike counters
+// into every peer's counter table and raise this rank's flag there.  The spike ids themselves
+// were stored into the peers' rings by the update kernels (NVLink peer stores).
+struct publish_args {
+	std::uint32_t* const* local_cnt;               // [npops] this rank's tables
+	std::uint32_t* const* peer_cnt;                // [world][npops] device array of peers' tables
+	unsigned long long* peer_flags[kMaxWorld];     // peers' flag arrays [world]
+	int npops, ring, world, rank;
+	long long t0;
+	int nsteps;
+	unsigned long long seq;
+};
+
+__global__ void __launch_bounds__(256) publish_window(publish_args a) {
+	int const n = a.npops * a.nsteps * a.world;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		int const q = i % a.world, s = (i / a.world) % a.nsteps, p = i / (a.world * a.nsteps);
+		if (q == a.rank)
+			continue;
+		long long const at       = ((a.t0 + s) % a.ring) * a.world + a.rank;
+		a.peer_cnt[q * a.npops + p][at] = a.local_cnt[p][at];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x < a.world) {
+		volatile unsigned long long* f = a.peer_flags[threadIdx.x] + a.rank;
+		*f                             = a.seq;
+	}
+}
+
+struct wait_args {
+	unsigned long long const* flags; // this rank's flag array [world]
+	int world;
+	unsigned long long seq;
+	int* error;
+};
+
+__global__ void wait_window(wait_args a) {
+	if (static_cast<int>(threadIdx.x) >= a.world)
+		return;
+	volatile unsigned long long const* f = a.flags + threadIdx.x;
+	long long const start                = clock64();
+	while (*f < a.seq) {
+		if (clock64() - start > 20000000000ll) { // ~10 s: a peer died; do not hang the GPU
+			atomicOr(a.error, 1);
+			break;
+		}
+		__nanosleep(200);
+	}
+	__threadfence_system();
+}
+
+// Raster log: append the window's spike lists to a device log (one block per (step, population)).
+struct raster_args {
+	std::int32_t const* const* ring_ids; // [npops]
+	std::uint32_t const* const* ring_cnt;
+	long long const* ring_cap;           // [npops]
+	long long const* seg_lo;             // [npops][world]
+	int npops, ring, world;
+	long long t0;
+	int nsteps;
+	long long step_index0;               // index of the window's first step in the log
+	unsigned long long* cursor;          // ids appended so far
+	std::int32_t* log_ids;
+	long long log_cap;
+	long long* log_off;                  // [steps][npops] offset of the list in log_ids
+	std::int32_t* log_cnt;               // [steps][npops][world]
+	long long log_steps_cap;
+	int* error;
+};
+
+__global__ void __launch_bounds__(256) raster_pack(raster_args a) {
+	int const s = blockIdx.x / a.npops, p = blockIdx.x % a.npops;
+	long long const si = a.step_index0 + s;
+	if (si >= a.log_steps_cap) {
+		if (threadIdx.x == 0)
+			atomicOr(a.error, 4);
+		return;
+	}
+	__shared__ unsigned long long base_s;
+	__shared__ unsigned total_s;
+	long long const slot = (a.t0 + s) % a.ring;
+	if (threadIdx.x == 0) {
+		unsigned total = 0;
+		for (int r = 0; r < a.world; r++) {
+			unsigned const c = a.ring_cnt[p][slot * a.world + r];
+			a.log_cnt[(si * a.npops + p) * a.world + r] = static_cast<std::int32_t>(c);
+			total += c;
+		}
+		base_s  = atomicAdd(a.cursor, static_cast<unsigned long long>(total));
+		total_s = total;
+		a.log_off[si * a.npops + p] = static_cast<long long>(base_s);
+	}
+	__syncthreads();
+	unsigned long long const base = base_s;
+	if (base + total_s > static_cast<unsigned long long>(a.log_cap)) {
+		if (threadIdx.x == 0)
+			atomicOr(a.error, 8);
+		return;
+	}
+	unsigned done = 0;
+	for (int r = 0; r < a.world; r++) {
+		unsigned const c          = a.ring_cnt[p][slot * a.world + r];
+		std::int32_t const* from = a.ring_ids[p] + slot * a.ring_cap[p] + a.seg_lo[p * a.world + r];
+		for (unsigned j = threadIdx.x; j < c; j += blockDim.x)
+			a.log_ids[base + done + j] = from[j];
+		done += c;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host state
+// ---------------------------------------------------------------------------------------------
+struct population {
+	spice_neuron_ops const* ops = nullptr;
+	long long size = 0, lo = 0, hi = 0, stride = 0;
+	std::vector<unsigned char> functor_host;
+	void* functor_dev       = nullptr;
+	std::uint32_t* state    = nullptr;
+	std::uint64_t* history  = nullptr;
+	long long rng_offset    = 0; // draws consumed per step by the populations added before this one
+	u128* jump_poly         = nullptr;
+	// exchange region views
+	long long ring_ids_off = 0, ring_cnt_off = 0; // byte offsets in the exchange region
+	std::vector<int> incoming;                     // connection indices, connect() order
+	std::vector<long long> seg_lo;                 // [world]
+};
+
+struct connection {
+	spice_synapse_ops const* ops = nullptr;
+	int src = 0, dst = 0;
+	long long delay = 0;
+	std::vector<unsigned char> functor_host;
+	void* functor_dev         = nullptr;
+	long long* offsets        = nullptr;
+	std::int32_t* neighbors   = nullptr;
+	long long edges           = 0;
+	std::uint32_t* counts     = nullptr; // [cring][n_dst_local]
+	apply_fn apply            = nullptr;
+};
+
+struct host_spikes {
+	std::vector<std::int32_t> ids;
+	long long step = -1;
+};
+}
+
+struct spice_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream     = false;
+	float dt            = 0;
+	long long max_delay = 1;
+	util::seed_seq seed{UInt128{0, 0}};
+	util::kahan_sum<float> simtime;
+	long long time = 0;
+	int rank = 0, world = 1, mode = 0;
+	std::vector<population> pops;
+	std::vector<connection> conns;
+	std::string error;
+	bool finalized = false;
+
+	// geometry
+	int window = 1, ring = 1, cring = 1;
+	bool any_rng = false;
+
+	// exchange region (spike rings, counters, flags)
+	unsigned char* xbase = nullptr;
+	size_t xbytes        = 0;
+	size_t flags_off     = 0;
+	unsigned char* peer_base[kMaxWorld] = {};
+	bool peers_set       = false;
+	unsigned long long seq = 0;
+
+	// device tables
+	std::uint32_t** d_ring_cnt        = nullptr; // [npops]
+	std::uint32_t** d_peer_cnt        = nullptr; // [world][npops]
+	std::int32_t** d_ring_ids         = nullptr; // [npops]
+	long long* d_ring_cap             = nullptr;
+	long long* d_seg_lo               = nullptr; // [npops][world]
+	u128* d_nib                       = nullptr;
+	unsigned long long* d_stats       = nullptr; // events, spikes
+	int* d_error                      = nullptr;
+	long long launches                = 0;
+
+	// raster
+	bool raster_on = false;
+	long long raster_steps = 0;
+	unsigned long long* d_cursor = nullptr;
+	std::int32_t* d_log_ids      = nullptr;
+	long long log_cap            = 0;
+	long long* d_log_off         = nullptr;
+	std::int32_t* d_log_cnt      = nullptr;
+	long long log_steps_cap      = 0;
+
+	// readout scratch
+	std::vector<std::vector<host_spikes>> spike_cache; // [pop][age]
+};
+
+namespace {
+#define CHECK_CUDA(ctx, expr)                                                       \
+	do {                                                                            \
+		cudaError_t e_ = (expr);                                                    \
+		if (e_ != cudaSuccess) {                                                    \
+			(ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(e_);     \
+			return SPICE_ERR_CUDA;                                                  \
+		}                                                                           \
+	} while (0)
+
+#define PRE(ctx, cond)                                                                                       \
+	do {                                                                                                     \
+		if (!(cond)) {                                                                                       \
+			(ctx)->error = std::string("Assertion failed (") + __FILE__ + ":" + std::to_string(__LINE__) + \
+			               "): " #cond;                                                                      \
+			return SPICE_ERR_PRECONDITION;                                                                   \
+		}                                                                                                    \
+	} while (0)
+
+int fail(spice_ctx* ctx, int code, std::string msg) {
+	ctx->error = std::move(msg);
+	return code;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class T>
+T* xptr(unsigned char* base, long long off) {
+	return reinterpret_cast<T*>(base + off);
+}
+
+struct peer_blob {
+	unsigned long long magic;
+	int pid;
+	int device;
+	int rank;
+	int pad;
+	unsigned long long bytes;
+	unsigned long long raw_ptr;
+	cudaIpcMemHandle_t handle;
+};
+
+int finalize(spice_ctx* ctx) {
+	if (ctx->finalized)
+		return SPICE_OK;
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	// window = min delay over connections (any partition of the steps into windows no longer than
+	// the shortest delay is valid), bounded by kMaxWindow
+	long long dmin = kMaxWindow, dmax = 1;
+	for (auto const& c : ctx->conns) {
+		dmin = std::min(dmin, c.delay);
+		dmax = std::max(dmax, c.delay);
+	}
+	ctx->window = static_cast<int>(std::max<long long>(1, std::min<long long>(dmin, kMaxWindow)));
+	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay, 2ll * ctx->window));
+	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
+
+	int const np = static_cast<int>(ctx->pops.size());
+	// exchange region layout (identical on every rank)
+	size_t off = 0;
+	for (auto& p : ctx->pops) {
+		p.ring_ids_off = static_cast<long long>(off);
+		off            = align_up(off + sizeof(std::int32_t) * static_cast<size_t>(ctx->ring) * static_cast<size_t>(std::max<long long>(p.size, 1)), 256);
+		p.ring_cnt_off = static_cast<long long>(off);
+		off            = align_up(off + sizeof(std::uint32_t) * static_cast<size_t>(ctx->ring) * ctx->world, 256);
+	}
+	ctx->flags_off = off;
+	off            = align_up(off + sizeof(unsigned long long) * kMaxWorld, 256);
+	ctx->xbytes    = off;
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->xbase, ctx->xbytes));
+	CHECK_CUDA(ctx, cudaMemset(ctx->xbase, 0, ctx->xbytes));
+	ctx->peer_base[ctx->rank] = ctx->xbase;
+
+	// connections: counters + incoming lists
+	for (size_t ci = 0; ci < ctx->conns.size(); ci++) {
+		auto& c           = ctx->conns[ci];
+		auto const& dst   = ctx->pops[c.dst];
+		long long const n = std::max<long long>(dst.hi - dst.lo, 1);
+		CHECK_CUDA(ctx, cudaMalloc(&c.counts, sizeof(std::uint32_t) * static_cast<size_t>(ctx->cring) * static_cast<size_t>(n)));
+		CHECK_CUDA(ctx, cudaMemset(c.counts, 0, sizeof(std::uint32_t) * static_cast<size_t>(ctx->cring) * static_cast<size_t>(n)));
+		ctx->pops[c.dst].incoming.push_back(static_cast<int>(ci));
+	}
+	for (auto const& p : ctx->pops)
+		if (p.incoming.size() > static_cast<size_t>(kMaxIncoming))
+			return fail(ctx, SPICE_ERR_UNSUPPORTED, "more than 8 connections into one population");
+
+	// per-population tables
+	std::vector<std::uint32_t*> h_cnt(np);
+	std::vector<std::int32_t*> h_ids(np);
+	std::vector<long long> h_cap(np), h_seg(static_cast<size_t>(np) * ctx->world);
+	long long rng_offset = 0;
+	for (int pi = 0; pi < np; pi++) {
+		auto& p   = ctx->pops[pi];
+		h_cnt[pi] = xptr<std::uint32_t>(ctx->xbase, p.ring_cnt_off);
+		h_ids[pi] = xptr<std::int32_t>(ctx->xbase, p.ring_ids_off);
+		h_cap[pi] = std::max<long long>(p.size, 1);
+		p.seg_lo.resize(ctx->world);
+		for (int r = 0; r < ctx->world; r++) {
+			p.seg_lo[r]                    = p.size * r / ctx->world;
+			h_seg[pi * ctx->world + r]     = p.seg_lo[r];
+		}
+		p.rng_offset = rng_offset;
+		rng_offset += p.size * p.ops->rng_draws;
+		if (p.ops->rng_draws > 0) {
+			ctx->any_rng = true;
+			// jump polynomial of every chunk of kRngChunk local neurons: x^(offset of its first draw)
+			long long const nl     = p.hi - p.lo;
+			long long const chunks = (nl + kRngChunk - 1) / kRngChunk;
+			std::vector<u128> polys(static_cast<size_t>(std::max<long long>(chunks, 1)));
+			util::jump::poly cur        = util::jump::xpow(static_cast<UInt>(p.rng_offset + p.lo * p.ops->rng_draws));
+			util::jump::poly const step = util::jump::xpow(static_cast<UInt>(kRngChunk) * p.ops->rng_draws);
+			for (long long c = 0; c < chunks; c++) {
+				polys[c] = u128{cur.lo, cur.hi};
+				cur      = util::jump::mulmod(cur, step);
+			}
+			CHECK_CUDA(ctx, cudaMalloc(&p.jump_poly, sizeof(u128) * polys.size()));
+			CHECK_CUDA(ctx, cudaMemcpy(p.jump_poly, polys.data(), sizeof(u128) * polys.size(), cudaMemcpyHostToDevice));
+		}
+	}
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_cnt, sizeof(void*) * std::max(np, 1)));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_ids, sizeof(void*) * std::max(np, 1)));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_cap, sizeof(long long) * std::max(np, 1)));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_seg_lo, sizeof(long long) * std::max<size_t>(h_seg.size(), 1)));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_peer_cnt, sizeof(void*) * std::max(np, 1) * ctx->world));
+	if (np) {
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_cnt, h_cnt.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_ids, h_ids.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_cap, h_cap.data(), sizeof(long long) * np, cudaMemcpyHostToDevice));
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_seg_lo, h_seg.data(), sizeof(long long) * h_seg.size(), cudaMemcpyHostToDevice));
+	}
+	if (ctx->any_rng)
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_nib, sizeof(u128) * kMaxWindow * 32 * 16));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_stats, sizeof(unsigned long long) * 2));
+	CHECK_CUDA(ctx, cudaMemset(ctx->d_stats, 0, sizeof(unsigned long long) * 2));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_error, sizeof(int)));
+	CHECK_CUDA(ctx, cudaMemset(ctx->d_error, 0, sizeof(int)));
+	ctx->spike_cache.assign(np, std::vector<host_spikes>(static_cast<size_t>(ctx->ring)));
+	ctx->finalized = true;
+	return SPICE_OK;
+}
+
+int upload_peer_tables(spice_ctx* ctx) {
+	int const np = static_cast<int>(ctx->pops.size());
+	std::vector<std::uint32_t*> h(static_cast<size_t>(std::max(np, 1)) * ctx->world);
+	for (int r = 0; r < ctx->world; r++)
+		for (int pi = 0; pi < np; pi++)
+			h[r * np + pi] = xptr<std::uint32_t>(ctx->peer_base[r], ctx->pops[pi].ring_cnt_off);
+	if (np)
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_peer_cnt, h.data(), sizeof(void*) * np * ctx->world, cudaMemcpyHostToDevice));
+	return SPICE_OK;
+}
+
+void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in) {
+	*n_in = static_cast<int>(p.incoming.size());
+	for (int k = 0; k < *n_in; k++) {
+		connection const& c = ctx->conns[p.incoming[k]];
+		in[k]               = incoming{c.counts, nullptr, c.apply, c.functor_dev, ctx->cring, 0};
+	}
+}
+
+int run_window(spice_ctx* ctx, int nsteps) {
+	int const np = static_cast<int>(ctx->pops.size());
+	// host-side per-step scalars: compensated dt (snn.cpp:8-10) and the step's stream seed (snn.cpp:12)
+	prologue_args pa{};
+	float dts[kMaxWindow];
+	for (int s = 0; s < nsteps; s++) {
+		dts[s] = ctx->simtime += ctx->dt;
+		if (ctx->simtime >= 1)
+			ctx->simtime.reset();
+		UInt128 const sd = (ctx->seed++).seed();
+		pa.seed[s]       = u128{sd.lo, sd.hi};
+	}
+	pa.nib      = ctx->any_rng ? ctx->d_nib : nullptr;
+	pa.ring_cnt = ctx->d_ring_cnt;
+	pa.npops    = np;
+	pa.ring     = ctx->ring;
+	pa.world    = ctx->world;
+	pa.rank     = ctx->rank;
+	pa.t0       = ctx->time;
+	pa.nsteps   = nsteps;
+	window_prologue<<<nsteps, 512, 0, ctx->stream>>>(pa);
+	ctx->launches++;
+
+	for (int pi = 0; pi < np; pi++) {
+		population& p = ctx->pops[pi];
+		update_args ua{};
+		ua.stream  = ctx->stream;
+		ua.functor = p.functor_dev;
+		ua.state   = p.state;
+		ua.n_local = p.hi - p.lo;
+		ua.lo      = p.lo;
+		ua.stride  = p.stride;
+		ua.t0      = ctx->time;
+		ua.nsteps  = nsteps;
+		std::memcpy(ua.dt, dts, sizeof(float) * nsteps);
+		for (int r = 0; r < ctx->world; r++)
+			ua.ring_ids[r] = xptr<std::int32_t>(ctx->peer_base[r], p.ring_ids_off);
+		ua.ring_cnt = xptr<std::uint32_t>(ctx->xbase, p.ring_cnt_off);
+		ua.ring_cap = std::max<long long>(p.size, 1);
+		ua.ring     = ctx->ring;
+		ua.rank     = ctx->rank;
+		ua.world    = ctx->world;
+		ua.history  = p.history;
+		fill_incoming(ctx, p, ua.in, &ua.n_in);
+		ua.rng.nib   = ctx->d_nib;
+		ua.jump_poly = p.jump_poly;
+		if (ua.n_local > 0) {
+			int const e = p.ops->launch_update(&ua);
+			if (e != 0)
+				return fail(ctx, SPICE_ERR_CUDA, std::string("update launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+			ctx->launches++;
+		}
+	}
+
+	if (ctx->world > 1) {
+		ctx->seq++;
+		publish_args pb{};
+		pb.local_cnt = ctx->d_ring_cnt;
+		pb.peer_cnt  = ctx->d_peer_cnt;
+		for (int r = 0; r < ctx->world; r++)
+			pb.peer_flags[r] = xptr<unsigned long long>(ctx->peer_base[r], static_cast<long long>(ctx->flags_off));
+		pb.npops  = np;
+		pb.ring   = ctx->ring;
+		pb.world  = ctx->world;
+		pb.rank   = ctx->rank;
+		pb.t0     = ctx->time;
+		pb.nsteps = nsteps;
+		pb.seq    = ctx->seq;
+		publish_window<<<1, 256, 0, ctx->stream>>>(pb);
+		wait_args wa{xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off)), ctx->world, ctx->seq, ctx->d_error};
+		wait_window<<<1, 32, 0, ctx->stream>>>(wa);
+		ctx->launches += 2;
+	}
+
+	for (auto& c : ctx->conns) {
+		population const& src = ctx->pops[c.src];
+		population const& dst = ctx->pops[c.dst];
+		if (dst.hi - dst.lo <= 0 || c.edges == 0)
+			continue;
+		deliver_args da{};
+		da.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
+		da.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
+		da.ring_cap = std::max<long long>(src.size, 1);
+		da.ring     = ctx->ring;
+		da.world    = ctx->world;
+		for (int r = 0; r < ctx->world; r++)
+			da.seg_lo[r] = src.seg_lo[r];
+		da.offsets     = c.offsets;
+		da.neighbors   = c.neighbors;
+		da.counts      = c.counts;
+		da.n_dst_local = dst.hi - dst.lo;
+		da.cring       = ctx->cring;
+		da.delay       = c.delay;
+		da.t0          = ctx->time;
+		da.nsteps      = nsteps;
+		da.stats       = ctx->d_stats;
+		// enough warps to cover the window's spikes at typical rates; the kernel strides
+		long long const est = std::max<long long>(1, src.size / 64) * nsteps;
+		int const blocks    = static_cast<int>(std::min<long long>(148 * 8, (est + 7) / 8));
+		deliver_counts<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(da);
+		ctx->launches++;
+	}
+
+	if (ctx->raster_on) {
+		raster_args ra{};
+		ra.ring_ids      = ctx->d_ring_ids;
+		ra.ring_cnt      = ctx->d_ring_cnt;
+		ra.ring_cap      = ctx->d_ring_cap;
+		ra.seg_lo        = ctx->d_seg_lo;
+		ra.npops         = np;
+		ra.ring          = ctx->ring;
+		ra.world         = ctx->world;
+		ra.t0            = ctx->time;
+		ra.nsteps        = nsteps;
+		ra.step_index0   = ctx->raster_steps;
+		ra.cursor        = ctx->d_cursor;
+		ra.log_ids       = ctx->d_log_ids;
+		ra.log_cap       = ctx->log_cap;
+		ra.log_off       = ctx->d_log_off;
+		ra.log_cnt       = ctx->d_log_cnt;
+		ra.log_steps_cap = ctx->log_steps_cap;
+		ra.error         = ctx->d_error;
+		if (np > 0) {
+			raster_pack<<<nsteps * np, 256, 0, ctx->stream>>>(ra);
+			ctx->launches++;
+		}
+		ctx->raster_steps += nsteps;
+	}
+	cudaError_t const e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return fail(ctx, SPICE_ERR_CUDA, std::string("window launch: ") + cudaGetErrorString(e));
+	ctx->time += nsteps;
+	return SPICE_OK;
+}
+
+int check_device_error(spice_ctx* ctx) {
+	int h = 0;
+	CHECK_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (h & 1)
+		return fail(ctx, SPICE_ERR_INTERNAL, "spike exchange timed out waiting for a peer rank");
+	if (h & 4)
+		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: step capacity exceeded (read the raster more often)");
+	if (h & 8)
+		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: id capacity exceeded (read the raster more often)");
+	return SPICE_OK;
+}
+
+int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop, float delay,
+                          void const* functor, connection* c) {
+	PRE(ctx, ops != nullptr && ops->abi_version == 1);
+	PRE(ctx, !ctx->finalized && "connect() after the first step is not supported");
+	PRE(ctx, src_pop >= 0 && src_pop < static_cast<int>(ctx->pops.size()));
+	PRE(ctx, dst_pop >= 0 && dst_pop < static_cast<int>(ctx->pops.size()));
+	PRE(ctx, ctx->pops[dst_pop].ops->neuron_bytes == ops->dst_neuron_bytes);
+	long long const d = static_cast<long long>(std::round(delay / ctx->dt)); // snn.h:33
+	PRE(ctx, d >= 1 && "The delay must be at least 1dt.");                 // snn.h:35
+	PRE(ctx, d <= ctx->max_delay && "The delay of a synapse population may not exceed the maximum delay of the network."); // snn.h:36-38
+	if (ops->synapse_bytes != 0 || ops->plastic || ops->deliver_from_to)
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateful / plastic / deliver-from-to synapses are not on the GPU path yet");
+	c->ops   = ops;
+	c->src   = src_pop;
+	c->dst   = dst_pop;
+	c->delay = d;
+	c->functor_host.assign(static_cast<unsigned char const*>(functor), static_cast<unsigned char const*>(functor) + ops->functor_bytes);
+	CHECK_CUDA(ctx, cudaMalloc(&c->functor_dev, std::max<size_t>(ops->functor_bytes, 16)));
+	CHECK_CUDA(ctx, cudaMemcpy(c->functor_dev, functor, ops->functor_bytes, cudaMemcpyHostToDevice));
+	int const e = ops->get_apply(&c->apply);
+	if (e != 0)
+		return fail(ctx, SPICE_ERR_CUDA, std::string("get_apply: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+	return SPICE_OK;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+char const* spice_version(void) { return "spice2_b200 0.1 (sm_100a)"; }
+
+int spice_device_check(int device) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n)
+		return SPICE_ERR_NO_DEVICE;
+	cudaDeviceProp prop{};
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+		return SPICE_ERR_NO_DEVICE;
+	return prop.major == 10 ? SPICE_OK : SPICE_ERR_UNSUPPORTED;
+}
+
+char const* spice_last_error(spice_ctx const* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uint32_t const* seed_words, int n_seed_words,
+                     int rank, int world, int mode) {
+	*out = nullptr;
+	if (!(dt > 0) || !(max_delay > 0) || !seed_words || n_seed_words <= 0 || world < 1 || world > kMaxWorld || rank < 0 ||
+	    rank >= world) {
+		g_create_error = "spice_ctx_create: invalid argument";
+		return SPICE_ERR_PRECONDITION;
+	}
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) {
+		g_create_error = "spice_ctx_create: no CUDA device — this backend has no CPU fallback";
+		return SPICE_ERR_NO_DEVICE;
+	}
+	auto ctx       = std::make_unique<spice_ctx>();
+	ctx->device    = device;
+	ctx->dt        = dt;
+	ctx->max_delay = static_cast<long long>(std::round(max_delay / dt)); // snn.h:18-19
+	if (ctx->max_delay < 1) {
+		g_create_error = "spice_ctx_create: max_delay must be at least 1 dt";
+		return SPICE_ERR_PRECONDITION;
+	}
+	ctx->seed  = util::seed_seq(seed_words, static_cast<std::size_t>(n_seed_words));
+	ctx->rank  = rank;
+	ctx->world = world;
+	ctx->mode  = mode;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		g_create_error = "spice_ctx_create: cannot create a stream on the device";
+		return SPICE_ERR_CUDA;
+	}
+	ctx->own_stream = true;
+	*out            = ctx.release();
+	return SPICE_OK;
+}
+
+int spice_ctx_destroy(spice_ctx* ctx) {
+	if (!ctx)
+		return SPICE_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (auto& p : ctx->pops) {
+		cudaFree(p.functor_dev);
+		cudaFree(p.state);
+		cudaFree(p.history);
+		cudaFree(p.jump_poly);
+	}
+	for (auto& c : ctx->conns) {
+		cudaFree(c.functor_dev);
+		cudaFree(c.offsets);
+		cudaFree(c.neighbors);
+		cudaFree(c.counts);
+	}
+	for (int r = 0; r < ctx->world; r++)
+		if (r != ctx->rank && ctx->peer_base[r] && ctx->peers_set) {
+			// only IPC-opened mappings need closing; same-process peers are plain pointers
+			cudaIpcCloseMemHandle(ctx->peer_base[r]);
+		}
+	cudaFree(ctx->xbase);
+	cudaFree(ctx->d_ring_cnt);
+	cudaFree(ctx->d_ring_ids);
+	cudaFree(ctx->d_ring_cap);
+	cudaFree(ctx->d_seg_lo);
+	cudaFree(ctx->d_peer_cnt);
+	cudaFree(ctx->d_nib);
+	cudaFree(ctx->d_stats);
+	cudaFree(ctx->d_error);
+	cudaFree(ctx->d_cursor);
+	cudaFree(ctx->d_log_ids);
+	cudaFree(ctx->d_log_off);
+	cudaFree(ctx->d_log_cnt);
+	cudaGetLastError();
+	if (ctx->own_stream)
+		cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return SPICE_OK;
+}
+
+int spice_ctx_set_stream(spice_ctx* ctx, void* cuda_stream) {
+	if (ctx->own_stream) {
+		cudaStreamSynchronize(ctx->stream);
+		cudaStreamDestroy(ctx->stream);
+		ctx->own_stream = false;
+	}
+	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return SPICE_OK;
+}
+
+int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t size, void const* functor, int* pop_out) {
+	PRE(ctx, ops != nullptr && ops->abi_version == 1);
+	PRE(ctx, size >= 0 && size < 2147483647);
+	PRE(ctx, !ctx->finalized && "add_population() after the first step is not supported");
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	population p;
+	p.ops    = ops;
+	p.size   = size;
+	p.lo     = size * ctx->rank / ctx->world;
+	p.hi     = size * (ctx->rank + 1) / ctx->world;
+	p.stride = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(p.hi - p.lo, 1)), 32));
+	std::vector<unsigned char> zero(std::max<std::uint32_t>(ops->functor_bytes, 1), 0);
+	unsigned char const* f = functor ? static_cast<unsigned char const*>(functor) : zero.data();
+	p.functor_host.assign(f, f + ops->functor_bytes);
+	CHECK_CUDA(ctx, cudaMalloc(&p.functor_dev, std::max<size_t>(ops->functor_bytes, 16)));
+	CHECK_CUDA(ctx, cudaMemcpy(p.functor_dev, f, ops->functor_bytes, cudaMemcpyHostToDevice));
+	if (ops->neuron_bytes) {
+		// the stateful adapter consumes one seed++ whether or not the model has an init hook
+		// (neuron_population.h:60); the hook runs over the WHOLE population with that engine
+		UInt128 const sd = (ctx->seed++).seed();
+		std::vector<unsigned char> aos(static_cast<size_t>(std::max<long long>(size, 1)) * ops->neuron_bytes);
+		ops->init_host(f, aos.data(), size, sd.lo, sd.hi);
+		int const words = ops->neuron_bytes / 4;
+		std::vector<std::uint32_t> soa(static_cast<size_t>(words) * static_cast<size_t>(p.stride), 0);
+		for (long long i = p.lo; i < p.hi; i++)
+			for (int w = 0; w < words; w++)
+				std::memcpy(&soa[static_cast<size_t>(w) * p.stride + (i - p.lo)], aos.data() + i * ops->neuron_bytes + 4 * w, 4);
+		CHECK_CUDA(ctx, cudaMalloc(&p.state, sizeof(std::uint32_t) * soa.size()));
+		CHECK_CUDA(ctx, cudaMemcpy(p.state, soa.data(), sizeof(std::uint32_t) * soa.size(), cudaMemcpyHostToDevice));
+	}
+	ctx->pops.push_back(std::move(p));
+	if (pop_out)
+		*pop_out = static_cast<int>(ctx->pops.size()) - 1;
+	return SPICE_OK;
+}
+
+int64_t spice_population_size(spice_ctx const* ctx, int pop) {
+	return (pop >= 0 && pop < static_cast<int>(ctx->pops.size())) ? ctx->pops[pop].size : -1;
+}
+
+int spice_population_range(spice_ctx const* ctx, int pop, int64_t* lo, int64_t* hi) {
+	if (pop < 0 || pop >= static_cast<int>(ctx->pops.size()))
+		return SPICE_ERR_PRECONDITION;
+	*lo = ctx->pops[pop].lo;
+	*hi = ctx->pops[pop].hi;
+	return SPICE_OK;
+}
+
+int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop, double p,
+                                    float delay, void const* functor, int* conn_out) {
+	PRE(ctx, 0 <= p && p <= 1); // topology.cpp:73
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	connection c;
+	int rc = add_connection_common(ctx, ops, src_pop, dst_pop, delay, functor, &c);
+	if (rc != SPICE_OK)
+		return rc;
+	// synapse_population ctor: _graph(c, seed++) (synapse_population.h:30-31)
+	UInt128 const sd      = (ctx->seed++).seed();
+	population const& src = ctx->pops[src_pop];
+	population const& dst = ctx->pops[dst_pop];
+	gen::result r;
+	std::string err;
+	rc = gen::generate_fixed_probability(ctx->stream, src.size, dst.size, p, sd.lo, sd.hi, dst.lo, dst.hi, 0, &r, &err);
+	if (rc != 0)
+		return fail(ctx, rc, err);
+	c.offsets   = r.offsets;
+	c.neighbors = r.neighbors;
+	c.edges     = r.edges;
+	ctx->launches += r.launches;
+	ctx->conns.push_back(std::move(c));
+	if (conn_out)
+		*conn_out = static_cast<int>(ctx->conns.size()) - 1;
+	return SPICE_OK;
+}
+
+int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop, int32_t const* edges_src,
+                           int32_t const* edges_dst, int64_t n_edges, float delay, void const* functor, int* conn_out) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	connection c;
+	int rc = add_connection_common(ctx, ops, src_pop, dst_pop, delay, functor, &c);
+	if (rc != SPICE_OK)
+		return rc;
+	(void)(ctx->seed++); // the graph still consumes its seed (synapse_population.h:31)
+	population const& src = ctx->pops[src_pop];
+	population const& dst = ctx->pops[dst_pop];
+	// adj_list::generate: sort packed (src << 32 | dst) and stream into CSR (topology.cpp:63-71)
+	std::vector<std::uint64_t> packed(static_cast<size_t>(n_edges));
+	for (int64_t i = 0; i < n_edges; i++) {
+		PRE(ctx, edges_src[i] >= 0 && edges_src[i] < src.size);
+		PRE(ctx, edges_dst[i] >= 0 && edges_dst[i] < dst.size);
+		packed[static_cast<size_t>(i)] = (static_cast<std::uint64_t>(edges_src[i]) << 32) | static_cast<std::uint32_t>(edges_dst[i]);
+	}
+	std::sort(packed.begin(), packed.end());
+	std::vector<long long> offsets(static_cast<size_t>(src.size) + 1, 0);
+	std::vector<std::int32_t> nb;
+	nb.reserve(packed.size());
+	size_t k = 0;
+	for (long long s = 0; s < src.size; s++) {
+		offsets[static_cast<size_t>(s)] = static_cast<long long>(nb.size());
+		for (; k < packed.size() && static_cast<long long>(packed[k] >> 32) == s; k++) {
+			long long const d = static_cast<long long>(packed[k] & 0xffffffffu);
+			if (d >= dst.lo && d < dst.hi)
+				nb.push_back(static_cast<std::int32_t>(d - dst.lo));
+		}
+	}
+	offsets[static_cast<size_t>(src.size)] = static_cast<long long>(nb.size());
+	c.edges = static_cast<long long>(nb.size());
+	CHECK_CUDA(ctx, cudaMalloc(&c.offsets, sizeof(long long) * offsets.size()));
+	CHECK_CUDA(ctx, cudaMemcpy(c.offsets, offsets.data(), sizeof(long long) * offsets.size(), cudaMemcpyHostToDevice));
+	CHECK_CUDA(ctx, cudaMalloc(&c.neighbors, sizeof(std::int32_t) * std::max<size_t>(nb.size(), 1)));
+	CHECK_CUDA(ctx, cudaMemcpy(c.neighbors, nb.data(), sizeof(std::int32_t) * nb.size(), cudaMemcpyHostToDevice));
+	ctx->conns.push_back(std::move(c));
+	if (conn_out)
+		*conn_out = static_cast<int>(ctx->conns.size()) - 1;
+	return SPICE_OK;
+}
+
+int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t* offsets_out, int32_t* neighbors_out) {
+	PRE(ctx, conn >= 0 && conn < static_cast<int>(ctx->conns.size()));
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	connection const& c = ctx->conns[conn];
+	if (n_edges_out)
+		*n_edges_out = c.edges;
+	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (offsets_out)
+		CHECK_CUDA(ctx, cudaMemcpy(offsets_out, c.offsets, sizeof(long long) * static_cast<size_t>(ctx->pops[c.src].size + 1), cudaMemcpyDeviceToHost));
+	if (neighbors_out && c.edges)
+		CHECK_CUDA(ctx, cudaMemcpy(neighbors_out, c.neighbors, sizeof(std::int32_t) * static_cast<size_t>(c.edges), cudaMemcpyDeviceToHost));
+	return SPICE_OK;
+}
+
+int spice_connection_synapses(spice_ctx* ctx, int conn, void* out, int64_t bytes) {
+	PRE(ctx, conn >= 0 && conn < static_cast<int>(ctx->conns.size()));
+	(void)out, (void)bytes;
+	return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateless connection: no per-synapse state");
+}
+
+int spice_ctx_finalize(spice_ctx* ctx) { return finalize(ctx); }
+
+int spice_ctx_peer_handle(spice_ctx* ctx, void* out, int64_t* bytes) {
+	int rc = finalize(ctx);
+	if (rc != SPICE_OK)
+		return rc;
+	if (bytes)
+		*bytes = sizeof(peer_blob);
+	if (!out)
+		return SPICE_OK;
+	peer_blob b{};
+	b.magic   = 0x5350494345423230ull;
+	b.pid     = static_cast<int>(getpid());
+	b.device  = ctx->device;
+	b.rank    = ctx->rank;
+	b.bytes   = ctx->xbytes;
+	b.raw_ptr = reinterpret_cast<unsigned long long>(ctx->xbase);
+	CHECK_CUDA(ctx, cudaIpcGetMemHandle(&b.handle, ctx->xbase));
+	std::memcpy(out, &b, sizeof b);
+	return SPICE_OK;
+}
+
+int spice_ctx_set_peers(spice_ctx* ctx, void const* blobs, int64_t bytes_each) {
+	PRE(ctx, ctx->finalized);
+	PRE(ctx, bytes_each == static_cast<int64_t>(sizeof(peer_blob)));
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	for (int r = 0; r < ctx->world; r++) {
+		peer_blob b;
+		std::memcpy(&b, static_cast<unsigned char const*>(blobs) + r * sizeof(peer_blob), sizeof b);
+		PRE(ctx, b.magic == 0x5350494345423230ull && b.rank == r && b.bytes == ctx->xbytes);
+		if (r == ctx->rank)
+			continue;
+		if (b.pid == static_cast<int>(getpid())) {
+			// same process (tests, single-process multi-device): the raw pointer is directly usable
+			if (b.device != ctx->device) {
+				cudaError_t const e = cudaDeviceEnablePeerAccess(b.device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+					CHECK_CUDA(ctx, e);
+				cudaGetLastError();
+			}
+			ctx->peer_base[r] = reinterpret_cast<unsigned char*>(b.raw_ptr);
+		} else {
+			void* p = nullptr;
+			CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess));
+			ctx->peer_base[r] = static_cast<unsigned char*>(p);
+			ctx->peers_set    = true;
+		}
+	}
+	return upload_peer_tables(ctx);
+}
+
+int spice_run(spice_ctx* ctx, int64_t n_steps) {
+	PRE(ctx, n_steps >= 0);
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	int rc = finalize(ctx);
+	if (rc != SPICE_OK)
+		return rc;
+	if (ctx->world > 1)
+		for (int r = 0; r < ctx->world; r++)
+			PRE(ctx, ctx->peer_base[r] != nullptr && "multi-rank context: call spice_ctx_set_peers() first");
+	while (n_steps > 0) {
+		int const n = static_cast<int>(std::min<int64_t>(n_steps, ctx->window));
+		rc          = run_window(ctx, n);
+		if (rc != SPICE_OK)
+			return rc;
+		n_steps -= n;
+	}
+	return SPICE_OK;
+}
+
+int spice_sync(spice_ctx* ctx) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->finalized) {
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return SPICE_OK;
+	}
+	return check_device_error(ctx);
+}
+
+int64_t spice_time(spice_ctx const* ctx) { return ctx->time; }
+
+int spice_spikes(spice_ctx* ctx, int pop, int64_t age, int32_t const** ids_out, int64_t* n_out) {
+	PRE(ctx, pop >= 0 && pop < static_cast<int>(ctx->pops.size()));
+	// neuron_population.h:148: 0 <= age < number of steps held (at most max_delay)
+	PRE(ctx, 0 <= age && age < std::min<long long>(ctx->time, ctx->max_delay));
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	int rc = check_device_error(ctx);
+	if (rc != SPICE_OK)
+		return rc;
+	population const& p  = ctx->pops[pop];
+	long long const step = ctx->time - 1 - age;
+	long long const slot = step % ctx->ring;
+	host_spikes& hs      = ctx->spike_cache[pop][static_cast<size_t>(slot)];
+	if (hs.step != step) {
+		std::vector<std::uint32_t> cnt(ctx->world);
+		CHECK_CUDA(ctx, cudaMemcpy(cnt.data(), xptr<std::uint32_t>(ctx->xbase, p.ring_cnt_off) + slot * ctx->world,
+		                           sizeof(std::uint32_t) * ctx->world, cudaMemcpyDeviceToHost));
+		long long total = 0;
+		for (auto c : cnt)
+			total += c;
+		hs.ids.resize(static_cast<size_t>(total));
+		long long at = 0;
+		for (int r = 0; r < ctx->world; r++) {
+			if (cnt[r]) {
+				CHECK_CUDA(ctx, cudaMemcpy(hs.ids.data() + at,
+				                           xptr<std::int32_t>(ctx->xbase, p.ring_ids_off) + slot * std::max<long long>(p.size, 1) + p.seg_lo[r],
+				                           sizeof(std::int32_t) * cnt[r], cudaMemcpyDeviceToHost));
+				// a segment holds one rank's spikes in arrival order; the reference lists them ascending
+				std::sort(hs.ids.begin() + at, hs.ids.begin() + at + cnt[r]);
+			}
+			at += cnt[r];
+		}
+		hs.step = step;
+	}
+	*ids_out = hs.ids.data();
+	*n_out   = static_cast<int64_t>(hs.ids.size());
+	return SPICE_OK;
+}
+
+int spice_neurons(spice_ctx* ctx, int pop, void* out, int64_t bytes) {
+	PRE(ctx, pop >= 0 && pop < static_cast<int>(ctx->pops.size()));
+	population& p = ctx->pops[pop];
+	PRE(ctx, p.ops->neuron_bytes != 0 && "Can only return collections of stateful neurons.");
+	long long const n = p.hi - p.lo;
+	PRE(ctx, bytes == n * p.ops->neuron_bytes);
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	int rc = finalize(ctx);
+	if (rc != SPICE_OK)
+		return rc;
+	if (n == 0)
+		return SPICE_OK;
+	void* dev = nullptr;
+	CHECK_CUDA(ctx, cudaMalloc(&dev, static_cast<size_t>(bytes)));
+	export_args ea{};
+	ea.stream  = ctx->stream;
+	ea.state   = p.state;
+	ea.n_local = n;
+	ea.stride  = p.stride;
+	ea.t_next  = ctx->time;
+	fill_incoming(ctx, p, ea.in, &ea.n_in);
+	ea.out_aos = dev;
+	int const e = p.ops->launch_export(&ea);
+	ctx->launches++;
+	if (e != 0) {
+		cudaFree(dev);
+		return fail(ctx, SPICE_ERR_CUDA, std::string("export launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+	}
+	cudaError_t ce = cudaMemcpyAsync(out, dev, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, ctx->stream);
+	if (ce == cudaSuccess)
+		ce = cudaStreamSynchronize(ctx->stream);
+	cudaFree(dev);
+	CHECK_CUDA(ctx, ce);
+	return SPICE_OK;
+}
+
+int spice_set_neurons(spice_ctx* ctx, int pop, void const* in, int64_t bytes) {
+	PRE(ctx, pop >= 0 && pop < static_cast<int>(ctx->pops.size()));
+	population& p = ctx->pops[pop];
+	PRE(ctx, p.ops->neuron_bytes != 0);
+	long long const n = p.hi - p.lo;
+	PRE(ctx, bytes == n * p.ops->neuron_bytes);
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (n == 0)
+		return SPICE_OK;
+	void* dev = nullptr;
+	CHECK_CUDA(ctx, cudaMalloc(&dev, static_cast<size_t>(bytes)));
+	cudaError_t ce = cudaMemcpyAsync(dev, in, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, ctx->stream);
+	import_args ia{ctx->stream, p.state, n, p.stride, dev};
+	if (ce == cudaSuccess)
+		ce = static_cast<cudaError_t>(p.ops->launch_import(&ia));
+	ctx->launches++;
+	if (ce == cudaSuccess)
+		ce = cudaStreamSynchronize(ctx->stream);
+	cudaFree(dev);
+	CHECK_CUDA(ctx, ce);
+	return SPICE_OK;
+}
+
+int spice_raster_enable(spice_ctx* ctx, int enable) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (enable && !ctx->d_cursor) {
+		long long total = 0;
+		for (auto const& p : ctx->pops)
+			total += p.size;
+		ctx->log_steps_cap = 1 << 16;
+		ctx->log_cap       = std::max<long long>(1 << 22, std::min<long long>(total * 64, 1ll << 28));
+		int const np       = static_cast<int>(std::max<size_t>(ctx->pops.size(), 1));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
+		CHECK_CUDA(ctx, cudaMemset(ctx->d_cursor, 0, sizeof(unsigned long long)));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_ids, sizeof(std::int32_t) * static_cast<size_t>(ctx->log_cap)));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_off, sizeof(long long) * static_cast<size_t>(ctx->log_steps_cap) * np));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_cnt, sizeof(std::int32_t) * static_cast<size_t>(ctx->log_steps_cap) * np * ctx->world));
+	}
+	ctx->raster_on = enable != 0;
+	return SPICE_OK;
+}
+
+int spice_raster_size(spice_ctx* ctx, int64_t* n_steps_out, int64_t* n_ids_out) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	unsigned long long cur = 0;
+	if (ctx->d_cursor) {
+		int rc = check_device_error(ctx);
+		if (rc != SPICE_OK)
+			return rc;
+		CHECK_CUDA(ctx, cudaMemcpy(&cur, ctx->d_cursor, sizeof cur, cudaMemcpyDeviceToHost));
+	}
+	if (n_steps_out)
+		*n_steps_out = ctx->raster_steps;
+	if (n_ids_out)
+		*n_ids_out = static_cast<int64_t>(cur);
+	return SPICE_OK;
+}
+
+int spice_raster_read(spice_ctx* ctx, int64_t* counts_out, int32_t* ids_out) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	int64_t steps = 0, nids = 0;
+	int rc = spice_raster_size(ctx, &steps, &nids);
+	if (rc != SPICE_OK)
+		return rc;
+	int const np = static_cast<int>(ctx->pops.size());
+	if (steps == 0 || np == 0)
+		return SPICE_OK;
+	std::vector<long long> off(static_cast<size_t>(steps) * np);
+	std::vector<std::int32_t> cnt(static_cast<size_t>(steps) * np * ctx->world);
+	std::vector<std::int32_t> raw(static_cast<size_t>(std::max<int64_t>(nids, 1)));
+	CHECK_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_log_off, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost));
+	CHECK_CUDA(ctx, cudaMemcpy(cnt.data(), ctx->d_log_cnt, sizeof(std::int32_t) * cnt.size(), cudaMemcpyDeviceToHost));
+	if (nids)
+		CHECK_CUDA(ctx, cudaMemcpy(raw.data(), ctx->d_log_ids, sizeof(std::int32_t) * static_cast<size_t>(nids), cudaMemcpyDeviceToHost));
+	long long at = 0;
+	for (long long i = 0; i < steps * np; i++) {
+		long long total = 0, from = off[static_cast<size_t>(i)];
+		for (int r = 0; r < ctx->world; r++) {
+			std::int32_t const c = cnt[static_cast<size_t>(i) * ctx->world + r];
+			std::sort(raw.begin() + from + total, raw.begin() + from + total + c);
+			total += c;
+		}
+		counts_out[i] = total;
+		std::memcpy(ids_out + at, raw.data() + from, sizeof(std::int32_t) * static_cast<size_t>(total));
+		at += total;
+	}
+	CHECK_CUDA(ctx, cudaMemset(ctx->d_cursor, 0, sizeof(unsigned long long)));
+	ctx->raster_steps = 0;
+	return SPICE_OK;
+}
+
+int spice_stats(spice_ctx* ctx, int64_t* synaptic_events, int64_t* spikes_delivered, int64_t* kernel_launches) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	unsigned long long h[2] = {0, 0};
+	if (ctx->d_stats) {
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CHECK_CUDA(ctx, cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+	}
+	if (synaptic_events)
+		*synaptic_events = static_cast<int64_t>(h[0]);
+	if (spikes_delivered)
+		*spikes_delivered = static_cast<int64_t>(h[1]);
+	if (kernel_launches)
+		*kernel_launches = ctx->launches;
+	return SPICE_OK;
+}
+
+// ---- standalone generation ---------------------------------------------------------------------
+struct spice_adjacency {
+	int device;
+	long long src;
+	gen::result r;
+};
+
+int64_t spice_fixed_probability_max_degree(int64_t dst_count, double p) { return gen::max_degree(dst_count, p); }
+
+int spice_fixed_probability_generate(int device, int64_t src_count, int64_t dst_count, double p, uint64_t seed_lo,
+                                     uint64_t seed_hi, int64_t col_lo, int64_t col_hi, spice_adjacency** out) {
+	*out = nullptr;
+	if (!(0 <= p && p <= 1) || src_count < 0 || dst_count < 0 || src_count >= 2147483647 || dst_count >= 2147483647 ||
+	    col_lo < 0 || col_hi > dst_count || col_lo > col_hi) {
+		g_create_error = "spice_fixed_probability_generate: invalid argument";
+		return SPICE_ERR_PRECONDITION;
+	}
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) {
+		g_create_error = "no CUDA device — this backend has no CPU fallback";
+		return SPICE_ERR_NO_DEVICE;
+	}
+	cudaSetDevice(device);
+	auto a    = std::make_unique<spice_adjacency>();
+	a->device = device;
+	a->src    = src_count;
+	std::string err;
+	int const rc = gen::generate_fixed_probability(nullptr, src_count, dst_count, p, seed_lo, seed_hi, col_lo, col_hi, 0, &a->r, &err);
+	if (rc != 0) {
+		cudaFree(a->r.offsets);
+		cudaFree(a->r.neighbors);
+		g_create_error = err;
+		return rc;
+	}
+	*out = a.release();
+	return SPICE_OK;
+}
+
+int64_t spice_adjacency_edges(spice_adjacency const* a) { return a->r.edges; }
+void* spice_adjacency_offsets_dev(spice_adjacency const* a) { return a->r.offsets; }
+void* spice_adjacency_neighbors_dev(spice_adjacency const* a) { return a->r.neighbors; }
+
+int spice_adjacency_copy(spice_adjacency const* a, int64_t* offsets_host, int32_t* neighbors_host) {
+	cudaSetDevice(a->device);
+	if (offsets_host && cudaMemcpy(offsets_host, a->r.offsets, sizeof(long long) * static_cast<size_t>(a->src + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
+		return SPICE_ERR_CUDA;
+	if (neighbors_host && a->r.edges &&
+	    cudaMemcpy(neighbors_host, a->r.neighbors, sizeof(std::int32_t) * static_cast<size_t>(a->r.edges), cudaMemcpyDeviceToHost) != cudaSuccess)
+		return SPICE_ERR_CUDA;
+	return SPICE_OK;
+}
+
+int spice_adjacency_timing(spice_adjacency const* a, float* total_ms, float* rows_kernel_ms, int64_t* draws) {
+	if (total_ms)
+		*total_ms = a->r.total_ms;
+	if (rows_kernel_ms)
+		*rows_kernel_ms = a->r.rows_ms;
+	if (draws)
+		*draws = a->r.draws;
+	return SPICE_OK;
+}
+
+int spice_adjacency_destroy(spice_adjacency* a) {
+	if (!a)
+		return SPICE_OK;
+	cudaSetDevice(a->device);
+	cudaFree(a->r.offsets);
+	cudaFree(a->r.neighbors);
+	delete a;
+	return SPICE_OK;
+}
+
+void spice_seed_seq(uint32_t const* words, int n, uint64_t out[2]) {
+	util::seed_seq s(words, static_cast<std::size_t>(n));
+	out[0] = s.seed().lo;
+	out[1] = s.seed().hi;
+}
+
+void spice_seed_next(uint64_t seed[2]) {
+	util::seed_seq s(UInt128{seed[0], seed[1]});
+	s++;
+	seed[0] = s.seed().lo;
+	seed[1] = s.seed().hi;
+}
+}

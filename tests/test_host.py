@@ -1,0 +1,133 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the public
+header declares, the host RNG / jump-ahead / glibc-log restatements agree with the oracle and the
+golden vectors.  No compute call is made (no GPU here)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+hx = lambda v: f"{int(v):016x}"
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import spice2_b200 as sp
+
+    sp.lib()
+    return sp
+
+
+def test_library_exports_every_declared_symbol(sp):
+    header = (ROOT / "include" / "spice_b200.h").read_text()
+    declared = set(re.findall(r"SPICE_API [^;(]*?\b(spice_\w+)\(", header))
+    assert len(declared) >= 35
+    so = ROOT / "spice2_b200" / "libspice_b200.so"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (spice_\w+)", out))
+    assert declared <= exported, declared - exported
+    L = C.CDLL(str(so))
+    for name in declared:
+        getattr(L, name)
+
+
+def test_library_is_sm100a_cuda(sp):
+    so = ROOT / "spice2_b200" / "libspice_b200.so"
+    out = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert b"spice2_b200" in sp.lib().spice_version()
+
+
+def test_no_device_fails_loudly(sp):
+    """No CPU fallback: without a CUDA device the computing entry points refuse."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sp.SpiceError, match="no CPU fallback|no CUDA device"):
+        sp.snn(1e-4, 15e-4)
+    with pytest.raises(sp.SpiceError):
+        sp.generate_fixed_probability(10, 10, 0.5)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "spice2_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".cpp") and p.is_file():
+            text = p.read_text()
+            for needle in ("liboracle", "oracle_lib", "spice_oracle", "oracle/"):
+                assert needle not in text, f"{p} mentions {needle}"
+
+
+def test_host_seed_seq_matches_golden(sp, golden):
+    for k, want in golden["seed_1337"].items():
+        assert [hx(x) for x in sp.seed_seq([1337], int(k))] == want
+    for il, want in golden["seed_il"].items():
+        assert [hx(x) for x in sp.seed_seq([int(x) for x in il.split(",")])] == want
+
+
+def test_max_degree_matches_golden(sp, golden):
+    for g in golden["fixed_probability"]:
+        if g["src"] > 0:
+            assert sp.lib().spice_fixed_probability_max_degree(g["dst"], g["p"]) * g["src"] == g["capacity"]
+
+
+@pytest.fixture(scope="module")
+def hosttool(tmp_path_factory):
+    """Small host program exercising the header-only restatements (glibc log, jump-ahead)."""
+    d = tmp_path_factory.mktemp("hosttool")
+    src = d / "t.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include "spice/detail/glibc_log.h"
+#include "spice/util/random.h"
+#include "spice/util/numeric.h"
+using namespace spice::util;
+int main(int argc, char** argv) {
+	if (!strcmp(argv[1], "log")) {   // stdin: doubles as hex bit patterns; stdout: log bits
+		unsigned long long u;
+		while (scanf("%llx", &u) == 1) printf("%016llx\n", (unsigned long long)spice::detail::glibc::double_to_bits(spice::detail::glibc::log(spice::detail::glibc::bits_to_double(u))));
+	} else if (!strcmp(argv[1], "jump")) { // args: lo hi k -> state after k steps via jump polynomial
+		xoroshiro64_128p s(strtoull(argv[2], 0, 16), strtoull(argv[3], 0, 16));
+		auto r = jump::apply(jump::xpow(strtoull(argv[4], 0, 10)), s);
+		printf("%016llx %016llx\n", (unsigned long long)r.s0, (unsigned long long)r.s1);
+	} else if (!strcmp(argv[1], "kahan")) {
+		kahan_sum<float> k; int n = atoi(argv[2]);
+		for (int i = 0; i < n; i++) { float d = k += 1e-4f; if (k >= 1) k.reset(); unsigned b; memcpy(&b, &d, 4); printf("%08x\n", b); }
+	}
+	return 0;
+}
+''')
+    exe = d / "t"
+    inc = ROOT / "spice2_b200" / "csrc" / "include"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-mfma", f"-I{inc}", str(src),
+                    str(ROOT / "spice2_b200" / "csrc" / "jump.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+def test_glibc_log_restatement_matches_golden_pins(hosttool):
+    z = np.load(ROOT / "tests" / "golden" / "libm_pins.npz")
+    x, y = z["log_x"], z["log_y"]
+    inp = "\n".join(f"{int(v):x}" for v in x.view(np.uint64))
+    out = subprocess.run([str(hosttool), "log"], input=inp, capture_output=True, text=True, check=True).stdout.split()
+    got = np.array([int(v, 16) for v in out], np.uint64)
+    assert np.array_equal(got, y.view(np.uint64))
+
+
+def test_jump_ahead_matches_sequential(hosttool, orc):
+    seed = orc.seed_seq([1337], 3)
+    for k in (0, 1, 2, 127, 128, 129, 1000, 65537, 1234567):
+        out = subprocess.run([str(hosttool), "jump", hx(seed.lo), hx(seed.hi), str(k)], capture_output=True, text=True,
+                             check=True).stdout.split()
+        assert (int(out[0], 16), int(out[1], 16)) == orc.state_at(seed, k), k
+
+
+def test_host_kahan_dt_matches_oracle(hosttool, orc):
+    out = subprocess.run([str(hosttool), "kahan", "12000"], capture_output=True, text=True, check=True).stdout.split()
+    got = np.array([int(v, 16) for v in out], np.uint32)
+    assert np.array_equal(got, orc.kahan_dt(np.float32(1e-4), 12000).view(np.uint32))
