@@ -70,6 +70,10 @@ typedef struct spice_synapse_ops spice_synapse_ops;
  * synapses.  world == 1 for single-GPU. */
 SPICE_API int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uint32_t const* seed_words,
                      int n_seed_words, int rank, int world, int mode);
+/* same, from an already-hashed 128-bit seed (util::seed_seq::seed(), random.h:161) — what the C++
+ * facade holds when the user passes `{1337}` through the reference's constructor signature */
+SPICE_API int spice_ctx_create_seeded(spice_ctx** out, int device, float dt, float max_delay, uint64_t seed_lo,
+                                      uint64_t seed_hi, int rank, int world, int mode);
 SPICE_API int spice_ctx_destroy(spice_ctx* ctx);
 /* message of the last failure on this context (or of the last failed create when ctx == NULL) */
 SPICE_API char const* spice_last_error(spice_ctx const* ctx);
@@ -138,6 +142,13 @@ SPICE_API int spice_raster_read(spice_ctx* ctx, int64_t* counts_out, int32_t* id
 /* counters: synaptic events (Syn::deliver invocations, synapse_population.h:118-133) and spikes
  * processed by this rank since creation */
 SPICE_API int spice_stats(spice_ctx* ctx, int64_t* synaptic_events, int64_t* spikes_delivered, int64_t* kernel_launches);
+
+/* Phase timing with CUDA events recorded on the context's stream around each window's update
+ * and delivery launches (measurement only; bench.py's roofline numbers come from here).
+ * spice_profile_read synchronises, returns the sums since the last read and clears them. */
+SPICE_API int spice_profile_enable(spice_ctx* ctx, int enable);
+SPICE_API int spice_profile_read(spice_ctx* ctx, double* update_ms, double* deliver_ms, double* exchange_ms,
+                                 int64_t* windows);
 
 /* ---- multi-GPU spike exchange (new) ---------------------------------------------
  * One process per GPU.  Every rank keeps a copy of each population's spike ring in one device

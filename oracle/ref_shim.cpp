@@ -211,7 +211,34 @@ int ref_brunel_run(std::int64_t N, double p, float w_exc, float w_inh, float dt,
 		*build_seconds = seconds(t0, t1);
 	if (sim_seconds)
 		*sim_seconds = sim;
-	(void)synaptic_events;
+	// Tally of Syn::deliver invocations (synapse_population.h:118-133), recomputed outside the
+	// timed region: regenerate each connection's offsets from its seed (the stateless P burns no
+	// seed, E and I one each, so connection j was built from the (2 + j)-th increment) and add the
+	// out-degree of every spike that was delivered, i.e. emitted at a step <= steps - delay.
+	if (synaptic_events && counts && !r.overflow) {
+		std::int64_t const d   = static_cast<std::int64_t>(std::round(delay / dt));
+		std::int64_t const nsz[3] = {N / 2, N * 4 / 10, N / 10};
+		int const csrc[6] = {0, 0, 1, 1, 2, 2}, cdst[6] = {1, 2, 1, 2, 1, 2};
+		std::int64_t total = 0;
+		for (int j = 0; j < 6; j++) {
+			spice::fixed_probability fp(p);
+			fp(nsz[csrc[j]], nsz[cdst[j]]);
+			std::vector<Int> off(static_cast<std::size_t>(nsz[csrc[j]]) + 1);
+			std::vector<Int32> nb(static_cast<std::size_t>(fp.size()));
+			std::uint32_t il[1] = {seed};
+			fp.generate(off, nb, make_seed(il, 1, 2 + j));
+			std::int64_t at = 0;
+			for (std::int64_t s = 0; s < steps; s++)
+				for (int pop = 0; pop < 3; pop++) {
+					std::int64_t const c = counts[s * 3 + pop];
+					if (pop == csrc[j] && s <= steps - d)
+						for (std::int64_t k = 0; k < c; k++)
+							total += off[ids[at + k] + 1] - off[ids[at + k]];
+					at += c;
+				}
+		}
+		*synaptic_events = total;
+	}
 	return r.overflow ? 1 : 0;
 }
 

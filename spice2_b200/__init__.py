@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
         sig = {
             "spice_ctx_create": (i32, [C.POINTER(vp), i32, C.c_float, C.c_float, vp, i32, i32, i32, i32]),
+            "spice_ctx_create_seeded": (i32, [C.POINTER(vp), i32, C.c_float, C.c_float, C.c_uint64, C.c_uint64, i32, i32, i32]),
             "spice_ctx_destroy": (i32, [vp]),
             "spice_last_error": (C.c_char_p, [vp]),
             "spice_ctx_set_stream": (i32, [vp, vp]),
@@ -67,6 +68,9 @@ def lib() -> C.CDLL:
             "spice_raster_size": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
             "spice_raster_read": (i32, [vp, vp, vp]),
             "spice_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+            "spice_profile_enable": (i32, [vp, i32]),
+            "spice_profile_read": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(i64)]),
             "spice_ctx_finalize": (i32, [vp]),
             "spice_ctx_peer_handle": (i32, [vp, vp, C.POINTER(i64)]),
             "spice_ctx_set_peers": (i32, [vp, vp, i64]),
@@ -250,6 +254,11 @@ class snn:
         self._check(lib().spice_connection_csr(self._h, conn, C.byref(n), _ptr(off), _ptr(nb)))
         return off, nb[: n.value]
 
+    def connection_edges(self, conn: int) -> int:
+        n = C.c_int64()
+        self._check(lib().spice_connection_csr(self._h, conn, C.byref(n), None, None))
+        return n.value
+
     def step(self, n: int = 1):
         """snn::step() n times (spice/src/snn.cpp:7-28).  Asynchronous; readouts synchronise."""
         self._check(lib().spice_run(self._h, n))
@@ -280,6 +289,14 @@ class snn:
         ev, sp, kl = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(lib().spice_stats(self._h, C.byref(ev), C.byref(sp), C.byref(kl)))
         return dict(synaptic_events=ev.value, spikes_delivered=sp.value, kernel_launches=kl.value)
+
+    def profile_enable(self, on=True):
+        self._check(lib().spice_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        u, d, x, w = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self._check(lib().spice_profile_read(self._h, C.byref(u), C.byref(d), C.byref(x), C.byref(w)))
+        return dict(update_ms=u.value, deliver_ms=d.value, exchange_ms=x.value, windows=w.value)
 
     # multi-GPU plumbing (one process per GPU; handles are all-gathered by the caller)
     def finalize(self):

@@ -1,0 +1,156 @@
+// class spice::snn — the reference's C++20 API (spice/include/spice/snn.h:16-75), kept intact as
+// the drop-in boundary, over the B200 backend.
+//
+//     snn net(dt, max_delay, {1337});
+//     auto P = net.add_population<poisson>(N / 2);
+//     auto E = net.add_population<lif>(N * 4 / 10);
+//     net.connect<fixed_weight>(P, E, fixed_probability(0.1), delay, {2.0 / N});
+//     net.step();
+//     E->spikes(0);
+//
+// Differences a user sees:
+//   * the translation unit is compiled by nvcc (-std=c++20 -fmad=false, sm_100a): add_population
+//     and connect instantiate the simulation kernels for the user's functors right here;
+//   * functor members that run in kernels carry SPICE_HD; neurons that draw declare rng_draws;
+//   * step() enqueues work; results are observable through spikes()/get_neurons(), which
+//     synchronise.  run(n) advances n steps with one launch window per min-delay steps;
+//   * snn::spikes(i) (named by the north star) = spikes(0) of the i-th population added.
+// Errors keep the reference's convention: std::logic_error("Assertion failed (file:line): cond").
+#pragma once
+
+#include <cmath>
+#include <memory>
+#include <span>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+#include "spice/concepts.h"
+#include "spice/detail/model_ops.cuh"
+#include "spice/topology.h"
+#include "spice/util/numeric.h"
+#include "spice/util/random.h"
+#include "spice_b200.h"
+
+namespace spice {
+namespace detail {
+inline void check(spice_ctx* ctx, int rc) {
+	if (rc != SPICE_OK)
+		throw std::logic_error(spice_last_error(ctx));
+}
+
+// type-erased view (reference: detail::NeuronPopulation, neuron_population.h:17-25)
+struct NeuronPopulation {
+	virtual ~NeuronPopulation() = default;
+	virtual Int size() const                             = 0;
+	virtual std::span<Int32 const> spikes(Int age) const = 0;
+	virtual int index() const                            = 0;
+};
+
+template <class T>
+struct state_cache {
+	std::vector<T> values;
+};
+template <>
+struct state_cache<void> {};
+
+template <Neuron Neur>
+class neuron_population : public NeuronPopulation {
+public:
+	neuron_population(spice_ctx* ctx, Neur neuron, Int const size) : _ctx(ctx), _size(size) {
+		check(ctx, spice_add_population(ctx, neuron_ops<Neur>(), size, &neuron, &_index));
+	}
+
+	Int size() const override { return _size; }
+	int index() const override { return _index; }
+
+	// spikes emitted `age` steps ago, ascending (neuron_population.h:147-153); valid until the next step()
+	std::span<Int32 const> spikes(Int age) const override {
+		Int32 const* ids = nullptr;
+		int64_t n        = 0;
+		check(_ctx, spice_spikes(_ctx, _index, age, &ids, &n));
+		return {ids, static_cast<std::size_t>(n)};
+	}
+
+	// copy of this rank's neurons (neuron_population.h:142-145); refreshed on every call
+	auto get_neurons() {
+		static_assert(StatefulNeuron<Neur>, "Can only return collections of stateful neurons.");
+		using N = neuron_traits_t<Neur>;
+		int64_t lo = 0, hi = 0;
+		check(_ctx, spice_population_range(_ctx, _index, &lo, &hi));
+		_cache.values.resize(static_cast<std::size_t>(hi - lo));
+		check(_ctx, spice_neurons(_ctx, _index, _cache.values.data(), static_cast<int64_t>(_cache.values.size() * sizeof(N))));
+		return std::span<N>(_cache.values);
+	}
+
+private:
+	spice_ctx* _ctx;
+	Int _size;
+	int _index = -1;
+	[[no_unique_address]] state_cache<neuron_traits_t<Neur>> _cache;
+};
+}
+
+inline Int fixed_probability::size() const { return src_count * spice_fixed_probability_max_degree(dst_count, _p); }
+
+class snn {
+public:
+	snn(float const dt, float const max_delay, util::seed_seq seed, int device = 0, int rank = 0, int world = 1,
+	    int mode = SPICE_MODE_DETERMINISTIC) :
+	_dt(dt) {
+		spice_ctx* ctx = nullptr;
+		int const rc   = spice_ctx_create_seeded(&ctx, device, dt, max_delay, seed.seed().lo, seed.seed().hi, rank, world, mode);
+		if (rc != SPICE_OK)
+			throw std::logic_error(spice_last_error(nullptr));
+		_ctx.reset(ctx);
+	}
+
+	template <Neuron Neur>
+	detail::neuron_population<Neur>* add_population(Int const size, Neur neur = {}) {
+		_neurons.push_back(std::make_unique<detail::neuron_population<Neur>>(_ctx.get(), std::move(neur), size));
+		return static_cast<detail::neuron_population<Neur>*>(_neurons.back().get());
+	}
+
+	template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
+	requires Synapse<Syn, SrcNeur, DstNeur>
+	void connect(detail::neuron_population<SrcNeur>* source, detail::neuron_population<DstNeur>* target, Topology& c,
+	             float const delay, Syn syn = {}) {
+		c(source->size(), target->size());
+		auto const* ops = detail::synapse_ops<Syn, SrcNeur, DstNeur>();
+		if (auto* fp = dynamic_cast<fixed_probability*>(&c))
+			detail::check(_ctx.get(), spice_connect_fixed_probability(_ctx.get(), ops, source->index(), target->index(), fp->p(),
+			                                                          delay, &syn, nullptr));
+		else if (auto* adj = dynamic_cast<adj_list*>(&c))
+			detail::check(_ctx.get(), spice_connect_adj_list(_ctx.get(), ops, source->index(), target->index(), adj->sources().data(),
+			                                                 adj->targets().data(), adj->size(), delay, &syn, nullptr));
+		else
+			throw std::logic_error("Assertion failed (snn.h): unsupported Topology subclass on the GPU backend");
+	}
+
+	template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
+	requires Synapse<Syn, SrcNeur, DstNeur>
+	void connect(detail::neuron_population<SrcNeur>* source, detail::neuron_population<DstNeur>* target, Topology&& c,
+	             float const delay, Syn syn = {}) {
+		connect<Syn, SrcNeur, DstNeur>(source, target, c, delay, std::move(syn));
+	}
+
+	// snn::step() (spice/src/snn.cpp:7-28)
+	void step() { run(1); }
+	// n steps, one launch window per min-delay steps
+	void run(Int n) { detail::check(_ctx.get(), spice_run(_ctx.get(), n)); }
+	void sync() { detail::check(_ctx.get(), spice_sync(_ctx.get())); }
+
+	// spikes of the i-th population added, emitted in the step that just ran
+	std::span<Int32 const> spikes(Int i) const { return _neurons.at(static_cast<std::size_t>(i))->spikes(0); }
+
+	spice_ctx* context() { return _ctx.get(); }
+
+private:
+	struct ctx_deleter {
+		void operator()(spice_ctx* c) const { spice_ctx_destroy(c); }
+	};
+	float _dt;
+	std::unique_ptr<spice_ctx, ctx_deleter> _ctx;
+	std::vector<std::unique_ptr<detail::NeuronPopulation>> _neurons;
+};
+}

@@ -350,6 +350,13 @@ struct spice_ctx {
 
 	// readout scratch
 	std::vector<std::vector<host_spikes>> spike_cache; // [pop][age]
+
+	// phase timing (spice_profile_*): 4 events per window
+	bool profile = false;
+	std::vector<cudaEvent_t> prof_events;
+	size_t prof_used = 0;
+	double prof_update = 0, prof_deliver = 0, prof_exchange = 0;
+	long long prof_windows = 0;
 };
 
 namespace {
@@ -512,8 +519,45 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	}
 }
 
+cudaEvent_t prof_mark(spice_ctx* ctx) {
+	if (ctx->prof_used == ctx->prof_events.size()) {
+		cudaEvent_t e = nullptr;
+		cudaEventCreate(&e);
+		ctx->prof_events.push_back(e);
+	}
+	cudaEvent_t e = ctx->prof_events[ctx->prof_used++];
+	cudaEventRecord(e, ctx->stream);
+	return e;
+}
+
+int prof_collect(spice_ctx* ctx) {
+	if (ctx->prof_used == 0)
+		return SPICE_OK;
+	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (size_t i = 0; i + 3 < ctx->prof_used; i += 4) {
+		float a = 0, b = 0, c = 0;
+		cudaEventElapsedTime(&a, ctx->prof_events[i], ctx->prof_events[i + 1]);
+		cudaEventElapsedTime(&b, ctx->prof_events[i + 1], ctx->prof_events[i + 2]);
+		cudaEventElapsedTime(&c, ctx->prof_events[i + 2], ctx->prof_events[i + 3]);
+		ctx->prof_update += a;
+		ctx->prof_exchange += b;
+		ctx->prof_deliver += c;
+		ctx->prof_windows++;
+	}
+	ctx->prof_used = 0;
+	return SPICE_OK;
+}
+
 int run_window(spice_ctx* ctx, int nsteps) {
 	int const np = static_cast<int>(ctx->pops.size());
+	if (ctx->profile) {
+		if (ctx->prof_used >= 4096) {
+			int const rc = prof_collect(ctx);
+			if (rc != SPICE_OK)
+				return rc;
+		}
+		prof_mark(ctx);
+	}
 	// host-side per-step scalars: compensated dt (snn.cpp:8-10) and the step's stream seed (snn.cpp:12)
 	prologue_args pa{};
 	float dts[kMaxWindow];
@@ -566,6 +610,8 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		}
 	}
 
+	if (ctx->profile)
+		prof_mark(ctx);
 	if (ctx->world > 1) {
 		ctx->seq++;
 		publish_args pb{};
@@ -586,6 +632,8 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		ctx->launches += 2;
 	}
 
+	if (ctx->profile)
+		prof_mark(ctx);
 	for (auto& c : ctx->conns) {
 		population const& src = ctx->pops[c.src];
 		population const& dst = ctx->pops[c.dst];
@@ -615,6 +663,8 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		ctx->launches++;
 	}
 
+	if (ctx->profile)
+		prof_mark(ctx);
 	if (ctx->raster_on) {
 		raster_args ra{};
 		ra.ring_ids      = ctx->d_ring_ids;
@@ -705,11 +755,10 @@ int spice_device_check(int device) {
 
 char const* spice_last_error(spice_ctx const* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
-int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uint32_t const* seed_words, int n_seed_words,
-                     int rank, int world, int mode) {
+int spice_ctx_create_seeded(spice_ctx** out, int device, float dt, float max_delay, uint64_t seed_lo, uint64_t seed_hi,
+                            int rank, int world, int mode) {
 	*out = nullptr;
-	if (!(dt > 0) || !(max_delay > 0) || !seed_words || n_seed_words <= 0 || world < 1 || world > kMaxWorld || rank < 0 ||
-	    rank >= world) {
+	if (!(dt > 0) || !(max_delay > 0) || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) {
 		g_create_error = "spice_ctx_create: invalid argument";
 		return SPICE_ERR_PRECONDITION;
 	}
@@ -726,7 +775,7 @@ int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uin
 		g_create_error = "spice_ctx_create: max_delay must be at least 1 dt";
 		return SPICE_ERR_PRECONDITION;
 	}
-	ctx->seed  = util::seed_seq(seed_words, static_cast<std::size_t>(n_seed_words));
+	ctx->seed  = util::seed_seq(UInt128{seed_lo, seed_hi});
 	ctx->rank  = rank;
 	ctx->world = world;
 	ctx->mode  = mode;
@@ -737,6 +786,17 @@ int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uin
 	ctx->own_stream = true;
 	*out            = ctx.release();
 	return SPICE_OK;
+}
+
+int spice_ctx_create(spice_ctx** out, int device, float dt, float max_delay, uint32_t const* seed_words, int n_seed_words,
+                     int rank, int world, int mode) {
+	*out = nullptr;
+	if (!seed_words || n_seed_words <= 0) {
+		g_create_error = "Assertion failed (random.h): il.size() > 0 && \"Please provide at least 1 seed to seed_seq\"";
+		return SPICE_ERR_PRECONDITION;
+	}
+	util::seed_seq const s(seed_words, static_cast<std::size_t>(n_seed_words));
+	return spice_ctx_create_seeded(out, device, dt, max_delay, s.seed().lo, s.seed().hi, rank, world, mode);
 }
 
 int spice_ctx_destroy(spice_ctx* ctx) {
@@ -774,6 +834,8 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_log_ids);
 	cudaFree(ctx->d_log_off);
 	cudaFree(ctx->d_log_cnt);
+	for (auto e : ctx->prof_events)
+		cudaEventDestroy(e);
 	cudaGetLastError();
 	if (ctx->own_stream)
 		cudaStreamDestroy(ctx->stream);
@@ -1187,6 +1249,29 @@ int spice_stats(spice_ctx* ctx, int64_t* synaptic_events, int64_t* spikes_delive
 		*spikes_delivered = static_cast<int64_t>(h[1]);
 	if (kernel_launches)
 		*kernel_launches = ctx->launches;
+	return SPICE_OK;
+}
+
+int spice_profile_enable(spice_ctx* ctx, int enable) {
+	ctx->profile = enable != 0;
+	return SPICE_OK;
+}
+
+int spice_profile_read(spice_ctx* ctx, double* update_ms, double* deliver_ms, double* exchange_ms, int64_t* windows) {
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	int const rc = prof_collect(ctx);
+	if (rc != SPICE_OK)
+		return rc;
+	if (update_ms)
+		*update_ms = ctx->prof_update;
+	if (deliver_ms)
+		*deliver_ms = ctx->prof_deliver;
+	if (exchange_ms)
+		*exchange_ms = ctx->prof_exchange;
+	if (windows)
+		*windows = ctx->prof_windows;
+	ctx->prof_update = ctx->prof_deliver = ctx->prof_exchange = 0;
+	ctx->prof_windows = 0;
 	return SPICE_OK;
 }
 

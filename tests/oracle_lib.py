@@ -371,12 +371,13 @@ class RefShim:
         args = [C.c_int64(N), C.c_double(p), C.c_float(w_exc), C.c_float(w_inh), C.c_float(dt), C.c_float(delay),
                 C.c_uint32(seed), C.c_int64(steps), _ptr(ids), C.c_int64(cap), _ptr(counts), _ptr(sE), _ptr(sI),
                 C.byref(b), C.byref(s)]
+        ev = C.c_int64(-1)
         if fn == "ref_brunel_run":
-            args.append(None)
+            args.append(C.byref(ev) if record else None)
         r = getattr(self.L, fn)(*args)
         if r != 0:
             raise RuntimeError("raster capacity exceeded")
-        out = dict(build_seconds=b.value, sim_seconds=s.value, state_E=sE, state_I=sI)
+        out = dict(build_seconds=b.value, sim_seconds=s.value, state_E=sE, state_I=sI, synaptic_events=ev.value)
         if record:
             counts = counts.reshape(steps, npop)
             out["counts"] = counts
