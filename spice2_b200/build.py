@@ -24,7 +24,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", f"-I{CSRC / 'include'}", f"-I{ROOT / 'include'}",
           f"-I{CSRC}"]
-UNITS = [("runtime.cu", []), ("generator.cu", []), ("builtin_models.cu", ["-fmad=false"]), ("jump.cpp", [])]
+UNITS = [("runtime.cu", []), ("deliver.cu", ["-Xptxas", "-v"]), ("generator.cu", []), ("builtin_models.cu", ["-fmad=false"]), ("jump.cpp", [])]
 
 
 def _digest() -> str:

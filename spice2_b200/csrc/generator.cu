@@ -533,7 +533,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	GEN_CUDA(cudaMalloc(&st, sizeof(orbit_state)));
 	GEN_CUDA(cudaMalloc(&error, sizeof(int)));
 	GEN_CUDA(cudaMallocHost(&st_host, sizeof(orbit_state)));
-	GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(capacity)));
+	GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(capacity + 8))); // +8: the delivery kernel reads whole 16-byte groups
 	if (filtered)
 		GEN_CUDA(cudaMalloc(&degree, sizeof(long long) * static_cast<size_t>(src)));
 	GEN_CUDA(cudaMemsetAsync(st, 0, sizeof(orbit_state), stream));

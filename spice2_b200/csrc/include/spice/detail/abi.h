@@ -26,12 +26,13 @@ using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
 
 // One incoming connection as the target population's update kernel sees it.
 struct incoming {
-	std::uint32_t* counts; // [ring][n_local] event counters, slot = consume step % ring
-	float* accum;          // [ring][n_local] float contributions of stateful synapses (or null)
-	apply_fn apply;        // device function pointer (same module as the update kernel)
-	void const* functor;   // device copy of the Syn object
+	std::uint32_t* counts;     // [ring][cstride] event counters, slot = consume step % ring
+	std::int64_t cstride;      // row stride of counts (local targets rounded up to 8)
+	apply_fn apply;            // device function pointer (same module as the update kernel)
+	void const* functor;       // device copy of the Syn object
 	std::int32_t ring;
-	std::int32_t accum_word; // neuron word the accumulated float is added to (stateful synapses)
+	std::int32_t zero_after_read; // 1: the producer accumulates with atomics and expects zeroed counters;
+	                              // 0: the producer overwrites the whole slot (tiled delivery)
 };
 
 // Per-window random-access tables for the step streams: for every step of the window, the 128

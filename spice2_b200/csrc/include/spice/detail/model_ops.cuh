@@ -120,10 +120,11 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 		// fold in the events whose delivery the reference ran at the end of step t-1
 		for (int c = 0; c < a.n_in; c++) {
 			incoming const& in   = a.in[c];
-			std::int64_t const o = (t % in.ring) * a.n_local + ii;
+			std::int64_t const o = (t % in.ring) * in.cstride + ii;
 			unsigned const k     = active ? in.counts[o] : 0;
 			if (k) {
-				in.counts[o] = 0;
+				if (in.zero_after_read)
+					in.counts[o] = 0;
 				in.apply(in.functor, &n, k);
 			}
 		}
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) export_kernel(export_args a) {
 	N n = load_soa<N>(a.state, a.stride, i);
 	for (int c = 0; c < a.n_in; c++) {
 		incoming const& in = a.in[c];
-		unsigned const k   = in.counts[(a.t_next % in.ring) * a.n_local + i];
+		unsigned const k   = in.counts[(a.t_next % in.ring) * in.cstride + i];
 		if (k)
 			in.apply(in.functor, &n, k);
 	}

@@ -19,11 +19,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "deliver.h"
 #include "generator.h"
 #include "spice/detail/abi.h"
 #include "spice/util/numeric.h"
@@ -51,10 +53,13 @@ struct prologue_args {
 	int ring, world, rank;
 	long long t0;
 	int nsteps;
+	unsigned* work; // unit counter of the tiled delivery kernel
 };
 
 __global__ void __launch_bounds__(512) window_prologue(prologue_args a) {
 	int const s = blockIdx.x;
+	if (s == 0 && threadIdx.x == 0 && a.work)
+		*a.work = 0;
 	for (int p = threadIdx.x; p < a.npops; p += blockDim.x)
 		a.ring_cnt[p][((a.t0 + s) % a.ring) * a.world + a.rank] = 0;
 	if (!a.nib)
@@ -92,8 +97,8 @@ struct deliver_args {
 	long long seg_lo[kMaxWorld]; // first neuron of each rank's range in the source population
 	long long const* offsets;    // CSR (rows = all sources, local columns)
 	std::int32_t const* neighbors;
-	std::uint32_t* counts;       // [cring][n_dst_local]
-	long long n_dst_local;
+	std::uint32_t* counts;       // [cring][cstride]
+	long long cstride;
 	int cring;
 	long long delay;
 	long long t0;
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(256) deliver_counts(deliver_args a) {
 		long long const t   = a.t0 + s;
 		std::int32_t const src = a.ring_ids[(t % a.ring) * a.ring_cap + a.seg_lo[r] + (item - prefix[lo])];
 		long long const beg = a.offsets[src], end = a.offsets[src + 1];
-		std::uint32_t* cnt  = a.counts + ((t + a.delay) % a.cring) * a.n_dst_local;
+		std::uint32_t* cnt  = a.counts + ((t + a.delay) % a.cring) * a.cstride;
 		long long e = beg + lane;
 		for (; e + 96 < end; e += 128) {
 			std::int32_t const d0 = a.neighbors[e], d1 = a.neighbors[e + 32], d2 = a.neighbors[e + 64],
@@ -290,8 +295,13 @@ struct connection {
 	long long* offsets        = nullptr;
 	std::int32_t* neighbors   = nullptr;
 	long long edges           = 0;
-	std::uint32_t* counts     = nullptr; // [cring][n_dst_local]
+	std::uint32_t* counts     = nullptr; // [cring][cstride]
+	long long cstride         = 0;       // row stride of counts: n_dst_local rounded up to 8
 	apply_fn apply            = nullptr;
+	// tiled delivery (deliver.cu)
+	long long* tile_ptr       = nullptr; // [src][tiles + 1]
+	int tile = 0, tiles = 0;
+	bool duplicates           = false;   // rows may repeat a target (adj_list)
 };
 
 struct host_spikes {
@@ -326,6 +336,12 @@ struct spice_ctx {
 	unsigned char* peer_base[kMaxWorld] = {};
 	bool peers_set       = false;
 	unsigned long long seq = 0;
+
+	// delivery
+	bool tiled                        = true;    // SPICE_DELIVER=atomic selects the one-atomic-per-event kernel
+	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
+	unsigned* d_work                  = nullptr;
+	int total_tiles = 0, tile_cap = 0, n_desc = 0;
 
 	// device tables
 	std::uint32_t** d_ring_cnt        = nullptr; // [npops]
@@ -433,13 +449,76 @@ int finalize(spice_ctx* ctx) {
 	ctx->peer_base[ctx->rank] = ctx->xbase;
 
 	// connections: counters + incoming lists
+	{
+		char const* dm = std::getenv("SPICE_DELIVER");
+		ctx->tiled     = !(dm && std::string(dm) == "atomic");
+	}
+	long long target_len = 100; // column indices one warp-wide pass of the tiled kernel should find per row and tile
+	if (char const* tl = std::getenv("SPICE_TILE_LEN"))
+		target_len = std::max(8ll, std::atoll(tl));
 	for (size_t ci = 0; ci < ctx->conns.size(); ci++) {
 		auto& c           = ctx->conns[ci];
+		auto const& src   = ctx->pops[c.src];
 		auto const& dst   = ctx->pops[c.dst];
 		long long const n = std::max<long long>(dst.hi - dst.lo, 1);
-		CHECK_CUDA(ctx, cudaMalloc(&c.counts, sizeof(std::uint32_t) * static_cast<size_t>(ctx->cring) * static_cast<size_t>(n)));
-		CHECK_CUDA(ctx, cudaMemset(c.counts, 0, sizeof(std::uint32_t) * static_cast<size_t>(ctx->cring) * static_cast<size_t>(n)));
+		c.cstride         = static_cast<long long>(align_up(static_cast<size_t>(n), 8));
+		size_t const bytes = sizeof(std::uint32_t) * static_cast<size_t>(ctx->cring) * static_cast<size_t>(c.cstride);
+		CHECK_CUDA(ctx, cudaMalloc(&c.counts, bytes));
+		CHECK_CUDA(ctx, cudaMemset(c.counts, 0, bytes));
 		ctx->pops[c.dst].incoming.push_back(static_cast<int>(ci));
+		if (ctx->tiled && c.edges > 0 && dst.hi > dst.lo) {
+			// tile width: ~target_len entries of a row per tile, a multiple of 256, <= kTileMax
+			double const density = static_cast<double>(c.edges) / (static_cast<double>(std::max<long long>(src.size, 1)) * static_cast<double>(n));
+			long long b          = static_cast<long long>(static_cast<double>(target_len) / std::max(density, 1e-9));
+			b                    = std::clamp<long long>((b + 128) / 256 * 256, 256, deliver::kTileMax);
+			c.tiles              = static_cast<int>((n + b - 1) / b);
+			c.tile               = static_cast<int>(std::min<long long>(b, static_cast<long long>(align_up(static_cast<size_t>((n + c.tiles - 1) / c.tiles), 256))));
+			c.tiles              = static_cast<int>((n + c.tile - 1) / c.tile);
+			CHECK_CUDA(ctx, cudaMalloc(&c.tile_ptr, sizeof(long long) * static_cast<size_t>(src.size) * static_cast<size_t>(c.tiles + 1)));
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::build_tile_ptr(ctx->stream, c.offsets, c.neighbors, src.size, c.tile, c.tiles, c.tile_ptr)));
+			ctx->launches++;
+		}
+	}
+	if (ctx->tiled) {
+		// schedule order: connections whose sources emit the most spikes per step first (largest units first)
+		std::vector<int> order;
+		for (size_t ci = 0; ci < ctx->conns.size(); ci++)
+			if (ctx->conns[ci].tiles > 0)
+				order.push_back(static_cast<int>(ci));
+		std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->pops[ctx->conns[x].src].size > ctx->pops[ctx->conns[y].src].size; });
+		std::vector<deliver::conn_desc> descs;
+		for (int ci : order) {
+			connection const& c = ctx->conns[ci];
+			population const& src = ctx->pops[c.src];
+			population const& dst = ctx->pops[c.dst];
+			deliver::conn_desc d{};
+			d.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
+			d.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
+			d.ring_cap = std::max<long long>(src.size, 1);
+			for (int r = 0; r < ctx->world; r++)
+				d.seg_lo[r] = src.size * r / ctx->world;
+			d.neighbors   = c.neighbors;
+			d.tile_ptr    = c.tile_ptr;
+			d.counts      = c.counts;
+			d.n_dst       = dst.hi - dst.lo;
+			d.cstride     = c.cstride;
+			d.delay       = c.delay;
+			d.cring       = ctx->cring;
+			d.tiles       = c.tiles;
+			d.tile        = c.tile;
+			d.tile_prefix = ctx->total_tiles;
+			d.atomic      = c.duplicates ? 1 : 0;
+			ctx->total_tiles += c.tiles;
+			ctx->tile_cap = std::max(ctx->tile_cap, c.tile);
+			descs.push_back(d);
+		}
+		if (!descs.empty()) {
+			CHECK_CUDA(ctx, cudaMalloc(&ctx->d_conn_desc, sizeof(deliver::conn_desc) * descs.size()));
+			CHECK_CUDA(ctx, cudaMemcpy(ctx->d_conn_desc, descs.data(), sizeof(deliver::conn_desc) * descs.size(), cudaMemcpyHostToDevice));
+		}
+		ctx->n_desc = static_cast<int>(descs.size());
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_work, sizeof(unsigned)));
+		CHECK_CUDA(ctx, cudaMemset(ctx->d_work, 0, sizeof(unsigned)));
 	}
 	for (auto const& p : ctx->pops)
 		if (p.incoming.size() > static_cast<size_t>(kMaxIncoming))
@@ -515,7 +594,7 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	*n_in = static_cast<int>(p.incoming.size());
 	for (int k = 0; k < *n_in; k++) {
 		connection const& c = ctx->conns[p.incoming[k]];
-		in[k]               = incoming{c.counts, nullptr, c.apply, c.functor_dev, ctx->cring, 0};
+		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1};
 	}
 }
 
@@ -576,6 +655,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	pa.rank     = ctx->rank;
 	pa.t0       = ctx->time;
 	pa.nsteps   = nsteps;
+	pa.work     = ctx->d_work;
 	window_prologue<<<nsteps, 512, 0, ctx->stream>>>(pa);
 	ctx->launches++;
 
@@ -634,34 +714,53 @@ int run_window(spice_ctx* ctx, int nsteps) {
 
 	if (ctx->profile)
 		prof_mark(ctx);
-	for (auto& c : ctx->conns) {
-		population const& src = ctx->pops[c.src];
-		population const& dst = ctx->pops[c.dst];
-		if (dst.hi - dst.lo <= 0 || c.edges == 0)
-			continue;
-		deliver_args da{};
-		da.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
-		da.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
-		da.ring_cap = std::max<long long>(src.size, 1);
-		da.ring     = ctx->ring;
-		da.world    = ctx->world;
-		for (int r = 0; r < ctx->world; r++)
-			da.seg_lo[r] = src.seg_lo[r];
-		da.offsets     = c.offsets;
-		da.neighbors   = c.neighbors;
-		da.counts      = c.counts;
-		da.n_dst_local = dst.hi - dst.lo;
-		da.cring       = ctx->cring;
-		da.delay       = c.delay;
-		da.t0          = ctx->time;
-		da.nsteps      = nsteps;
-		da.stats       = ctx->d_stats;
-		// enough warps to cover the window's spikes at typical rates; the kernel strides
-		long long const est = std::max<long long>(1, src.size / 64) * nsteps;
-		int const blocks    = static_cast<int>(std::min<long long>(148 * 8, (est + 7) / 8));
-		deliver_counts<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(da);
-		ctx->launches++;
-	}
+	if (ctx->tiled) {
+		if (ctx->n_desc > 0) {
+			deliver::tiles_args ta{};
+			ta.conns       = ctx->d_conn_desc;
+			ta.nconns      = ctx->n_desc;
+			ta.total_tiles = ctx->total_tiles;
+			ta.ring        = ctx->ring;
+			ta.world       = ctx->world;
+			ta.t0          = ctx->time;
+			ta.nsteps      = nsteps;
+			ta.work        = ctx->d_work;
+			ta.stats       = ctx->d_stats;
+			ta.tile_cap    = ctx->tile_cap;
+			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device);
+			if (e != 0)
+				return fail(ctx, SPICE_ERR_CUDA, std::string("delivery launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+			ctx->launches++;
+		}
+	} else
+		for (auto& c : ctx->conns) {
+			population const& src = ctx->pops[c.src];
+			population const& dst = ctx->pops[c.dst];
+			if (dst.hi - dst.lo <= 0 || c.edges == 0)
+				continue;
+			deliver_args da{};
+			da.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
+			da.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
+			da.ring_cap = std::max<long long>(src.size, 1);
+			da.ring     = ctx->ring;
+			da.world    = ctx->world;
+			for (int r = 0; r < ctx->world; r++)
+				da.seg_lo[r] = src.seg_lo[r];
+			da.offsets     = c.offsets;
+			da.neighbors   = c.neighbors;
+			da.counts      = c.counts;
+			da.cstride     = c.cstride;
+			da.cring       = ctx->cring;
+			da.delay       = c.delay;
+			da.t0          = ctx->time;
+			da.nsteps      = nsteps;
+			da.stats       = ctx->d_stats;
+			// enough warps to cover the window's spikes at typical rates; the kernel strides
+			long long const est = std::max<long long>(1, src.size / 64) * nsteps;
+			int const blocks    = static_cast<int>(std::min<long long>(148 * 8, (est + 7) / 8));
+			deliver_counts<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(da);
+			ctx->launches++;
+		}
 
 	if (ctx->profile)
 		prof_mark(ctx);
@@ -815,6 +914,7 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 		cudaFree(c.offsets);
 		cudaFree(c.neighbors);
 		cudaFree(c.counts);
+		cudaFree(c.tile_ptr);
 	}
 	for (int r = 0; r < ctx->world; r++)
 		if (r != ctx->rank && ctx->peer_base[r] && ctx->peers_set) {
@@ -828,6 +928,8 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_seg_lo);
 	cudaFree(ctx->d_peer_cnt);
 	cudaFree(ctx->d_nib);
+	cudaFree(ctx->d_conn_desc);
+	cudaFree(ctx->d_work);
 	cudaFree(ctx->d_stats);
 	cudaFree(ctx->d_error);
 	cudaFree(ctx->d_cursor);
@@ -962,7 +1064,7 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 	c.edges = static_cast<long long>(nb.size());
 	CHECK_CUDA(ctx, cudaMalloc(&c.offsets, sizeof(long long) * offsets.size()));
 	CHECK_CUDA(ctx, cudaMemcpy(c.offsets, offsets.data(), sizeof(long long) * offsets.size(), cudaMemcpyHostToDevice));
-	CHECK_CUDA(ctx, cudaMalloc(&c.neighbors, sizeof(std::int32_t) * std::max<size_t>(nb.size(), 1)));
+	CHECK_CUDA(ctx, cudaMalloc(&c.neighbors, sizeof(std::int32_t) * (nb.size() + 8))); // +8: the delivery kernel reads whole 16-byte groups
 	CHECK_CUDA(ctx, cudaMemcpy(c.neighbors, nb.data(), sizeof(std::int32_t) * nb.size(), cudaMemcpyHostToDevice));
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
