@@ -39,6 +39,7 @@ struct tiles_args {
 	int nsteps;
 	unsigned* work;            // dynamic unit counter, zeroed by the window prologue
 	unsigned long long* stats; // [0] events, [1] spikes
+	int* error;                // bit 16: internal error in the delivery kernel
 	int tile_cap;              // u16 counters per warp in shared memory (max conns[].tile)
 };
 

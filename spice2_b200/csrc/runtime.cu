@@ -726,6 +726,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ta.nsteps      = nsteps;
 			ta.work        = ctx->d_work;
 			ta.stats       = ctx->d_stats;
+			ta.error       = ctx->d_error;
 			ta.tile_cap    = ctx->tile_cap;
 			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device);
 			if (e != 0)
@@ -802,6 +803,8 @@ int check_device_error(spice_ctx* ctx) {
 	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (h & 1)
 		return fail(ctx, SPICE_ERR_INTERNAL, "spike exchange timed out waiting for a peer rank");
+	if (h & 16)
+		return fail(ctx, SPICE_ERR_INTERNAL, "spike delivery: internal error (pipeline made no progress)");
 	if (h & 4)
 		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: step capacity exceeded (read the raster more often)");
 	if (h & 8)
