@@ -51,6 +51,9 @@ struct update_args {
 	std::int64_t stride;
 	std::int64_t t0;        // first step of the window (snn::_time)
 	std::int32_t nsteps;
+	std::int32_t cring;     // length of the incoming connections' counter rings, and the window's first slot in it
+	std::int32_t cslot0;    // = t0 % cring
+	std::int32_t rslot0;    // = t0 % ring (spike ring slot of the window's first step)
 	float dt[kMaxWindow];   // kahan-compensated dt of each step (snn.cpp:8)
 	// spike ring: ids[(step % ring) * cap + seg_base + j], cnt[(step % ring) * world + rank]
 	std::int32_t* ring_ids[kMaxWorld]; // this rank's copy first ([rank]); peers' copies for direct stores

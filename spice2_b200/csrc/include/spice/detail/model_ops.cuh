@@ -91,11 +91,15 @@ struct counting_rng {
 // ---- apply: k deliveries of a stateless synapse to one neuron ------------------------------------
 template <class Syn, class DstNeur>
 __device__ void apply_impl(void const* functor, void* neuron, unsigned k) {
-	Syn const& syn = *static_cast<Syn const*>(functor);
-	auto& n        = *static_cast<typename DstNeur::neuron*>(neuron);
 	if constexpr (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+		// work on register copies: the k deliveries are a dependent chain of the functor's own
+		// float operations, nothing else
+		using N       = typename DstNeur::neuron;
+		Syn const syn = *static_cast<Syn const*>(functor);
+		N n           = *static_cast<N*>(neuron);
 		for (unsigned j = 0; j < k; j++)
 			syn.deliver(n);
+		*static_cast<N*>(neuron) = n;
 	}
 }
 template <class Syn, class DstNeur>
@@ -115,25 +119,42 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 	std::int32_t const my_id = static_cast<std::int32_t>(a.lo + i);
 	null_rng rng;
 
+	// event counters of the step, one per incoming connection; the next step's are fetched while
+	// this step's are applied (they were all written before this window began)
+	unsigned kk[kMaxIncoming];
+	// (all incoming connections share one counter ring length; slots advance with the step)
+	auto fetch = [&](int s, int cslot, unsigned (&k)[kMaxIncoming]) {
+#pragma unroll
+		for (int c = 0; c < kMaxIncoming; c++) {
+			k[c] = 0;
+			if (c < a.n_in && active && s < a.nsteps)
+				k[c] = a.in[c].counts[cslot * a.in[c].cstride + ii];
+		}
+	};
+	int cslot = a.cslot0, rslot = a.rslot0;
+	fetch(0, cslot, kk);
+
 	for (int s = 0; s < a.nsteps; s++) {
-		std::int64_t const t = a.t0 + s;
+		int const cnext      = cslot + 1 == a.cring ? 0 : cslot + 1;
+		unsigned kn[kMaxIncoming];
+		fetch(s + 1, cnext, kn);
 		// fold in the events whose delivery the reference ran at the end of step t-1
-		for (int c = 0; c < a.n_in; c++) {
-			incoming const& in   = a.in[c];
-			std::int64_t const o = (t % in.ring) * in.cstride + ii;
-			unsigned const k     = active ? in.counts[o] : 0;
-			if (k) {
+#pragma unroll
+		for (int c = 0; c < kMaxIncoming; c++) {
+			if (c < a.n_in && kk[c]) {
+				incoming const& in = a.in[c];
 				if (in.zero_after_read)
-					in.counts[o] = 0;
-				in.apply(in.functor, &n, k);
+					in.counts[cslot * in.cstride + ii] = 0;
+				in.apply(in.functor, &n, kk[c]);
 			}
+			kk[c] = kn[c];
 		}
 		bool const spiked = active && neur.update(n, a.dt[s], rng);
 		hist              = (hist << 1) | (spiked ? 1u : 0u);
 
 		unsigned const m = __ballot_sync(0xffffffffu, spiked);
 		if (m) {
-			std::int64_t const slot = t % a.ring;
+			std::int64_t const slot = rslot;
 			unsigned base           = 0;
 			if ((threadIdx.x & 31) == 0)
 				base = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], __popc(m));
@@ -144,6 +165,8 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 					a.ring_ids[r][at] = my_id;
 			}
 		}
+		cslot = cnext;
+		rslot = rslot + 1 == a.ring ? 0 : rslot + 1;
 	}
 	if (active) {
 		store_soa<N>(a.state, a.stride, i, n);

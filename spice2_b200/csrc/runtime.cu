@@ -670,6 +670,9 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		ua.stride  = p.stride;
 		ua.t0      = ctx->time;
 		ua.nsteps  = nsteps;
+		ua.cring   = ctx->cring;
+		ua.cslot0  = static_cast<int>(ctx->time % ctx->cring);
+		ua.rslot0  = static_cast<int>(ctx->time % ctx->ring);
 		std::memcpy(ua.dt, dts, sizeof(float) * nsteps);
 		for (int r = 0; r < ctx->world; r++)
 			ua.ring_ids[r] = xptr<std::int32_t>(ctx->peer_base[r], p.ring_ids_off);
