@@ -270,9 +270,9 @@ def main():
             traffic = json.loads(tf.read_text()).get("deliver_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "deliver_counts (6 launches per 15-step window)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "deliver_tiles (1 launch per 15-step window, all 6 connections)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes / max(1, prof["windows"] * 6),
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, prof["windows"]),
                 "deliver_ms_total": prof["deliver_ms"], "update_ms_total": prof["update_ms"],
                 "exchange_ms_total": prof["exchange_ms"], "windows": prof["windows"],
                 "deliver_share_of_step": deliver_ms_max / ms_max}
