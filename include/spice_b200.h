@@ -194,6 +194,11 @@ SPICE_API void spice_seed_next(uint64_t seed[2]);
 SPICE_API spice_neuron_ops const* spice_builtin_neuron(char const* name);
 SPICE_API spice_synapse_ops const* spice_builtin_synapse(char const* name);
 
+/* Diagnostics: evaluate on the DEVICE the libm restatements user models reach through
+ * spice/util/math.h, so tests can pin them against the host libm the reference links:
+ * kind 0: y[i] = exp((float)x[i]) (x, y float32); kind 1: y[i] = pow(x[i], n[i]) (x, y float64, n int64). */
+SPICE_API int spice_selftest_libm(int device, int kind, void const* x, int64_t const* n, void* y, int64_t count);
+
 /* device probe: 0 when a CUDA device with compute capability 10.x is usable */
 SPICE_API int spice_device_check(int device);
 SPICE_API char const* spice_version(void);

@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
             "spice_seed_next": (None, [vp]),
             "spice_builtin_neuron": (vp, [C.c_char_p]),
             "spice_builtin_synapse": (vp, [C.c_char_p]),
+            "spice_selftest_libm": (i32, [i32, i32, vp, vp, vp, i64]),
             "spice_device_check": (i32, [i32]),
             "spice_version": (C.c_char_p, []),
         }
@@ -113,6 +114,11 @@ SYNAPSE_MODELS = {
     "brunel.fixed_weight": lambda weight: struct.pack("<f", np.float32(weight)),
     "vogels.excitatory": lambda weight: struct.pack("<f", np.float32(weight)),
     "vogels.inhibitory": lambda weight: struct.pack("<f", np.float32(weight)),
+    "brunel+.plastic": lambda: b"\0",
+}
+# per-synapse state of the stateful synapse models (csr<T>::_edges, csr.h:99)
+SYNAPSE_STATE = {
+    "brunel+.plastic": np.dtype([("W", np.float32), ("Zpre", np.float32), ("Zpost", np.float32)]),
 }
 
 
@@ -253,6 +259,13 @@ class snn:
         nb = np.zeros(max(n.value, 1), np.int32)
         self._check(lib().spice_connection_csr(self._h, conn, C.byref(n), _ptr(off), _ptr(nb)))
         return off, nb[: n.value]
+
+    def connection_synapses(self, conn: int) -> np.ndarray:
+        """csr<T>::_edges of a stateful connection (csr.h:99), parallel to connection_csr()[1]."""
+        dt = SYNAPSE_STATE[self.connections[conn][0]]
+        out = np.zeros(self.connection_edges(conn), dt)
+        self._check(lib().spice_connection_synapses(self._h, conn, _ptr(out), out.nbytes))
+        return out
 
     def connection_edges(self, conn: int) -> int:
         n = C.c_int64()

@@ -24,15 +24,58 @@ struct u128 {
 // reference does event by event (synapse_population.h:118-133).
 using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
 
+// Device function applying the `n` events of one step that a stateful connection addressed to
+// one neuron: `list` holds the edge indices (arrival order); it is sorted ascending — the
+// reference's (source, row) order (synapse_population.h:88,99) — and Syn::deliver(synapse, neuron)
+// is called for each, reading the synapse state word-SoA (word w of edge e at syn[w*stride + e]).
+using apply_events_fn = void (*)(void const* functor, void* neuron, std::uint32_t const* syn, std::int64_t syn_stride,
+                                 std::int32_t* list, unsigned n);
+
 // One incoming connection as the target population's update kernel sees it.
 struct incoming {
-	std::uint32_t* counts;     // [ring][cstride] event counters, slot = consume step % ring
+	std::uint32_t* counts;     // stateless synapses: [ring][cstride] event counters, slot = consume step % ring
 	std::int64_t cstride;      // row stride of counts (local targets rounded up to 8)
 	apply_fn apply;            // device function pointer (same module as the update kernel)
 	void const* functor;       // device copy of the Syn object
 	std::int32_t ring;
 	std::int32_t zero_after_read; // 1: the producer accumulates with atomics and expects zeroed counters;
 	                              // 0: the producer overwrites the whole slot (tiled delivery)
+	// stateful synapses (evt_cnt != null): the events of the step that just ran, per target
+	std::uint32_t* evt_cnt;        // [n_local] events addressed to each neuron (zeroed by the consumer)
+	std::uint32_t const* evt_off;  // [n_local] where the neuron's events start in evt_list
+	std::int32_t* evt_list;        // edge indices
+	std::uint32_t const* syn;      // synapse state, word-SoA
+	std::int64_t syn_stride;
+	apply_events_fn apply_events;
+};
+
+// One step of a stateful connection (launched by the runtime through spice_synapse_ops).
+struct stateful_args {
+	void* stream;
+	void const* functor;            // device copy of the Syn object
+	std::int32_t phase;             // 0 visit (catch-up + count), 1 reserve, 2 fill, 3 flush (all sources, no delivery)
+	// spikes to deliver: the source population's ring slot of step time - (delay - 1)
+	std::int32_t const* ring_ids;   // slot base
+	std::uint32_t const* ring_cnt;  // [world] counts of the slot
+	std::int64_t seg_lo[kMaxWorld];
+	std::int32_t world;
+	std::int64_t n_src, n_dst;      // all sources; local targets
+	std::int64_t const* offsets;    // CSR (rows = all sources, local columns)
+	std::int32_t const* neighbors;
+	std::uint32_t* syn;             // word-SoA synapse state
+	std::int64_t syn_stride;
+	std::uint64_t const* dst_history; // [n_dst] 64-bit spike history of the local targets (plastic only)
+	std::uint64_t* ages;              // [n_src] (last visit + 1) | delivered << 63 (synapse_population.h:89-94,137-138)
+	std::int64_t time;                // snn::_time
+	float dt;                         // the nominal dt (snn.cpp:19,23)
+	std::uint32_t* evt_cnt;
+	std::uint32_t* evt_off;
+	std::uint32_t* evt_fill;
+	unsigned long long* evt_cursor;
+	std::int32_t* evt_list;
+	std::int64_t evt_cap;
+	unsigned long long* stats;        // [0] events, [1] spikes
+	int* error;                       // bit 32: event list capacity exceeded
 };
 
 // Per-window random-access tables for the step streams: for every step of the window, the 128
@@ -116,5 +159,12 @@ struct spice_synapse_ops {
 	std::uint32_t deliver_from_to; // deliver takes the source neuron (unsupported on this path yet)
 	// device function pointer of apply<Syn, DstNeur>, fetched from the module that holds the kernels
 	int (*get_apply)(spice::detail::apply_fn* out);
+	// stateful synapses: default-construct `n_edges` synapses (AoS) and run the model's init hook, if any,
+	// over the CSR in row order with an engine seeded by (seed_lo, seed_hi) (synapse_population.h:34-41)
+	std::uint32_t per_synapse_init; // the hook exists (it consumes one seed++)
+	void (*init_host)(void const* functor, void* out_aos, std::int64_t const* offsets, std::int32_t const* neighbors,
+	                  std::int64_t n_src, std::uint64_t seed_lo, std::uint64_t seed_hi);
+	int (*get_apply_events)(spice::detail::apply_events_fn* out);
+	int (*launch_stateful)(spice::detail::stateful_args const*);
 };
 }

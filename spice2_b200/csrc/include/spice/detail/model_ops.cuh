@@ -105,6 +105,147 @@ __device__ void apply_impl(void const* functor, void* neuron, unsigned k) {
 template <class Syn, class DstNeur>
 __device__ apply_fn apply_ptr = apply_impl<Syn, DstNeur>;
 
+// ---- stateful / plastic synapses -------------------------------------------------------------------
+// apply_events: the events one stateful connection addressed to one neuron in the step that just ran
+template <class Syn, class DstNeur>
+__device__ void apply_events_impl(void const* functor, void* neuron, std::uint32_t const* syn, std::int64_t syn_stride,
+                                  std::int32_t* list, unsigned n) {
+	if constexpr (StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+		using N = typename DstNeur::neuron;
+		using S = typename Syn::synapse;
+		for (unsigned i = 1; i < n; i++) { // insertion sort: ascending edge index = (source, row) order
+			std::int32_t const key = list[i];
+			int j                  = static_cast<int>(i) - 1;
+			for (; j >= 0 && list[j] > key; j--)
+				list[j + 1] = list[j];
+			list[j + 1] = key;
+		}
+		Syn const f = *static_cast<Syn const*>(functor);
+		N nn        = *static_cast<N*>(neuron);
+		for (unsigned i = 0; i < n; i++) {
+			S const sy = load_soa<S>(syn, syn_stride, list[i]);
+			f.deliver(sy, nn);
+		}
+		*static_cast<N*>(neuron) = nn;
+	}
+}
+template <class Syn, class DstNeur>
+__device__ apply_events_fn apply_events_ptr = apply_events_impl<Syn, DstNeur>;
+
+// Lazy plasticity: bring one synapse from step `age` up to and including step `time`
+// (synapse_population.h:95-116 with Outdated == true).  hist bit j = the target fired at step time - j.
+template <class Syn>
+__device__ __forceinline__ void catch_up(Syn const& f, typename Syn::synapse& sy, float dt, std::uint64_t hist, bool pre,
+                                         std::int64_t time, std::int64_t age) {
+	std::int64_t const prefix = 63 + (pre ? 1 : 0) - time + age;
+	// the reference shifts by `prefix` unguarded (UB at 64, only reachable when a source delivers in
+	// two consecutive steps); the intended value is taken here: no history bits left
+	std::uint64_t const mask = prefix >= 64 ? 0 : (prefix <= 0 ? ~std::uint64_t(0) : ~std::uint64_t(0) >> prefix);
+	if (pre)
+		f.update(sy, dt, true, (hist & (std::uint64_t(1) << (time - age))) != 0);
+	hist &= mask;
+	std::int64_t p = prefix;
+	while (hist) {
+		int const lz = __clzll(static_cast<long long>(hist));
+		f.skip(sy, dt, static_cast<Int>(lz - p));
+		f.update(sy, dt, false, true);
+		hist ^= std::uint64_t(1) << (63 - lz);
+		p = lz + 1;
+	}
+	f.skip(sy, dt, static_cast<Int>(64 - p));
+}
+
+// One warp per visited source: Deliver = true walks the spikes of the delivered step (catch the row's
+// synapses up, count one event per edge for its target), Deliver = false (the 64-step flush,
+// snn.cpp:17-19) walks every source and only catches up.
+template <class Syn, bool Deliver>
+__global__ void __launch_bounds__(256) stateful_visit_kernel(stateful_args a) {
+	using S              = typename Syn::synapse;
+	int const lane       = threadIdx.x & 31;
+	std::int64_t const w = (static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	std::int64_t const W = (static_cast<std::int64_t>(gridDim.x) * blockDim.x) >> 5;
+	Syn const f          = *static_cast<Syn const*>(a.functor);
+	if (Deliver && blockIdx.x == 0 && threadIdx.x == 0)
+		*a.evt_cursor = 0;
+	unsigned long long ev = 0, sp = 0;
+	int const nseg = Deliver ? a.world : 1;
+	for (int r = 0; r < nseg; r++) {
+		std::int64_t const n = Deliver ? a.ring_cnt[r] : a.n_src;
+		for (std::int64_t j = w; j < n; j += W) {
+			std::int64_t const src = Deliver ? a.ring_ids[a.seg_lo[r] + j] : j;
+			std::int64_t const beg = a.offsets[src], end = a.offsets[src + 1];
+			bool pre = false, outdated = false;
+			std::int64_t age = a.time + 1;
+			if constexpr (PlasticSynapse<Syn>) {
+				std::uint64_t const g = a.ages[src];
+				pre                   = (g >> 63) != 0;
+				age                   = static_cast<std::int64_t>(g & ~(std::uint64_t(1) << 63));
+				outdated              = a.time >= age;
+			}
+			for (std::int64_t e = beg + lane; e < end; e += 32) {
+				std::int32_t const dst = a.neighbors[e];
+				if constexpr (PlasticSynapse<Syn>) {
+					if (outdated) {
+						S sy = load_soa<S>(a.syn, a.syn_stride, e);
+						catch_up(f, sy, a.dt, a.dst_history[dst], pre, a.time, age);
+						store_soa<S>(a.syn, a.syn_stride, e, sy);
+					}
+				}
+				if constexpr (Deliver)
+					atomicAdd(a.evt_cnt + dst, 1u);
+			}
+			if constexpr (PlasticSynapse<Syn>) {
+				__syncwarp();
+				if (lane == 0)
+					a.ages[src] = static_cast<std::uint64_t>(a.time + 1) | (std::uint64_t(Deliver ? 1 : 0) << 63);
+			}
+			ev += static_cast<unsigned long long>(end - beg);
+			sp++;
+		}
+	}
+	if (Deliver && lane == 0 && sp) {
+		atomicAdd(a.stats + 0, ev);
+		atomicAdd(a.stats + 1, sp);
+	}
+}
+
+// every target with events reserves its part of the event list
+__global__ void __launch_bounds__(256) stateful_reserve_kernel(stateful_args a) {
+	std::int64_t const i = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= a.n_dst)
+		return;
+	unsigned const c = a.evt_cnt[i];
+	a.evt_fill[i]    = 0;
+	if (c) {
+		unsigned long long const at = atomicAdd(a.evt_cursor, static_cast<unsigned long long>(c));
+		if (at + c > static_cast<unsigned long long>(a.evt_cap)) {
+			atomicOr(a.error, 32);
+			a.evt_cnt[i] = 0; // dropped (reported as an error by the next synchronising call)
+		} else
+			a.evt_off[i] = static_cast<std::uint32_t>(at);
+	}
+}
+
+__global__ void __launch_bounds__(256) stateful_fill_kernel(stateful_args a) {
+	int const lane       = threadIdx.x & 31;
+	std::int64_t const w = (static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	std::int64_t const W = (static_cast<std::int64_t>(gridDim.x) * blockDim.x) >> 5;
+	for (int r = 0; r < a.world; r++) {
+		std::int64_t const n = a.ring_cnt[r];
+		for (std::int64_t j = w; j < n; j += W) {
+			std::int64_t const src = a.ring_ids[a.seg_lo[r] + j];
+			std::int64_t const beg = a.offsets[src], end = a.offsets[src + 1];
+			for (std::int64_t e = beg + lane; e < end; e += 32) {
+				std::int32_t const dst = a.neighbors[e];
+				if (a.evt_cnt[dst]) {
+					unsigned const k                   = atomicAdd(a.evt_fill + dst, 1u);
+					a.evt_list[a.evt_off[dst] + k] = static_cast<std::int32_t>(e);
+				}
+			}
+		}
+	}
+}
+
 // ---- stateful neurons: one thread per neuron, whole window --------------------------------------
 template <class Neur>
 __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
@@ -127,7 +268,7 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 #pragma unroll
 		for (int c = 0; c < kMaxIncoming; c++) {
 			k[c] = 0;
-			if (c < a.n_in && active && s < a.nsteps)
+			if (c < a.n_in && active && s < a.nsteps && !a.in[c].evt_cnt)
 				k[c] = a.in[c].counts[cslot * a.in[c].cstride + ii];
 		}
 	};
@@ -146,6 +287,14 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 				if (in.zero_after_read)
 					in.counts[cslot * in.cstride + ii] = 0;
 				in.apply(in.functor, &n, kk[c]);
+			}
+			if (c < a.n_in && a.in[c].evt_cnt && active) { // stateful synapses: this step's event list (window = 1 step)
+				incoming const& in = a.in[c];
+				unsigned const ne  = in.evt_cnt[ii];
+				if (ne) {
+					in.evt_cnt[ii] = 0;
+					in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[ii], ne);
+				}
 			}
 			kk[c] = kn[c];
 		}
@@ -244,7 +393,13 @@ __global__ void __launch_bounds__(256) export_kernel(export_args a) {
 	N n = load_soa<N>(a.state, a.stride, i);
 	for (int c = 0; c < a.n_in; c++) {
 		incoming const& in = a.in[c];
-		unsigned const k   = in.counts[(a.t_next % in.ring) * in.cstride + i];
+		if (in.evt_cnt) {
+			unsigned const ne = in.evt_cnt[i];
+			if (ne)
+				in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[i], ne);
+			continue;
+		}
+		unsigned const k = in.counts[(a.t_next % in.ring) * in.cstride + i];
 		if (k)
 			in.apply(in.functor, &n, k);
 	}
@@ -349,6 +504,45 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 		static int get_apply(apply_fn* out) {
 			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_ptr<Syn, DstNeur>, sizeof(apply_fn)));
 		}
+		static int get_apply_events(apply_events_fn* out) {
+			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_events_ptr<Syn, DstNeur>, sizeof(apply_events_fn)));
+		}
+		static void init_host(void const* functor, void* out, std::int64_t const* offsets, std::int32_t const* neighbors,
+		                      std::int64_t n_src, std::uint64_t seed_lo, std::uint64_t seed_hi) {
+			if constexpr (StatefulSynapse<Syn>) {
+				using S = typename Syn::synapse;
+				S* v    = static_cast<S*>(out);
+				for (std::int64_t e = 0; e < offsets[n_src]; e++)
+					new (v + e) S();
+				if constexpr (PerSynapseInit<Syn>) { // synapse_population.h:34-41
+					Syn const f = *static_cast<Syn const*>(functor);
+					util::xoroshiro64_128p rng(seed_lo, seed_hi);
+					for (std::int64_t src = 0; src < n_src; src++)
+						for (std::int64_t e = offsets[src]; e < offsets[src + 1]; e++)
+							f.init(v[e], src, neighbors[e], rng);
+				}
+			}
+			(void)functor, (void)out, (void)offsets, (void)neighbors, (void)n_src, (void)seed_lo, (void)seed_hi;
+		}
+		static int launch_stateful(stateful_args const* a) {
+			if constexpr (StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+				auto stream = static_cast<cudaStream_t>(a->stream);
+				switch (a->phase) {
+				case 0: stateful_visit_kernel<Syn, true><<<148 * 4, 256, 0, stream>>>(*a); break;
+				case 1:
+					if (a->n_dst > 0)
+						stateful_reserve_kernel<<<grid_for(a->n_dst), 256, 0, stream>>>(*a);
+					break;
+				case 2: stateful_fill_kernel<<<148 * 4, 256, 0, stream>>>(*a); break;
+				case 3:
+					if constexpr (PlasticSynapse<Syn>)
+						stateful_visit_kernel<Syn, false><<<148 * 8, 256, 0, stream>>>(*a);
+					break;
+				}
+			}
+			(void)a;
+			return static_cast<int>(cudaGetLastError());
+		}
 	};
 	constexpr std::uint32_t syn_bytes = [] {
 		if constexpr (StatefulSynapse<Syn>)
@@ -363,7 +557,11 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 	                                   static_cast<std::uint32_t>(sizeof(typename DstNeur::neuron)),
 	                                   PlasticSynapse<Syn> ? 1u : 0u,
 	                                   DeliverTo<Syn, DstNeur> ? 0u : 1u,
-	                                   &B::get_apply};
+	                                   &B::get_apply,
+	                                   PerSynapseInit<Syn> ? 1u : 0u,
+	                                   &B::init_host,
+	                                   &B::get_apply_events,
+	                                   &B::launch_stateful};
 	return &ops;
 }
 }

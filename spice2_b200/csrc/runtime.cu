@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(256) raster_pack(raster_args a) {
 	}
 }
 
+__global__ void fill_u32(std::uint32_t* dst, long long n, std::uint32_t value) {
+	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n)
+		dst[i] = value;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host state
 // ---------------------------------------------------------------------------------------------
@@ -302,6 +308,16 @@ struct connection {
 	long long* tile_ptr       = nullptr; // [src][tiles + 1]
 	int tile = 0, tiles = 0;
 	bool duplicates           = false;   // rows may repeat a target (adj_list)
+	// stateful / plastic synapses (window = 1 step; spice/detail/model_ops.cuh)
+	bool stateful = false, plastic = false;
+	std::uint32_t* syn        = nullptr; // word-SoA synapse state, parallel to neighbors
+	long long syn_stride      = 0;
+	std::uint64_t* ages       = nullptr; // [src] (synapse_population.h:89-94)
+	std::uint32_t *evt_cnt = nullptr, *evt_off = nullptr, *evt_fill = nullptr;
+	unsigned long long* evt_cursor = nullptr;
+	std::int32_t* evt_list    = nullptr;
+	long long evt_cap         = 0;
+	apply_events_fn apply_events = nullptr;
 };
 
 struct host_spikes {
@@ -327,7 +343,7 @@ struct spice_ctx {
 
 	// geometry
 	int window = 1, ring = 1, cring = 1;
-	bool any_rng = false;
+	bool any_rng = false, any_stateful = false;
 
 	// exchange region (spike rings, counters, flags)
 	unsigned char* xbase = nullptr;
@@ -429,6 +445,13 @@ int finalize(spice_ctx* ctx) {
 		dmax = std::max(dmax, c.delay);
 	}
 	ctx->window = static_cast<int>(std::max<long long>(1, std::min<long long>(dmin, kMaxWindow)));
+	for (auto const& c : ctx->conns)
+		if (c.stateful) {
+			// a stateful synapse's delivery at step t depends on its target's spikes up to step t
+			// (lazy plasticity) and is consumed at step t + 1: such networks advance step by step
+			ctx->window       = 1;
+			ctx->any_stateful = true;
+		}
 	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay, 2ll * ctx->window));
 	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
 
@@ -466,7 +489,29 @@ int finalize(spice_ctx* ctx) {
 		CHECK_CUDA(ctx, cudaMalloc(&c.counts, bytes));
 		CHECK_CUDA(ctx, cudaMemset(c.counts, 0, bytes));
 		ctx->pops[c.dst].incoming.push_back(static_cast<int>(ci));
-		if (ctx->tiled && c.edges > 0 && dst.hi > dst.lo) {
+		if (c.stateful) {
+			c.evt_cap = std::max<long long>(1, std::min<long long>(c.edges, 1ll << 28));
+			CHECK_CUDA(ctx, cudaMalloc(&c.evt_cnt, sizeof(std::uint32_t) * static_cast<size_t>(n)));
+			CHECK_CUDA(ctx, cudaMalloc(&c.evt_off, sizeof(std::uint32_t) * static_cast<size_t>(n)));
+			CHECK_CUDA(ctx, cudaMalloc(&c.evt_fill, sizeof(std::uint32_t) * static_cast<size_t>(n)));
+			CHECK_CUDA(ctx, cudaMalloc(&c.evt_cursor, sizeof(unsigned long long)));
+			CHECK_CUDA(ctx, cudaMalloc(&c.evt_list, sizeof(std::int32_t) * static_cast<size_t>(c.evt_cap)));
+			CHECK_CUDA(ctx, cudaMemset(c.evt_cnt, 0, sizeof(std::uint32_t) * static_cast<size_t>(n)));
+			CHECK_CUDA(ctx, cudaMemset(c.evt_cursor, 0, sizeof(unsigned long long)));
+			if (c.plastic) {
+				CHECK_CUDA(ctx, cudaMalloc(&c.ages, sizeof(std::uint64_t) * static_cast<size_t>(std::max<long long>(src.size, 1))));
+				CHECK_CUDA(ctx, cudaMemset(c.ages, 0, sizeof(std::uint64_t) * static_cast<size_t>(std::max<long long>(src.size, 1))));
+				// the lazy updates read the TARGET's spike history (snn.cpp:19,25); the reference
+				// allocates it on the source (snn.h:46-47), which is the same population whenever
+				// the reference's own behaviour is defined
+				population& dp = ctx->pops[c.dst];
+				if (!dp.history) {
+					CHECK_CUDA(ctx, cudaMalloc(&dp.history, sizeof(std::uint64_t) * static_cast<size_t>(n)));
+					CHECK_CUDA(ctx, cudaMemset(dp.history, 0, sizeof(std::uint64_t) * static_cast<size_t>(n)));
+				}
+			}
+		}
+		if (ctx->tiled && !c.stateful && c.edges > 0 && dst.hi > dst.lo) {
 			// tile width: ~target_len entries of a row per tile, a multiple of 256, <= kTileMax
 			double const density = static_cast<double>(c.edges) / (static_cast<double>(std::max<long long>(src.size, 1)) * static_cast<double>(n));
 			long long b          = static_cast<long long>(static_cast<double>(target_len) / std::max(density, 1e-9));
@@ -594,7 +639,8 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	*n_in = static_cast<int>(p.incoming.size());
 	for (int k = 0; k < *n_in; k++) {
 		connection const& c = ctx->conns[p.incoming[k]];
-		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1};
+		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1,
+		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events};
 	}
 }
 
@@ -717,6 +763,59 @@ int run_window(spice_ctx* ctx, int nsteps) {
 
 	if (ctx->profile)
 		prof_mark(ctx);
+	if (ctx->any_stateful) {
+		// nsteps == 1 here.  snn.cpp:17-25: every 64 steps catch every plastic synapse up, then deliver
+		// the spikes emitted delay - 1 steps ago, connection by connection
+		for (int pass = 0; pass < 2; pass++)
+			for (auto& c : ctx->conns) {
+				if (!c.stateful)
+					continue;
+				population const& src = ctx->pops[c.src];
+				population const& dst = ctx->pops[c.dst];
+				if (dst.hi - dst.lo <= 0)
+					continue;
+				if (pass == 0 && !(c.plastic && ctx->time % 64 == 0))
+					continue;
+				if (pass == 1 && ctx->time < c.delay - 1)
+					continue;
+				long long const slot = (ctx->time - (c.delay - 1) + ctx->ring) % ctx->ring;
+				stateful_args sa{};
+				sa.stream   = ctx->stream;
+				sa.functor  = c.functor_dev;
+				sa.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off) + slot * std::max<long long>(src.size, 1);
+				sa.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off) + slot * ctx->world;
+				for (int r = 0; r < ctx->world; r++)
+					sa.seg_lo[r] = src.size * r / ctx->world;
+				sa.world       = ctx->world;
+				sa.n_src       = src.size;
+				sa.n_dst       = dst.hi - dst.lo;
+				sa.offsets     = reinterpret_cast<std::int64_t const*>(c.offsets);
+				sa.neighbors   = c.neighbors;
+				sa.syn         = c.syn;
+				sa.syn_stride  = c.syn_stride;
+				sa.dst_history = dst.history;
+				sa.ages        = c.ages;
+				sa.time        = ctx->time;
+				sa.dt          = ctx->dt;
+				sa.evt_cnt     = c.evt_cnt;
+				sa.evt_off     = c.evt_off;
+				sa.evt_fill    = c.evt_fill;
+				sa.evt_cursor  = c.evt_cursor;
+				sa.evt_list    = c.evt_list;
+				sa.evt_cap     = c.evt_cap;
+				sa.stats       = ctx->d_stats;
+				sa.error       = ctx->d_error;
+				for (int phase : {pass == 0 ? 3 : 0, 1, 2}) {
+					sa.phase    = phase;
+					int const e = c.ops->launch_stateful(&sa);
+					if (e != 0)
+						return fail(ctx, SPICE_ERR_CUDA, std::string("stateful delivery launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+					ctx->launches++;
+					if (pass == 0)
+						break;
+				}
+			}
+	}
 	if (ctx->tiled) {
 		if (ctx->n_desc > 0) {
 			deliver::tiles_args ta{};
@@ -740,7 +839,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		for (auto& c : ctx->conns) {
 			population const& src = ctx->pops[c.src];
 			population const& dst = ctx->pops[c.dst];
-			if (dst.hi - dst.lo <= 0 || c.edges == 0)
+			if (dst.hi - dst.lo <= 0 || c.edges == 0 || c.stateful)
 				continue;
 			deliver_args da{};
 			da.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
@@ -808,6 +907,8 @@ int check_device_error(spice_ctx* ctx) {
 		return fail(ctx, SPICE_ERR_INTERNAL, "spike exchange timed out waiting for a peer rank");
 	if (h & 16)
 		return fail(ctx, SPICE_ERR_INTERNAL, "spike delivery: internal error (pipeline made no progress)");
+	if (h & 32)
+		return fail(ctx, SPICE_ERR_INTERNAL, "stateful delivery: event list capacity exceeded");
 	if (h & 4)
 		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: step capacity exceeded (read the raster more often)");
 	if (h & 8)
@@ -825,8 +926,11 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	long long const d = static_cast<long long>(std::round(delay / ctx->dt)); // snn.h:33
 	PRE(ctx, d >= 1 && "The delay must be at least 1dt.");                 // snn.h:35
 	PRE(ctx, d <= ctx->max_delay && "The delay of a synapse population may not exceed the maximum delay of the network."); // snn.h:36-38
-	if (ops->synapse_bytes != 0 || ops->plastic || ops->deliver_from_to)
-		return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateful / plastic / deliver-from-to synapses are not on the GPU path yet");
+	if (ops->deliver_from_to)
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, "synapses whose deliver() reads the source neuron are not on the GPU path yet");
+	PRE(ctx, ops->synapse_bytes % 4 == 0);
+	c->stateful = ops->synapse_bytes != 0;
+	c->plastic  = ops->plastic != 0;
 	c->ops   = ops;
 	c->src   = src_pop;
 	c->dst   = dst_pop;
@@ -834,9 +938,58 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	c->functor_host.assign(static_cast<unsigned char const*>(functor), static_cast<unsigned char const*>(functor) + ops->functor_bytes);
 	CHECK_CUDA(ctx, cudaMalloc(&c->functor_dev, std::max<size_t>(ops->functor_bytes, 16)));
 	CHECK_CUDA(ctx, cudaMemcpy(c->functor_dev, functor, ops->functor_bytes, cudaMemcpyHostToDevice));
-	int const e = ops->get_apply(&c->apply);
+	int e = ops->get_apply(&c->apply);
+	if (e == 0 && c->stateful)
+		e = ops->get_apply_events(&c->apply_events);
 	if (e != 0)
 		return fail(ctx, SPICE_ERR_CUDA, std::string("get_apply: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+	return SPICE_OK;
+}
+
+// per-synapse state of a stateful connection: default-constructed synapses, then the model's init
+// hook (synapse_population.h:34-41), stored word-SoA parallel to the CSR
+int init_synapses(spice_ctx* ctx, connection* c) {
+	if (!c->stateful)
+		return SPICE_OK;
+	PRE(ctx, c->edges < 2147483647ll && "a stateful connection holds at most 2^31 - 1 synapses per rank");
+	int const words       = static_cast<int>(c->ops->synapse_bytes / 4);
+	population const& src = ctx->pops[c->src];
+	population const& dst = ctx->pops[c->dst];
+	c->syn_stride         = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(c->edges, 1)), 32));
+	CHECK_CUDA(ctx, cudaMalloc(&c->syn, sizeof(std::uint32_t) * static_cast<size_t>(words) * static_cast<size_t>(c->syn_stride)));
+	if (c->ops->per_synapse_init) {
+		if (ctx->world != 1)
+			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
+		UInt128 const sd = (ctx->seed++).seed(); // the hook's own engine (synapse_population.h:35)
+		std::vector<long long> off(static_cast<size_t>(src.size) + 1);
+		std::vector<std::int32_t> nb(static_cast<size_t>(std::max<long long>(c->edges, 1)));
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CHECK_CUDA(ctx, cudaMemcpy(off.data(), c->offsets, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost));
+		if (c->edges)
+			CHECK_CUDA(ctx, cudaMemcpy(nb.data(), c->neighbors, sizeof(std::int32_t) * static_cast<size_t>(c->edges), cudaMemcpyDeviceToHost));
+		for (auto& d : nb)
+			d += static_cast<std::int32_t>(dst.lo);
+		std::vector<unsigned char> aos(static_cast<size_t>(std::max<long long>(c->edges, 1)) * c->ops->synapse_bytes);
+		c->ops->init_host(c->functor_host.data(), aos.data(), reinterpret_cast<std::int64_t const*>(off.data()), nb.data(), src.size, sd.lo, sd.hi);
+		std::vector<std::uint32_t> soa(static_cast<size_t>(words) * static_cast<size_t>(c->syn_stride), 0);
+		for (long long e = 0; e < c->edges; e++)
+			for (int w = 0; w < words; w++)
+				std::memcpy(&soa[static_cast<size_t>(w) * c->syn_stride + e], aos.data() + e * c->ops->synapse_bytes + 4 * w, 4);
+		CHECK_CUDA(ctx, cudaMemcpy(c->syn, soa.data(), sizeof(std::uint32_t) * soa.size(), cudaMemcpyHostToDevice));
+	} else {
+		// one default-constructed synapse, replicated
+		std::int64_t const one_off[2] = {0, 1};
+		std::int32_t const one_nb  = 0;
+		std::vector<unsigned char> one(c->ops->synapse_bytes);
+		c->ops->init_host(c->functor_host.data(), one.data(), one_off, &one_nb, 1, 0, 0);
+		for (int w = 0; w < words; w++) {
+			std::uint32_t v;
+			std::memcpy(&v, one.data() + 4 * w, 4);
+			fill_u32<<<static_cast<unsigned>((c->syn_stride + 255) / 256), 256, 0, ctx->stream>>>(c->syn + static_cast<size_t>(w) * c->syn_stride, c->syn_stride, v);
+			ctx->launches++;
+		}
+		CHECK_CUDA(ctx, cudaGetLastError());
+	}
 	return SPICE_OK;
 }
 } // namespace
@@ -921,6 +1074,13 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 		cudaFree(c.neighbors);
 		cudaFree(c.counts);
 		cudaFree(c.tile_ptr);
+		cudaFree(c.syn);
+		cudaFree(c.ages);
+		cudaFree(c.evt_cnt);
+		cudaFree(c.evt_off);
+		cudaFree(c.evt_fill);
+		cudaFree(c.evt_cursor);
+		cudaFree(c.evt_list);
 	}
 	for (int r = 0; r < ctx->world; r++)
 		if (r != ctx->rank && ctx->peer_base[r] && ctx->peers_set) {
@@ -1030,6 +1190,9 @@ int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops
 	c.neighbors = r.neighbors;
 	c.edges     = r.edges;
 	ctx->launches += r.launches;
+	rc = init_synapses(ctx, &c);
+	if (rc != SPICE_OK)
+		return rc;
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
 		*conn_out = static_cast<int>(ctx->conns.size()) - 1;
@@ -1072,6 +1235,12 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 	CHECK_CUDA(ctx, cudaMemcpy(c.offsets, offsets.data(), sizeof(long long) * offsets.size(), cudaMemcpyHostToDevice));
 	CHECK_CUDA(ctx, cudaMalloc(&c.neighbors, sizeof(std::int32_t) * (nb.size() + 8))); // +8: the delivery kernel reads whole 16-byte groups
 	CHECK_CUDA(ctx, cudaMemcpy(c.neighbors, nb.data(), sizeof(std::int32_t) * nb.size(), cudaMemcpyHostToDevice));
+	for (size_t i = 1; i < packed.size(); i++)
+		if (packed[i] == packed[i - 1])
+			c.duplicates = true; // a multapse: rows may repeat a target
+	rc = init_synapses(ctx, &c);
+	if (rc != SPICE_OK)
+		return rc;
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
 		*conn_out = static_cast<int>(ctx->conns.size()) - 1;
@@ -1094,8 +1263,20 @@ int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t
 
 int spice_connection_synapses(spice_ctx* ctx, int conn, void* out, int64_t bytes) {
 	PRE(ctx, conn >= 0 && conn < static_cast<int>(ctx->conns.size()));
-	(void)out, (void)bytes;
-	return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateless connection: no per-synapse state");
+	connection const& c = ctx->conns[conn];
+	if (!c.stateful)
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateless connection: no per-synapse state");
+	PRE(ctx, bytes == c.edges * static_cast<int64_t>(c.ops->synapse_bytes));
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	int const words = static_cast<int>(c.ops->synapse_bytes / 4);
+	std::vector<std::uint32_t> soa(static_cast<size_t>(words) * static_cast<size_t>(c.syn_stride));
+	CHECK_CUDA(ctx, cudaMemcpy(soa.data(), c.syn, sizeof(std::uint32_t) * soa.size(), cudaMemcpyDeviceToHost));
+	auto* o = static_cast<unsigned char*>(out);
+	for (long long e = 0; e < c.edges; e++)
+		for (int w = 0; w < words; w++)
+			std::memcpy(o + e * c.ops->synapse_bytes + 4 * w, &soa[static_cast<size_t>(w) * c.syn_stride + e], 4);
+	return SPICE_OK;
 }
 
 int spice_ctx_finalize(spice_ctx* ctx) { return finalize(ctx); }

@@ -171,3 +171,67 @@ def test_two_ranks_one_device(sp, orc):
     for _ in range(14):
         onet.step()
     assert sum(net.stats()["synaptic_events"] for net, _ in nets) == onet.events()
+
+
+# ---- plastic synapses (samples/brunel+.cpp): lazy event-driven STDP --------------------------------
+# Parity contract: the plastic path calls libm (expf, pow).  expf is restated
+# bit-exactly, pow(base, n) is evaluated correctly rounded, which glibc's pow is except in rare
+# near-halfway cases, so the comparison below is exact in practice; the stated tolerance is what
+# the test falls back to if a last-bit libm difference ever shows.
+PLASTIC_V_TOL = 1e-5   # volts, on membrane potentials of ~1e-2
+PLASTIC_W_TOL = 1e-9   # on weights of ~1e-4
+
+
+def _close_or_equal(got, want, fields, tol):
+    if np.array_equal(got, want):
+        return True
+    return all(np.allclose(got[f], want[f], rtol=0, atol=tol) for f in fields)
+
+
+def test_brunel_plus_step_by_step(sp, orc):
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=3000, p=0.1, w_exc=np.float32(2.0 / 300), w_inh=np.float32(-10.0 / 300), seed=(5,), plastic=True)
+    net, pops = brunel(**kw)
+    onet, opops = brunel_oracle(orc, **kw)
+    for step in range(200):
+        net.step()
+        onet.step()
+        for p, op in zip(pops, opops):
+            assert np.array_equal(p.spikes(0), onet.spikes(op, 0)), step
+        if step % 20 == 19 or step in (63, 64, 65, 127, 128, 129):
+            assert _close_or_equal(pops[1].get_neurons(), onet.neurons(1), ("V",), PLASTIC_V_TOL), step
+            assert _close_or_equal(pops[2].get_neurons(), onet.neurons(2), ("V",), PLASTIC_V_TOL), step
+    got, want = net.connection_synapses(2), onet.connection_synapses(2)
+    assert _close_or_equal(got, want, ("W", "Zpre", "Zpost"), PLASTIC_W_TOL)
+    for _ in range(14):
+        onet.step()
+
+
+def test_brunel_plus_300_golden(sp, orc, golden):
+    """samples/brunel+ (N = 20000, 300 steps): raster of the compiled reference (strict flavour)."""
+    from spice2_b200.samples import brunel
+
+    g = golden["samples"]["brunel_plus_300_strict"]
+    net, (P, E, I) = brunel(plastic=True)
+    counts, ids = gpu_raster(net, 300, 50)
+    assert [int(x) for x in counts.sum(0)] == g["totals"]
+    assert hx(orc.fnv(ids)) == g["fnv_ids"]
+
+
+def test_device_libm_matches_host_pins(sp):
+    """exp(float) and pow(double, n) as the plastic model evaluates them on the device vs the host
+    glibc values the reference would compute (tests/golden/libm_pins.npz, from the compiled reference's
+    process).  expf is a bit-exact restatement; pow must be exact on the 65 values skip() can ask for."""
+    from pathlib import Path
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "libm_pins.npz")
+    x = np.ascontiguousarray(z["expf_x"], np.float32)
+    y = np.zeros_like(x)
+    assert sp.lib().spice_selftest_libm(0, 0, x.ctypes.data, None, y.ctypes.data, len(x)) == 0
+    assert np.array_equal(y.view(np.uint32), z["expf_y"].astype(np.float32).view(np.uint32))
+    px = np.ascontiguousarray(z["pow_x"], np.float64)
+    pn = np.ascontiguousarray(z["pow_n"], np.int64)
+    py = np.zeros_like(px)
+    assert sp.lib().spice_selftest_libm(0, 1, px.ctypes.data, pn.ctypes.data, py.ctypes.data, len(px)) == 0
+    assert np.array_equal(py.view(np.uint64), z["pow_y"].astype(np.float64).view(np.uint64))

@@ -85,6 +85,7 @@ def hosttool(tmp_path_factory):
 #include <cmath>
 #include <cstring>
 #include "spice/detail/glibc_log.h"
+#include "spice/detail/glibc_expf.h"
 #include "spice/util/random.h"
 #include "spice/util/numeric.h"
 using namespace spice::util;
@@ -92,6 +93,9 @@ int main(int argc, char** argv) {
 	if (!strcmp(argv[1], "log")) {   // stdin: doubles as hex bit patterns; stdout: log bits
 		unsigned long long u;
 		while (scanf("%llx", &u) == 1) printf("%016llx\n", (unsigned long long)spice::detail::glibc::double_to_bits(spice::detail::glibc::log(spice::detail::glibc::bits_to_double(u))));
+	} else if (!strcmp(argv[1], "expf")) { // stdin: floats as hex bit patterns; stdout: expf bits
+		unsigned u;
+		while (scanf("%x", &u) == 1) { float x; memcpy(&x, &u, 4); float y = spice::detail::glibc::expf_restated(x); memcpy(&u, &y, 4); printf("%08x\n", u); }
 	} else if (!strcmp(argv[1], "jump")) { // args: lo hi k -> state after k steps via jump polynomial
 		xoroshiro64_128p s(strtoull(argv[2], 0, 16), strtoull(argv[3], 0, 16));
 		auto r = jump::apply(jump::xpow(strtoull(argv[4], 0, 10)), s);
@@ -117,6 +121,15 @@ def test_glibc_log_restatement_matches_golden_pins(hosttool):
     out = subprocess.run([str(hosttool), "log"], input=inp, capture_output=True, text=True, check=True).stdout.split()
     got = np.array([int(v, 16) for v in out], np.uint64)
     assert np.array_equal(got, y.view(np.uint64))
+
+
+def test_glibc_expf_restatement_matches_golden_pins(hosttool):
+    z = np.load(ROOT / "tests" / "golden" / "libm_pins.npz")
+    x, y = z["expf_x"].astype(np.float32), z["expf_y"].astype(np.float32)
+    inp = "\n".join(f"{int(v):x}" for v in x.view(np.uint32))
+    out = subprocess.run([str(hosttool), "expf"], input=inp, capture_output=True, text=True, check=True).stdout.split()
+    got = np.array([int(v, 16) for v in out], np.uint32)
+    assert np.array_equal(got, y.view(np.uint32))
 
 
 def test_jump_ahead_matches_sequential(hosttool, orc):
