@@ -97,8 +97,16 @@ __device__ void apply_impl(void const* functor, void* neuron, unsigned k) {
 		using N       = typename DstNeur::neuron;
 		Syn const syn = *static_cast<Syn const*>(functor);
 		N n           = *static_cast<N*>(neuron);
-		for (unsigned j = 0; j < k; j++)
-			syn.deliver(n);
+		// k sequential deliveries: the remainder first (predicated), then groups of 8 back to back
+#pragma unroll
+		for (unsigned u = 1; u < 8; u++)
+			if (u <= (k & 7u))
+				syn.deliver(n);
+		for (unsigned j = k >> 3; j; j--) {
+#pragma unroll
+			for (int u = 0; u < 8; u++)
+				syn.deliver(n);
+		}
 		*static_cast<N*>(neuron) = n;
 	}
 }
@@ -247,8 +255,13 @@ __global__ void __launch_bounds__(256) stateful_fill_kernel(stateful_args a) {
 }
 
 // ---- stateful neurons: one thread per neuron, whole window --------------------------------------
-template <class Neur>
-__global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
+// NIN = number of incoming connections the loops are unrolled for; Generic = false promises that
+// a.n_in == NIN, that every incoming connection is a stateless one fed by the tiled delivery kernel
+// (counters never need zeroing) — the common case, with nothing but the loads, the calls and the
+// model's own arithmetic left in the loop.  Generic = true handles everything else (stateful
+// synapses' event lists, the atomic delivery mode, up to kMaxIncoming connections).
+template <class Neur, int NIN, bool Generic>
+__global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) {
 	using N                  = typename Neur::neuron;
 	std::int64_t const i     = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	bool const active        = i < a.n_local;
@@ -259,41 +272,51 @@ __global__ void __launch_bounds__(256) update_stateful_kernel(update_args a) {
 	std::uint64_t hist       = (a.history && active) ? a.history[ii] : 0;
 	std::int32_t const my_id = static_cast<std::int32_t>(a.lo + i);
 	null_rng rng;
+	constexpr int C = NIN > 0 ? NIN : 1;
 
 	// event counters of the step, one per incoming connection; the next step's are fetched while
-	// this step's are applied (they were all written before this window began)
-	unsigned kk[kMaxIncoming];
-	// (all incoming connections share one counter ring length; slots advance with the step)
-	auto fetch = [&](int s, int cslot, unsigned (&k)[kMaxIncoming]) {
+	// this step's are applied (they were all written before this window began).  All incoming
+	// connections share one counter ring length; slots advance with the step.
+	std::uint32_t const* cp[C];
+	unsigned kk[C];
 #pragma unroll
-		for (int c = 0; c < kMaxIncoming; c++) {
-			k[c] = 0;
-			if (c < a.n_in && active && s < a.nsteps && !a.in[c].evt_cnt)
-				k[c] = a.in[c].counts[cslot * a.in[c].cstride + ii];
+	for (int c = 0; c < C; c++) {
+		cp[c] = nullptr;
+		kk[c] = 0;
+		if (c < NIN && active && (!Generic || (c < a.n_in && !a.in[c].evt_cnt))) {
+			cp[c] = a.in[c].counts + ii;
+			kk[c] = cp[c][static_cast<std::int64_t>(a.cslot0) * a.in[c].cstride];
 		}
-	};
+	}
 	int cslot = a.cslot0, rslot = a.rslot0;
-	fetch(0, cslot, kk);
 
 	for (int s = 0; s < a.nsteps; s++) {
-		int const cnext      = cslot + 1 == a.cring ? 0 : cslot + 1;
-		unsigned kn[kMaxIncoming];
-		fetch(s + 1, cnext, kn);
+		int const cnext = cslot + 1 == a.cring ? 0 : cslot + 1;
+		unsigned kn[C];
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			kn[c] = 0;
+			if (c < NIN && s + 1 < a.nsteps && cp[c])
+				kn[c] = cp[c][static_cast<std::int64_t>(cnext) * a.in[c].cstride];
+		}
 		// fold in the events whose delivery the reference ran at the end of step t-1
 #pragma unroll
-		for (int c = 0; c < kMaxIncoming; c++) {
-			if (c < a.n_in && kk[c]) {
+		for (int c = 0; c < C; c++) {
+			if (c < NIN && kk[c]) {
 				incoming const& in = a.in[c];
-				if (in.zero_after_read)
-					in.counts[cslot * in.cstride + ii] = 0;
+				if constexpr (Generic)
+					if (in.zero_after_read)
+						in.counts[cslot * in.cstride + ii] = 0;
 				in.apply(in.functor, &n, kk[c]);
 			}
-			if (c < a.n_in && a.in[c].evt_cnt && active) { // stateful synapses: this step's event list (window = 1 step)
-				incoming const& in = a.in[c];
-				unsigned const ne  = in.evt_cnt[ii];
-				if (ne) {
-					in.evt_cnt[ii] = 0;
-					in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[ii], ne);
+			if constexpr (Generic) {
+				if (c < a.n_in && a.in[c].evt_cnt && active) { // stateful synapses: this step's event list (window = 1 step)
+					incoming const& in = a.in[c];
+					unsigned const ne  = in.evt_cnt[ii];
+					if (ne) {
+						in.evt_cnt[ii] = 0;
+						in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[ii], ne);
+					}
 				}
 			}
 			kk[c] = kn[c];
@@ -444,8 +467,22 @@ struct neuron_ops_builder {
 		auto stream = static_cast<cudaStream_t>(a->stream);
 		if constexpr (StatefulNeuron<Neur>) {
 			static_assert(rng_draws_v<Neur> == 0, "stateful neurons that draw from the rng are not supported yet");
-			if (a->n_local > 0)
-				update_stateful_kernel<Neur><<<grid_for(a->n_local), 256, 0, stream>>>(*a);
+			if (a->n_local > 0) {
+				bool fast = a->n_in <= 4;
+				for (int c = 0; c < a->n_in; c++)
+					fast = fast && !a->in[c].evt_cnt && !a->in[c].zero_after_read;
+				int const grid = grid_for(a->n_local, 128);
+				if (!fast)
+					update_stateful_kernel<Neur, kMaxIncoming, true><<<grid, 128, 0, stream>>>(*a);
+				else
+					switch (a->n_in) {
+					case 0: update_stateful_kernel<Neur, 0, false><<<grid, 128, 0, stream>>>(*a); break;
+					case 1: update_stateful_kernel<Neur, 1, false><<<grid, 128, 0, stream>>>(*a); break;
+					case 2: update_stateful_kernel<Neur, 2, false><<<grid, 128, 0, stream>>>(*a); break;
+					case 3: update_stateful_kernel<Neur, 3, false><<<grid, 128, 0, stream>>>(*a); break;
+					default: update_stateful_kernel<Neur, 4, false><<<grid, 128, 0, stream>>>(*a); break;
+					}
+			}
 		} else {
 			std::int64_t const items = ((a->n_local + kRngChunk - 1) / kRngChunk) * a->nsteps;
 			if (items > 0)
