@@ -12,16 +12,26 @@
 // Layout of the work:
 //   * the targets of a connection are cut into tiles of <= 5120 neurons; tile_ptr[src][k] says
 //     where tile k's share of row src starts (built once per connection), so a tile's share of
-//     a row is one contiguous run of ~p * tile column indices;
+//     a row is one contiguous run of ~p * tile entries;
 //   * a unit = (connection, step of the window, tile).  A CTA of 4 warps owns a unit.  Every
-//     warp keeps its own copy of the tile's counters as u16 in 10 KB of shared memory and takes
-//     every 4th batch of 32 spikes of the step's spike list; it streams each spiking source's
-//     run with one 16-byte load per lane (16 runs in flight, in registers) and counts with
-//     non-atomic shared-memory read-modify-writes — inside a warp no barrier and no atomic;
-//   * at the end the CTA adds its four copies and stores the tile's counters to
-//     counts[slot(step + delay)][tile] with plain vector stores: it is the only writer of that
-//     range, and the target's update kernel (the only reader) runs in a later window.  Units
-//     are handed out by a global counter to a persistent grid, heaviest connections first.
+//     warp keeps its own counters for the tile in 10 KB of shared memory and takes every 4th
+//     batch of 32 spikes of the step's spike list; it streams each spiking source's run with
+//     one 16-byte load per lane (16 runs in flight, in registers) and counts with non-atomic
+//     shared-memory read-modify-writes — inside a warp no barrier and no atomic;
+//   * bank conflicts.  A counting instruction scatters 32 lanes over the tile; at random that
+//     costs ~3.1 shared-memory wavefronts per instruction instead of 1 and made the first
+//     version of this kernel LSU-bound at 39 % of the HBM roofline.  So every target has TWO
+//     u8 counters (arrays A and B, whose bank assignments differ by a per-row rotation), and
+//     once per connection arrange_runs() rewrites each run: every entry becomes the byte
+//     address of one of its target's two counters, chosen (2-choice balancing) and ordered so
+//     that the lanes of one instruction fall into different banks.  The canonical ascending
+//     order of a run is recovered by decoding and sorting (restore_runs);
+//   * a u8 counter holds 255: a warp counts at most 224 runs (7 batches) per round; after each
+//     round the CTA adds its 4 x 2 arrays and stores (first round) or adds (later rounds) the
+//     tile's counters to counts[slot(step + delay)][tile] with plain vector accesses: it is the
+//     only writer of that range, and the target's update kernel (the only reader) runs in a
+//     later window.  Units are handed out by a global counter to a persistent grid, heaviest
+//     connections first.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -34,40 +44,36 @@ namespace {
 constexpr int kWarps       = 4;  // warps per CTA: they share a unit, each with its own copy of the tile
 constexpr int kCtasPerSm   = 4;  // register budget: 16 warps per SM
 constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane and run, in registers)
+constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
 constexpr unsigned kFull   = 0xffffffffu;
-constexpr unsigned kU16Max = 65535u;
 
 // count the (up to 4) entries of `v` that lie inside the run: entry i has index e0 + i, valid
-// when 0 <= e0 + i < len.  The four targets are distinct, so loads may all precede the stores.
-template <bool Atomic>
-__device__ __forceinline__ void tally(unsigned short* cnt, int4 v, int e0, int len, int lo) {
+// when 0 <= e0 + i < len.  Entries are counter addresses (arrange_runs); the four targets are
+// distinct, so the loads may all precede the stores.
+__device__ __forceinline__ void tally(unsigned char* cnt, int4 v, int e0, int len) {
 	bool const p0 = static_cast<unsigned>(e0) < static_cast<unsigned>(len);
 	bool const p1 = static_cast<unsigned>(e0 + 1) < static_cast<unsigned>(len);
 	bool const p2 = static_cast<unsigned>(e0 + 2) < static_cast<unsigned>(len);
 	bool const p3 = static_cast<unsigned>(e0 + 3) < static_cast<unsigned>(len);
-	int const t0 = v.x - lo, t1 = v.y - lo, t2 = v.z - lo, t3 = v.w - lo;
-	if constexpr (Atomic) {
-		unsigned* w = reinterpret_cast<unsigned*>(cnt);
-		if (p0) atomicAdd(w + (t0 >> 1), 1u << ((t0 & 1) * 16));
-		if (p1) atomicAdd(w + (t1 >> 1), 1u << ((t1 & 1) * 16));
-		if (p2) atomicAdd(w + (t2 >> 1), 1u << ((t2 & 1) * 16));
-		if (p3) atomicAdd(w + (t3 >> 1), 1u << ((t3 & 1) * 16));
-	} else {
-		unsigned short c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-		if (p0) c0 = cnt[t0];
-		if (p1) c1 = cnt[t1];
-		if (p2) c2 = cnt[t2];
-		if (p3) c3 = cnt[t3];
-		if (p0) cnt[t0] = c0 + 1;
-		if (p1) cnt[t1] = c1 + 1;
-		if (p2) cnt[t2] = c2 + 1;
-		if (p3) cnt[t3] = c3 + 1;
-	}
+	unsigned char c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+	if (p0) c0 = cnt[v.x];
+	if (p1) c1 = cnt[v.y];
+	if (p2) c2 = cnt[v.z];
+	if (p3) c3 = cnt[v.w];
+	if (p0) cnt[v.x] = c0 + 1;
+	if (p1) cnt[v.y] = c1 + 1;
+	if (p2) cnt[v.z] = c2 + 1;
+	if (p3) cnt[v.w] = c3 + 1;
 }
 
-__device__ __forceinline__ void zero_tile(uint4* cnt4, int words16, int lane) {
-	for (int i = lane; i < words16; i += 32)
-		cnt4[i] = make_uint4(0, 0, 0, 0);
+// zero counters [0, bytes) of array A and of array B (bytes a multiple of 128)
+__device__ __forceinline__ void zero_tile(unsigned char* cnt, int cap, int bytes, int lane) {
+	uint4* a4 = reinterpret_cast<uint4*>(cnt);
+	uint4* b4 = reinterpret_cast<uint4*>(cnt + cap);
+	for (int i = lane; i < bytes / 16; i += 32) {
+		a4[i] = make_uint4(0, 0, 0, 0);
+		b4[i] = make_uint4(0, 0, 0, 0);
+	}
 	__syncwarp();
 }
 
@@ -84,10 +90,10 @@ struct run_desc {
 	int mis;               // entries of that group that precede the run (0..3)
 };
 
-// shared memory of one warp: [descriptors: 2 batches x 32 x 16 B][counters: tile_cap x 2 B]
+// shared memory of one warp: [descriptors: 2 batches x 32 x 16 B][counters: 2 arrays x tile_cap x 1 B]
 constexpr int kDescBytes = 2 * 32 * static_cast<int>(sizeof(run_desc));
 __host__ __device__ constexpr size_t warp_smem(int tile_cap) {
-	return static_cast<size_t>(kDescBytes) + static_cast<size_t>(tile_cap) * sizeof(unsigned short);
+	return static_cast<size_t>(kDescBytes) + 2 * static_cast<size_t>(tile_cap);
 }
 
 // What a unit needs to know, worked out once per CTA.
@@ -110,21 +116,18 @@ struct unit_info {
 //   * registers: the column indices of the next kRing runs on their way from HBM (one 16-byte
 //     load per lane and run), and the run being counted.
 // The loop over a half batch is fully unrolled, so the kRing landing slots are plain registers.
-// Guarded = true adds the u16 overflow guard (spill the counters to global memory with atomics
-// before any of them can wrap) and uses it for the final flush as well.
-template <bool Atomic, bool Guarded>
+// One call counts the batches of one round (at most kRoundBatches, so no u8 counter can wrap).
 struct unit_walker {
 	tiles_args const& a;
 	unit_info const& U;
 	unsigned char* smem; // this warp's
 	int lane;
-	unsigned short* cnt;
+	unsigned char* cnt;
 	unsigned my_n, my_first;
 	long long p_beg; // this lane's run of the batch whose descriptors are written next
 	int p_len;
 	std::int32_t id_next; // this lane's spike of the batch after that
 	long long ev;
-	unsigned acc; // runs counted since the counters were last zeroed
 
 	__device__ __forceinline__ std::int32_t spike_id(unsigned q) const { // flat index -> source neuron (0 when q >= total)
 		int r       = 0;
@@ -147,27 +150,9 @@ struct unit_walker {
 			p_len              = static_cast<int>(p[1] - p_beg);
 		}
 	}
-	// add this warp's counters to global memory with atomics and clear them (rare path)
-	__device__ __forceinline__ void spill_atomic() {
-		__syncwarp();
-		for (int i = lane; i < U.width; i += 32) {
-			unsigned const c = cnt[i];
-			if (c)
-				atomicAdd(U.out + i, c);
-		}
-		__syncwarp();
-		zero_tile(reinterpret_cast<uint4*>(cnt), (U.width + 7) / 8, lane);
-		acc = 0;
-	}
-
 	// publish the descriptors of the i-th batch of this warp (from p_beg / p_len), then start
 	// fetching the pointers of batch `b_next` and the ids of batch `b_next + step`
 	__device__ __forceinline__ void write_desc(unsigned i, unsigned b_next, unsigned step) {
-		if constexpr (Guarded) {
-			if (acc + 64 + kRing > kU16Max)
-				spill_atomic();
-			acc += 32;
-		}
 		ev += p_len;
 		int const mis = static_cast<int>(p_beg & 3);
 		run_desc d;
@@ -195,7 +180,7 @@ struct unit_walker {
 				int4 w = make_int4(0, 0, 0, 0);
 				if (e0 + off < r.len)
 					w = ldg_stream(g + off * 4);
-				tally<Atomic>(cnt, w, e0 + off, r.len, U.lo);
+				tally(cnt, w, e0 + off, r.len);
 			}
 			__syncwarp();
 		}
@@ -204,7 +189,7 @@ struct unit_walker {
 
 	// batches first, first + step, ... (< nbatch)
 	__device__ __forceinline__ void run(unsigned first, unsigned step, unsigned nbatch) {
-		cnt = reinterpret_cast<unsigned short*>(smem + kDescBytes);
+		cnt = smem + kDescBytes;
 		// the step's spike list: one segment per rank; lane r keeps segment r's start in the flat order
 		my_n = 0;
 		if (lane < a.world)
@@ -217,8 +202,8 @@ struct unit_walker {
 		}
 		my_first -= my_n; // exclusive prefix
 
-		zero_tile(reinterpret_cast<uint4*>(cnt), (U.width + 7) / 8, lane);
-		ev = 0, acc = 0;
+		zero_tile(cnt, a.tile_cap, (U.width + 127) & ~127, lane);
+		ev = 0;
 		unsigned const mine = first < nbatch ? (nbatch - first + step - 1) / step : 0; // batches of this warp
 		if (mine > 0) {
 			id_next = spike_id(first * 32 + lane);
@@ -242,14 +227,12 @@ struct unit_walker {
 #pragma unroll
 				for (int j = 0; j < kRing; j++) {
 					int2 const m = *reinterpret_cast<int2 const*>(&cd[j].len);
-					tally<Atomic>(cnt, v[j], lane * 4 - m.y, m.x, U.lo);
+					tally(cnt, v[j], lane * 4 - m.y, m.x);
 					__syncwarp();
 					v[j] = issue(id + j);
 				}
 			}
 		}
-		if constexpr (Guarded)
-			spill_atomic();
 		for (int off = 16; off; off >>= 1)
 			ev += __shfl_xor_sync(kFull, ev, off);
 		if (lane == 0 && ev)
@@ -257,12 +240,26 @@ struct unit_walker {
 	}
 };
 
-// the rare variants (rows with repeated targets; more spikes in a step than u16 counters can
-// take) stay out of line so that they do not cost the common one registers
-__device__ __noinline__ void walk_slow(tiles_args const& a, unit_info const& U, unsigned char* smem, int lane, unsigned first,
-                                       unsigned step, unsigned nbatch) {
-	unit_walker<true, true> w{a, U, smem, lane};
-	w.run(first, step, nbatch);
+// Rare path, out of line: connections whose entries are plain columns (rows that may repeat a
+// target: adj_list multapses).  One global atomic per event into the tile's (zeroed) range.
+__device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U, int lane, int warp) {
+	unsigned const world = static_cast<unsigned>(a.world);
+	long long ev         = 0;
+	unsigned q0          = 0;
+	for (unsigned r = 0; r < world; r++) {
+		unsigned const n = U.C->ring_cnt[U.ring_slot * a.world + r];
+		for (unsigned j = warp; j < n; j += kWarps) {
+			long long const id  = U.ids0[U.C->seg_lo[r] + j];
+			long long const* tp = U.tile_ptr + id * U.stride;
+			long long const beg = tp[0], end = tp[1];
+			for (long long e = beg + lane; e < end; e += 32)
+				atomicAdd(U.out + (U.C->neighbors[e] - U.lo), 1u);
+			ev += end - beg;
+		}
+		q0 += n;
+	}
+	if (lane == 0 && ev)
+		atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
 }
 
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_args a) {
@@ -305,35 +302,182 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 		if (claimed >= units)
 			break;
 		unsigned const nbatch = (U.total + 31) / 32;
-		int const words16     = (U.width + 7) / 8;
-		// every warp can take at most kU16Max runs before a counter could wrap
-		bool const big = (nbatch + kWarps - 1) / kWarps * 32 + 64 + kRing > kU16Max;
-		if (U.C->atomic || big) {
-			// rare: counters go to global memory with atomics; clear the tile's range first
-			for (int i = threadIdx.x; i < words16 * 8; i += kWarps * 32)
+		int const words       = (U.width + 3) / 4; // 4 targets per 32-bit word of u8 counters
+		if (!U.C->arranged) {
+			for (int i = threadIdx.x; i < words * 4; i += kWarps * 32)
 				U.out[i] = 0;
-			__threadfence();
+			__threadfence_block();
 			__syncthreads();
-			walk_slow(a, U, smem, lane, warp, kWarps, nbatch);
+			walk_plain(a, U, lane, warp);
 			__syncthreads();
-		} else {
-			unit_walker<false, false> w{a, U, smem, lane};
-			w.run(warp, kWarps, nbatch);
+			continue;
+		}
+		constexpr unsigned per_round = kWarps * kRoundBatches;
+		unsigned const rounds        = max(1u, (nbatch + per_round - 1) / per_round);
+		for (unsigned round = 0; round < rounds; round++) {
+			unsigned const b0 = round * per_round;
+			unit_walker w{a, U, smem, lane};
+			w.run(b0 + warp, kWarps, min(nbatch, b0 + per_round));
 			__syncthreads();
-			// add the warps' copies and store: this CTA is the only writer of the range
+			// add the warps' arrays and store / accumulate: this CTA is the only writer of the range.
+			// Word wd of array A holds targets 4 wd .. 4 wd + 3; their B counters sit in the same
+			// 128-byte row r = wd / 32, rotated by r words.
 			uint4* o = reinterpret_cast<uint4*>(U.out);
-			for (int i = threadIdx.x; i < words16; i += kWarps * 32) {
-				uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
+			for (int wd = threadIdx.x; wd < words; wd += kWarps * 32) {
+				int const r = wd >> 5;
+				int const wb = (wd & ~31) | ((wd + r) & 31);
+				unsigned even = 0, odd = 0; // two 16-bit lanes each: targets (0, 2) and (1, 3)
 #pragma unroll
 				for (int w2 = 0; w2 < kWarps; w2++) {
-					uint4 const c = reinterpret_cast<uint4 const*>(reinterpret_cast<unsigned char*>(smem4) + w2 * wbytes + kDescBytes)[i];
-					lo4.x += c.x & 0xffffu, lo4.y += c.x >> 16, lo4.z += c.y & 0xffffu, lo4.w += c.y >> 16;
-					hi4.x += c.z & 0xffffu, hi4.y += c.z >> 16, hi4.z += c.w & 0xffffu, hi4.w += c.w >> 16;
+					unsigned char const* base = reinterpret_cast<unsigned char const*>(smem4) + w2 * wbytes + kDescBytes;
+					unsigned const ca = reinterpret_cast<unsigned const*>(base)[wd];
+					unsigned const cb = reinterpret_cast<unsigned const*>(base + a.tile_cap)[wb];
+					even += (ca & 0x00ff00ffu) + (cb & 0x00ff00ffu);
+					odd += ((ca >> 8) & 0x00ff00ffu) + ((cb >> 8) & 0x00ff00ffu);
 				}
-				o[2 * i]     = lo4;
-				o[2 * i + 1] = hi4;
+				uint4 c = make_uint4(even & 0xffffu, odd & 0xffffu, even >> 16, odd >> 16);
+				if (round) {
+					uint4 const prev = o[wd];
+					c.x += prev.x, c.y += prev.y, c.z += prev.z, c.w += prev.w;
+				}
+				o[wd] = c;
 			}
 			__syncthreads();
+		}
+	}
+}
+
+// ---- arrange_runs / restore_runs -----------------------------------------------------------------
+// Counter addresses of local target t of a tile (t < cap, cap a multiple of 128):
+//   array A: t                       (bank (t >> 2) & 31)
+//   array B: cap + rot(t),  rot(t) = t with its bank field rotated by the 128-byte row number
+//                                      (bank ((t >> 2) + (t >> 7)) & 31)
+// Two targets that share a bank in A never share one in B (for tiles of <= 32 rows), which is what
+// makes the 2-choice balancing effective.
+__host__ __device__ __forceinline__ int rot_fwd(int t) { return (t & ~0x7c) | ((t + ((t >> 7) << 2)) & 0x7c); }
+__host__ __device__ __forceinline__ int rot_inv(int u) { return (u & ~0x7c) | ((u - ((u >> 7) << 2)) & 0x7c); }
+
+// One thread per run.  A run is processed in chunks of <= 128 entries aligned like the delivery
+// kernel's 16-byte loads: the entry at global position g is counted by instruction (g & 3) of its
+// chunk, together with the entries at g +- 4, +- 8, ... — those must fall into different banks.
+__global__ void __launch_bounds__(128) arrange_kernel(std::int32_t* nb, long long const* tile_ptr, long long n_runs, int tiles,
+                                                      int tile, int cap) {
+	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (id >= n_runs)
+		return;
+	long long const row = id / tiles;
+	int const k         = static_cast<int>(id % tiles);
+	long long const beg = tile_ptr[row * (tiles + 1) + k], end = tile_ptr[row * (tiles + 1) + k + 1];
+	int const lo        = k * tile;
+	unsigned short t[128];
+	unsigned char bank[128]; // chosen bank | array << 7
+	unsigned char order[128];
+	unsigned char load[32], first[33];
+	for (long long cb = beg & ~3ll; cb < end; cb += 128) {
+		long long const g0 = cb > beg ? cb : beg;
+		long long const g1 = cb + 128 < end ? cb + 128 : end;
+		int const m        = static_cast<int>(g1 - g0);
+		for (int b = 0; b < 32; b++)
+			load[b] = 0;
+		// 2-choice greedy, then two passes that move entries out of banks more than one fuller than their alternative
+		for (int j = 0; j < m; j++) {
+			int const tt = __ldg(nb + g0 + j) - lo;
+			t[j]         = static_cast<unsigned short>(tt);
+			int const bA = (tt >> 2) & 31, bB = ((tt >> 2) + (tt >> 7)) & 31;
+			bool const pickB = load[bB] < load[bA];
+			int const b      = pickB ? bB : bA;
+			load[b]++;
+			bank[j] = static_cast<unsigned char>(b | (pickB ? 0x80 : 0));
+		}
+		for (int pass = 0; pass < 2; pass++)
+			for (int j = 0; j < m; j++) {
+				int const tt  = t[j];
+				int const bA  = (tt >> 2) & 31, bB = ((tt >> 2) + (tt >> 7)) & 31;
+				bool const inB = (bank[j] & 0x80) != 0;
+				int const cur = inB ? bB : bA, alt = inB ? bA : bB;
+				if (load[cur] > load[alt] + 1) {
+					load[cur]--;
+					load[alt]++;
+					bank[j] = static_cast<unsigned char>(alt | (inB ? 0 : 0x80));
+				}
+			}
+		// entries grouped by bank
+		int maxload = 0, run = 0;
+		for (int b = 0; b < 32; b++) {
+			first[b] = static_cast<unsigned char>(run);
+			run += load[b];
+			maxload = load[b] > maxload ? load[b] : maxload;
+		}
+		first[32] = static_cast<unsigned char>(run);
+		for (int b = 0; b < 32; b++)
+			load[b] = 0;
+		for (int j = 0; j < m; j++) {
+			int const b               = bank[j] & 31;
+			order[first[b] + load[b]] = static_cast<unsigned char>(j);
+			load[b]++;
+		}
+		// the four instructions of the chunk: how many positions each has, and its next free position
+		int rem[4];
+		long long next[4];
+		for (int c = 0; c < 4; c++) {
+			long long const f = g0 + ((c - g0) & 3); // first position >= g0 with (g & 3) == c
+			next[c]           = f;
+			rem[c]            = f < g1 ? static_cast<int>((g1 - f + 3) >> 2) : 0;
+		}
+		// fullest banks first; the entries of one bank go to different instructions, the emptiest first
+		for (int L = maxload; L >= 1; L--)
+			for (int b = 0; b < 32; b++) {
+				if (load[b] != L)
+					continue;
+				unsigned used = 0;
+				for (int i = 0; i < L; i++) {
+					int best = -1;
+					for (int c = 0; c < 4; c++)
+						if (!((used >> c) & 1) && rem[c] > 0 && (best < 0 || rem[c] > rem[best]))
+							best = c;
+					if (best < 0) { // more entries than instructions left for this bank: conflicts, still correct
+						used = 0;
+						for (int c = 0; c < 4; c++)
+							if (rem[c] > 0 && (best < 0 || rem[c] > rem[best]))
+								best = c;
+					}
+					used |= 1u << best;
+					rem[best]--;
+					int const j  = order[first[b] + i];
+					int const tt = t[j];
+					nb[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
+					next[best] += 4;
+				}
+			}
+	}
+}
+
+// One thread per run: decode the counter addresses back to local columns and emit them ascending.
+__global__ void __launch_bounds__(128) restore_kernel(std::int32_t const* nb, long long const* tile_ptr, long long n_runs, int tiles,
+                                                      int tile, int cap, std::int32_t* out) {
+	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (id >= n_runs)
+		return;
+	long long const row = id / tiles;
+	int const k         = static_cast<int>(id % tiles);
+	long long const beg = tile_ptr[row * (tiles + 1) + k], end = tile_ptr[row * (tiles + 1) + k + 1];
+	int const lo        = k * tile;
+	unsigned present[kTileMax / 32];
+	int const words = (tile + 31) / 32;
+	for (int i = 0; i < words; i++)
+		present[i] = 0;
+	for (long long e = beg; e < end; e++) {
+		int const v = nb[e];
+		int const t = v < cap ? v : rot_inv(v - cap);
+		present[t >> 5] |= 1u << (t & 31);
+	}
+	long long o = beg;
+	for (int i = 0; i < words; i++) {
+		unsigned m = present[i];
+		while (m) {
+			int const bit = __ffs(m) - 1;
+			m &= m - 1;
+			out[o++] = lo + i * 32 + bit;
 		}
 	}
 }
@@ -368,6 +512,24 @@ int build_tile_ptr(void* stream, long long const* offsets, std::int32_t const* n
 	if (n > 0)
 		tile_ptr_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(offsets, neighbors, src_count,
 		                                                                                                        tile, tiles, tile_ptr);
+	return static_cast<int>(cudaGetLastError());
+}
+
+int arrange_runs(void* stream, std::int32_t* neighbors, long long const* tile_ptr, long long src_count, int tile, int tiles,
+                 int cap) {
+	long long const n = src_count * tiles;
+	if (n > 0)
+		arrange_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, n, tiles,
+		                                                                                                    tile, cap);
+	return static_cast<int>(cudaGetLastError());
+}
+
+int restore_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, long long src_count, int tile,
+                 int tiles, int cap, std::int32_t* out) {
+	long long const n = src_count * tiles;
+	if (n > 0)
+		restore_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, n, tiles,
+		                                                                                                    tile, cap, out);
 	return static_cast<int>(cudaGetLastError());
 }
 

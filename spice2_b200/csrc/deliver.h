@@ -7,7 +7,7 @@
 
 namespace spice::deliver {
 
-constexpr int kTileMax = 5120; // u16 counters one warp keeps in shared memory (10 KB)
+constexpr int kTileMax = 5120; // targets per tile: one warp keeps two u8 counters per target in shared memory (10 KB)
 
 // One connection as the delivery kernel sees it (lives in device memory, one array per context,
 // in schedule order: heaviest connections first).
@@ -16,7 +16,7 @@ struct conn_desc {
 	std::uint32_t const* ring_cnt; // [ring][world]
 	long long ring_cap;
 	long long seg_lo[spice::detail::kMaxWorld]; // first source neuron of every rank's segment of a ring slot
-	std::int32_t const* neighbors; // CSR column indices (local to this rank's target range)
+	std::int32_t const* neighbors; // CSR entries: arranged connections hold counter addresses (see arrange_runs), others local columns
 	long long const* tile_ptr;     // [src][tiles + 1]: where each tile's share of the row starts
 	std::uint32_t* counts;         // [cring][cstride] event counters of the TARGET population
 	long long n_dst;               // local targets
@@ -26,7 +26,8 @@ struct conn_desc {
 	std::int32_t tiles;            // number of target tiles
 	std::int32_t tile;             // targets per tile (multiple of 256, <= kTileMax)
 	std::int32_t tile_prefix;      // tiles of the connections scheduled before this one
-	std::int32_t atomic;           // rows may hold duplicate targets (adj_list multapses)
+	std::int32_t arranged;         // 1: entries were rewritten by arrange_runs (fast path); 0: plain columns, counted with
+	                               //    global atomics (rows that may hold duplicate targets: adj_list multapses)
 	std::int32_t pad;
 };
 
@@ -40,13 +41,24 @@ struct tiles_args {
 	unsigned* work;            // dynamic unit counter, zeroed by the window prologue
 	unsigned long long* stats; // [0] events, [1] spikes
 	int* error;                // bit 16: internal error in the delivery kernel
-	int tile_cap;              // u16 counters per warp in shared memory (max conns[].tile)
+	int tile_cap;              // targets per warp-private counter array (max conns[].tile rounded up to 128)
 };
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
 // (k = tiles: the row end).  Returns a cudaError_t as int.
 int build_tile_ptr(void* stream, long long const* offsets, std::int32_t const* neighbors, long long src_count, int tile,
                    int tiles, long long* tile_ptr);
+
+// Rewrite the entries of every run (a tile's share of a row) for the fast delivery path: each entry
+// becomes the byte address of one of its target's two u8 counters (array A at [0, cap), array B at
+// [cap, 2 cap) with the bank rotated by the 128-byte row), and the entries of a run are permuted so
+// that the 32 lanes of one counting instruction hit 32 different shared-memory banks.  The rows of
+// the connection must be free of duplicate targets.  `cap` must equal tiles_args::tile_cap.
+// restore_runs writes the canonical (ascending, local column) entries of [0, edges) into `out`.
+int arrange_runs(void* stream, std::int32_t* neighbors, long long const* tile_ptr, long long src_count, int tile, int tiles,
+                 int cap);
+int restore_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, long long src_count, int tile,
+                 int tiles, int cap, std::int32_t* out);
 
 // One launch delivers every spike of the window on every connection.  `blocks` <= 0 picks a
 // persistent grid filling the device.  Returns a cudaError_t as int.

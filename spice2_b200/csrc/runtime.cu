@@ -308,6 +308,7 @@ struct connection {
 	long long* tile_ptr       = nullptr; // [src][tiles + 1]
 	int tile = 0, tiles = 0;
 	bool duplicates           = false;   // rows may repeat a target (adj_list)
+	bool arranged             = false;   // neighbors hold counter addresses (deliver::arrange_runs), not columns
 	// stateful / plastic synapses (window = 1 step; spice/detail/model_ops.cuh)
 	bool stateful = false, plastic = false;
 	std::uint32_t* syn        = nullptr; // word-SoA synapse state, parallel to neighbors
@@ -552,10 +553,20 @@ int finalize(spice_ctx* ctx) {
 			d.tiles       = c.tiles;
 			d.tile        = c.tile;
 			d.tile_prefix = ctx->total_tiles;
-			d.atomic      = c.duplicates ? 1 : 0;
+			d.arranged    = c.duplicates ? 0 : 1;
 			ctx->total_tiles += c.tiles;
-			ctx->tile_cap = std::max(ctx->tile_cap, c.tile);
+			ctx->tile_cap = std::max(ctx->tile_cap, static_cast<int>(align_up(static_cast<size_t>(c.tile), 128)));
 			descs.push_back(d);
+		}
+		// fast path: rewrite every run of the duplicate-free connections as bank-balanced counter addresses (deliver.h)
+		for (int ci : order) {
+			connection& c = ctx->conns[ci];
+			if (c.duplicates)
+				continue;
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::arrange_runs(ctx->stream, c.neighbors, c.tile_ptr, ctx->pops[c.src].size, c.tile,
+			                                                              c.tiles, ctx->tile_cap)));
+			c.arranged = true;
+			ctx->launches++;
 		}
 		if (!descs.empty()) {
 			CHECK_CUDA(ctx, cudaMalloc(&ctx->d_conn_desc, sizeof(deliver::conn_desc) * descs.size()));
@@ -1256,8 +1267,24 @@ int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t
 	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (offsets_out)
 		CHECK_CUDA(ctx, cudaMemcpy(offsets_out, c.offsets, sizeof(long long) * static_cast<size_t>(ctx->pops[c.src].size + 1), cudaMemcpyDeviceToHost));
-	if (neighbors_out && c.edges)
-		CHECK_CUDA(ctx, cudaMemcpy(neighbors_out, c.neighbors, sizeof(std::int32_t) * static_cast<size_t>(c.edges), cudaMemcpyDeviceToHost));
+	if (neighbors_out && c.edges) {
+		std::int32_t const* from = c.neighbors;
+		std::int32_t* tmp        = nullptr;
+		if (c.arranged) { // the delivery kernel's layout -> ascending local columns
+			CHECK_CUDA(ctx, cudaMalloc(&tmp, sizeof(std::int32_t) * static_cast<size_t>(c.edges)));
+			int const e = deliver::restore_runs(ctx->stream, c.neighbors, c.tile_ptr, ctx->pops[c.src].size, c.tile, c.tiles, ctx->tile_cap, tmp);
+			if (e != 0) {
+				cudaFree(tmp);
+				return fail(ctx, SPICE_ERR_CUDA, std::string("restore_runs: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+			}
+			from = tmp;
+		}
+		cudaError_t const e = cudaMemcpyAsync(neighbors_out, from, sizeof(std::int32_t) * static_cast<size_t>(c.edges), cudaMemcpyDeviceToHost, ctx->stream);
+		cudaError_t const e2 = cudaStreamSynchronize(ctx->stream);
+		cudaFree(tmp);
+		CHECK_CUDA(ctx, e);
+		CHECK_CUDA(ctx, e2);
+	}
 	return SPICE_OK;
 }
 
