@@ -107,28 +107,41 @@ def reference_arm(args, rank, world):
     from oracle_lib import RefShim
 
     n = args.ref_neurons
-    steps_per = max(1, args.ref_steps)
     if not RefShim.available("fast"):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
     shim = RefShim("fast")
     w_exc, w_inh = np.float32(0.2 / (P_CONN * n)), np.float32(-1.0 / (P_CONN * n))
-    vals = []
     total = args.warmup + args.steps
-    # each bench "step" here is a bounded sample: the reference simulating `steps_per` time steps
-    r = shim.brunel(N=n, p=P_CONN, w_exc=w_exc, w_inh=w_inh, dt=DT, delay=DELAY, steps=steps_per * total)
-    ev_s = r["synaptic_events"] / r["sim_seconds"]
-    ms_per_step = r["sim_seconds"] / (steps_per * total) * 1e3
+    # A bench "step" of this arm is a bounded sample: `per` consecutive time steps of the reference's
+    # own snn::step() on the same Brunel construction at a size one host core handles (the reference
+    # is single-threaded).  The network first runs PREROLL untimed time steps so that the sample is
+    # taken at the steady-state firing rates, like the GPU arm's.
+    per = args.ref_steps or max(1, min(200, 6000 // max(1, total)))
+    PREROLL = 300
+    run = shim.brunel_open(n, P_CONN, w_exc, w_inh, DT, DELAY, 1337)
+    run.advance(PREROLL)
+    for _ in range(args.warmup):
+        run.advance(per)
+    sec = ev = 0
+    for _ in range(args.steps):
+        s_, e_, _sp = run.advance(per)
+        sec += s_
+        ev += e_
+    run.close()
+    ev_s = ev / sec
+    ms_per_step = sec / (args.steps * per) * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": ev_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"brunel p={P_CONN} scaled weights, CPU sample N={n} ({steps_per * total} time steps)",
+        "config": {"workload": f"brunel-c5-share: Brunel p={P_CONN}, in-degree-scaled weights; CPU sample N={n}, "
+                               f"{per} time step(s) per bench step after {PREROLL} untimed pre-roll steps",
                    "neurons": n, "synapses": int(P_CONN * n * n / 2), "dt": DT, "delay_steps": 15},
-        "sim_s_per_wall_s": steps_per * total * DT / r["sim_seconds"],
+        "sim_s_per_wall_s": args.steps * per * DT / sec,
         "cpu_baseline": {"value": ev_s, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"reference build (-O2 -ffast-math) of Brunel N={n}, p={P_CONN}, {steps_per * total} steps; "
-                                   f"build {r['build_seconds']:.2f}s, step loop {r['sim_seconds']:.2f}s, 1 thread (the reference has no threading)"},
+                         "sample": f"reference build (-O2 -ffast-math) of Brunel N={n}, p={P_CONN}: {args.steps} x {per} timed time steps "
+                                   f"in snn::step(); build {run.build_seconds:.2f}s, timed {sec:.2f}s, 1 thread (the reference has no threading)"},
         "e2e": {"value": ev_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -143,8 +156,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--neurons", type=int, default=0, help="override the network size (default: weak-scaled C5 share)")
     ap.add_argument("--ref-neurons", type=int, default=200000)
-    ap.add_argument("--ref-steps", type=int, default=1, help="time steps per bench step in the reference arm")
-    ap.add_argument("--cpu-baseline-steps", type=int, default=600)
+    ap.add_argument("--ref-steps", type=int, default=0, help="time steps per bench step in the reference arm (0: sized from --steps)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -236,12 +249,18 @@ def main():
             s0 = net.stats()
             t0 = time.perf_counter()
             d2h = 0
-            done = 0
+            done = issued = 0
             batch = 150  # ten windows per readout
+            pending = []
+            # the host drains batch k from the page-locked sink while the device runs batch k + 1
             while done < args.steps:
-                k = min(batch, args.steps - done)
-                net.step(k)
-                counts, ids = net.raster_read()  # D2H of the spike lists (pageable->pinned inside the library)
+                while issued < args.steps and len(pending) < 2:
+                    k = min(batch, args.steps - issued)
+                    net.step(k)
+                    pending.append(k)
+                    issued += k
+                k = pending.pop(0)
+                counts, ids = net.raster_read(k)  # every spike id of these steps, in host memory
                 d2h += counts.nbytes + ids.nbytes
                 done += k
             barrier()
@@ -252,7 +271,8 @@ def main():
         ev2 = allreduce(s1["synaptic_events"] - s0["synaptic_events"], dist.ReduceOp.SUM if world > 1 else None)
         e2e = {"value": ev2 / wall_max, "unit": UNIT, "h2d_bytes_per_step": 20, "d2h_bytes_per_step": d2h / args.steps,
                "sim_s_per_wall_s": args.steps * DT / wall_max,
-               "note": "per step the host sends dt + the step's 128-bit stream seed (kernel arguments) and reads back every spike id"}
+               "note": "per step the host sends dt + the step's 128-bit stream seed (kernel arguments) and receives every spike id, "
+                       "sorted per (step, population) as neuron_population::spikes() returns them, in batches of 150 steps"}
 
     if rank != 0:
         if world > 1:
@@ -285,12 +305,16 @@ def main():
 
         nref = args.ref_neurons
         if RefShim.available("fast"):
-            r = RefShim("fast").brunel(N=nref, p=P_CONN, w_exc=np.float32(0.2 / (P_CONN * nref)), w_inh=np.float32(-1.0 / (P_CONN * nref)),
-                                       dt=DT, delay=DELAY, steps=args.cpu_baseline_steps)
-            cpu = {"value": r["synaptic_events"] / r["sim_seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
-                   "sample": f"compiled reference (its own flags), Brunel N={nref} p={P_CONN}, {args.cpu_baseline_steps} steps: "
-                             f"build {r['build_seconds']:.2f}s, step loop {r['sim_seconds']:.2f}s on 1 of {os.cpu_count()} host cores",
-                   "sim_s_per_wall_s": args.cpu_baseline_steps * DT / r["sim_seconds"]}
+            run = RefShim("fast").brunel_open(nref, P_CONN, np.float32(0.2 / (P_CONN * nref)), np.float32(-1.0 / (P_CONN * nref)),
+                                              DT, DELAY, 1337)
+            run.advance(300)  # untimed pre-roll to the steady-state rates
+            sec, ev, _sp = run.advance(args.cpu_baseline_steps)
+            run.close()
+            cpu = {"value": ev / sec, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"compiled reference (its own flags), Brunel N={nref} p={P_CONN}, {args.cpu_baseline_steps} time steps after a "
+                             f"300-step pre-roll: build {run.build_seconds:.2f}s, snn::step() loop {sec:.2f}s on 1 of {os.cpu_count()} host cores "
+                             f"(the reference is single-threaded)",
+                   "sim_s_per_wall_s": args.cpu_baseline_steps * DT / sec}
         else:
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not present"}
 

@@ -131,13 +131,17 @@ SPICE_API int spice_neurons(spice_ctx* ctx, int pop, void* out, int64_t bytes);
 /* overwrite this rank's neuron state (the reference exposes a mutable span) */
 SPICE_API int spice_set_neurons(spice_ctx* ctx, int pop, void const* in, int64_t bytes);
 
-/* Spike raster recording for batched readout (the per-step sink of the samples,
- * samples/matplot.cpp:96-134, without a device sync per step).  While enabled, every step's
- * spike lists are appended to host memory.  spice_raster_read copies and clears the log:
- * counts[step * n_pops + pop] and the concatenated ids in (step, pop) order. */
+/* Spike sink: batched readout of every step's spike lists (the per-step sink of the samples,
+ * samples/matplot.cpp:96-134, without a device sync per step).  While enabled, each window's
+ * lists are sorted on the device and written into a ring in page-locked host memory; a readout
+ * waits only for the steps it takes, so the host can drain batch k while the device runs batch
+ * k + 1.  spice_raster_size waits for the first max_steps unread steps (<= 0: all steps issued)
+ * and reports how many steps / ids they hold; spice_raster_read copies them out and frees their
+ * ring space: counts[step * n_pops + pop] and the concatenated ascending ids in (step, pop)
+ * order.  An unread log that outgrows the ring is an error reported by the next readout. */
 SPICE_API int spice_raster_enable(spice_ctx* ctx, int enable);
-SPICE_API int spice_raster_size(spice_ctx* ctx, int64_t* n_steps_out, int64_t* n_ids_out);
-SPICE_API int spice_raster_read(spice_ctx* ctx, int64_t* counts_out, int32_t* ids_out);
+SPICE_API int spice_raster_size(spice_ctx* ctx, int64_t max_steps, int64_t* n_steps_out, int64_t* n_ids_out);
+SPICE_API int spice_raster_read(spice_ctx* ctx, int64_t n_steps, int64_t* counts_out, int32_t* ids_out);
 
 /* counters: synaptic events (Syn::deliver invocations, synapse_population.h:118-133) and spikes
  * processed by this rank since creation */

@@ -242,6 +242,79 @@ int ref_brunel_run(std::int64_t N, double p, float w_exc, float w_inh, float dt,
 	return r.overflow ? 1 : 0;
 }
 
+// ---- Brunel, incremental: build once, advance in slices (bench.py's reference arm) --------------
+// The timed region is net.step() only; the tally of Syn::deliver invocations (out-degree of every
+// spike delivered in the slice: a spike of age delay-1 is delivered at the end of a step,
+// snn.cpp:21-25) is recomputed outside it from regenerated offsets.
+struct ref_brunel_net {
+	spice::snn net;
+	spice::detail::neuron_population<ref_brunel::poisson>* P;
+	spice::detail::neuron_population<ref_brunel::lif>* E;
+	spice::detail::neuron_population<ref_brunel::lif>* I;
+	std::vector<Int> outdeg[3]; // per source population: summed out-degree over its two connections
+	std::int64_t d, steps_run = 0;
+	ref_brunel_net(float dt, float delay, std::uint32_t seed) : net(dt, delay, {seed}) {}
+};
+
+void* ref_brunel_open(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay, std::uint32_t seed,
+                      double* build_seconds) {
+	using namespace ref_brunel;
+	auto const t0 = clk::now();
+	auto* h = new ref_brunel_net(dt, delay, seed);
+	h->P = h->net.add_population<poisson>(N / 2);
+	h->E = h->net.add_population<lif>(N * 4 / 10);
+	h->I = h->net.add_population<lif>(N / 10);
+	h->net.connect<fixed_weight>(h->P, h->E, spice::fixed_probability(p), delay, {w_exc});
+	h->net.connect<fixed_weight>(h->P, h->I, spice::fixed_probability(p), delay, {w_exc});
+	h->net.connect<fixed_weight>(h->E, h->E, spice::fixed_probability(p), delay, {w_exc});
+	h->net.connect<fixed_weight>(h->E, h->I, spice::fixed_probability(p), delay, {w_exc});
+	h->net.connect<fixed_weight>(h->I, h->E, spice::fixed_probability(p), delay, {w_inh});
+	h->net.connect<fixed_weight>(h->I, h->I, spice::fixed_probability(p), delay, {w_inh});
+	if (build_seconds)
+		*build_seconds = seconds(t0, clk::now());
+	h->d = static_cast<std::int64_t>(std::round(delay / dt));
+	std::int64_t const nsz[3] = {N / 2, N * 4 / 10, N / 10};
+	int const csrc[6] = {0, 0, 1, 1, 2, 2}, cdst[6] = {1, 2, 1, 2, 1, 2};
+	for (int s = 0; s < 3; s++)
+		h->outdeg[s].assign(static_cast<std::size_t>(nsz[s]), 0);
+	for (int j = 0; j < 6; j++) {
+		spice::fixed_probability fp(p);
+		fp(nsz[csrc[j]], nsz[cdst[j]]);
+		std::vector<Int> off(static_cast<std::size_t>(nsz[csrc[j]]) + 1);
+		std::vector<Int32> nb(static_cast<std::size_t>(fp.size()));
+		std::uint32_t il[1] = {seed};
+		fp.generate(off, nb, make_seed(il, 1, 2 + j));
+		for (std::int64_t i = 0; i < nsz[csrc[j]]; i++)
+			h->outdeg[csrc[j]][static_cast<std::size_t>(i)] += off[i + 1] - off[i];
+	}
+	return h;
+}
+
+int ref_brunel_advance(void* handle, std::int64_t steps, double* sim_seconds, std::int64_t* synaptic_events,
+                       std::int64_t* spikes) {
+	auto* h = static_cast<ref_brunel_net*>(handle);
+	double sim = 0;
+	std::int64_t ev = 0, sp = 0;
+	for (std::int64_t s = 0; s < steps; s++) {
+		auto const a = clk::now();
+		h->net.step();
+		sim += seconds(a, clk::now());
+		h->steps_run++;
+		sp += static_cast<std::int64_t>(h->P->spikes(0).size() + h->E->spikes(0).size() + h->I->spikes(0).size());
+		if (h->steps_run >= h->d) {
+			for (auto id : h->P->spikes(h->d - 1)) ev += h->outdeg[0][id];
+			for (auto id : h->E->spikes(h->d - 1)) ev += h->outdeg[1][id];
+			for (auto id : h->I->spikes(h->d - 1)) ev += h->outdeg[2][id];
+		}
+	}
+	if (sim_seconds) *sim_seconds = sim;
+	if (synaptic_events) *synaptic_events = ev;
+	if (spikes) *spikes = sp;
+	return 0;
+}
+
+void ref_brunel_close(void* handle) { delete static_cast<ref_brunel_net*>(handle); }
+
 // ---- Brunel+ (samples/brunel+.cpp:102-117): E->E plastic -------------------------------------
 int ref_brunel_plus_run(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay,
                         std::uint32_t seed, std::int64_t steps, std::int32_t* ids,

@@ -65,8 +65,8 @@ def lib() -> C.CDLL:
             "spice_neurons": (i32, [vp, i32, vp, i64]),
             "spice_set_neurons": (i32, [vp, i32, vp, i64]),
             "spice_raster_enable": (i32, [vp, i32]),
-            "spice_raster_size": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
-            "spice_raster_read": (i32, [vp, vp, vp]),
+            "spice_raster_size": (i32, [vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+            "spice_raster_read": (i32, [vp, i64, vp, vp]),
             "spice_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
             "spice_profile_enable": (i32, [vp, i32]),
             "spice_profile_read": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -289,13 +289,14 @@ class snn:
     def raster_enable(self, on=True):
         self._check(lib().spice_raster_enable(self._h, int(on)))
 
-    def raster_read(self):
-        """-> (counts[steps, npops], ids concatenated in (step, pop) order); clears the log."""
-        steps, nids = C.c_int64(), C.c_int64()
-        self._check(lib().spice_raster_size(self._h, C.byref(steps), C.byref(nids)))
-        counts = np.zeros((steps.value, len(self.populations)), np.int64)
-        ids = np.zeros(max(nids.value, 1), np.int32)
-        self._check(lib().spice_raster_read(self._h, _ptr(counts), _ptr(ids)))
+    def raster_read(self, steps: int = 0):
+        """-> (counts[steps, npops], ascending ids concatenated in (step, pop) order) of the first `steps`
+        unread steps (0: every step issued so far); waits only for those steps and frees their log space."""
+        n, nids = C.c_int64(), C.c_int64()
+        self._check(lib().spice_raster_size(self._h, steps, C.byref(n), C.byref(nids)))
+        counts = np.empty((n.value, len(self.populations)), np.int64)
+        ids = np.empty(max(nids.value, 1), np.int32)
+        self._check(lib().spice_raster_read(self._h, n.value, _ptr(counts), _ptr(ids)))
         return counts, ids[: nids.value]
 
     def stats(self):

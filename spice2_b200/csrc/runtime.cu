@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -210,62 +211,142 @@ __global__ void wait_window(wait_args a) {
 	__threadfence_system();
 }
 
-// Raster log: append the window's spike lists to a device log (one block per (step, population)).
-struct raster_args {
+// Spike sink (the per-step sink of the samples, samples/matplot.cpp:96-134, as a
+// batched ring drained by the host without a device-wide sync): one block per (step, population)
+// of the window sorts the step's spike list ascending — the order neuron_population::spikes()
+// has in the reference — and appends it to a ring in page-locked, device-mapped HOST memory.
+// Sorting is a bitmap over the population's id range in shared memory (ids are unique), read
+// back with popc prefix sums.  The lists of a window sit in (step, population) order, so a
+// readout of n steps is at most two memcpy()s on the host.
+constexpr int kSinkThreads = 1024;
+struct sink_args {
 	std::int32_t const* const* ring_ids; // [npops]
 	std::uint32_t const* const* ring_cnt;
 	long long const* ring_cap;           // [npops]
 	long long const* seg_lo;             // [npops][world]
+	long long const* pop_size;           // [npops]
 	int npops, ring, world;
 	long long t0;
 	int nsteps;
-	long long step_index0;               // index of the window's first step in the log
-	unsigned long long* cursor;          // ids appended so far
-	std::int32_t* log_ids;
-	long long log_cap;
-	long long* log_off;                  // [steps][npops] offset of the list in log_ids
-	std::int32_t* log_cnt;               // [steps][npops][world]
-	long long log_steps_cap;
-	int* error;
+	int parity;                          // window index & 1: cursor[parity] is this window's base
+	long long step_index0;               // index of the window's first step since the sink was enabled
+	unsigned long long* cursor;          // [2] ids appended before this / the next window
+	std::int32_t* stage;                 // device ring, same positions as the host ring
+	std::int32_t* h_ids;                 // host ring (mapped)
+	long long cap;                       // ids in either ring
+	long long* h_cnt;                    // [steps_cap][npops] (mapped)
+	unsigned long long* h_off;           // [steps_cap][npops] (mapped) monotonic position of the list
+	long long steps_cap;
+	unsigned long long const volatile* h_consumed; // [2] steps, ids the host has taken (mapped, host-written)
+	int* h_error;                        // mapped
 };
 
-__global__ void __launch_bounds__(256) raster_pack(raster_args a) {
+__global__ void __launch_bounds__(kSinkThreads) sink_pack(sink_args a) {
+	extern __shared__ unsigned sink_bm[];
+	__shared__ unsigned long long before_s, base_s;
+	__shared__ unsigned total_s, warp_sum[32];
+	__shared__ int ok_s;
+	int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	int const s = blockIdx.x / a.npops, p = blockIdx.x % a.npops;
-	long long const si = a.step_index0 + s;
-	if (si >= a.log_steps_cap) {
-		if (threadIdx.x == 0)
-			atomicOr(a.error, 4);
-		return;
-	}
-	__shared__ unsigned long long base_s;
-	__shared__ unsigned total_s;
+	long long const si   = a.step_index0 + s;
 	long long const slot = (a.t0 + s) % a.ring;
-	if (threadIdx.x == 0) {
-		unsigned total = 0;
-		for (int r = 0; r < a.world; r++) {
-			unsigned const c = a.ring_cnt[p][slot * a.world + r];
-			a.log_cnt[(si * a.npops + p) * a.world + r] = static_cast<std::int32_t>(c);
-			total += c;
-		}
-		base_s  = atomicAdd(a.cursor, static_cast<unsigned long long>(total));
-		total_s = total;
-		a.log_off[si * a.npops + p] = static_cast<long long>(base_s);
+	if (tid == 0)
+		before_s = 0, total_s = 0;
+	__syncthreads();
+	// where this list starts: after the lists of the window's earlier (step, population) pairs
+	for (int b = tid; b <= static_cast<int>(blockIdx.x); b += kSinkThreads) {
+		int const s2 = b / a.npops, p2 = b % a.npops;
+		long long const slot2 = (a.t0 + s2) % a.ring;
+		unsigned t = 0;
+		for (int r = 0; r < a.world; r++)
+			t += a.ring_cnt[p2][slot2 * a.world + r];
+		if (b < static_cast<int>(blockIdx.x))
+			atomicAdd(&before_s, static_cast<unsigned long long>(t));
+		else
+			total_s = t;
 	}
 	__syncthreads();
-	unsigned long long const base = base_s;
-	if (base + total_s > static_cast<unsigned long long>(a.log_cap)) {
-		if (threadIdx.x == 0)
-			atomicOr(a.error, 8);
+	if (tid == 0) {
+		unsigned long long const base = a.cursor[a.parity] + before_s;
+		if (blockIdx.x == gridDim.x - 1)
+			a.cursor[a.parity ^ 1] = base + total_s;
+		int ok = 1;
+		if (static_cast<unsigned long long>(si) - a.h_consumed[0] >= static_cast<unsigned long long>(a.steps_cap))
+			*a.h_error = 4, ok = 0;
+		else if (base + total_s - a.h_consumed[1] > static_cast<unsigned long long>(a.cap))
+			*a.h_error = 8, ok = 0;
+		if (ok) {
+			a.h_cnt[(si % a.steps_cap) * a.npops + p] = total_s;
+			a.h_off[(si % a.steps_cap) * a.npops + p] = base;
+		}
+		base_s = base;
+		ok_s   = ok;
+	}
+	__syncthreads();
+	if (!ok_s)
 		return;
+	unsigned long long const base = base_s;
+	unsigned const total          = total_s;
+	long long const size          = a.pop_size[p];
+	// words per thread: odd, so that a warp's strided bitmap reads fall into different banks
+	int const W            = static_cast<int>(min(31ll, ((size + 32 * kSinkThreads - 1) / (32 * kSinkThreads)) | 1));
+	int const words        = W * kSinkThreads;
+	long long const cbits  = static_cast<long long>(words) * 32;
+	unsigned emitted       = 0;
+	for (long long c0 = 0; c0 < size && emitted < total; c0 += cbits) {
+		for (int i = tid; i < words; i += kSinkThreads)
+			sink_bm[i] = 0;
+		__syncthreads();
+		for (int r = 0; r < a.world; r++) {
+			unsigned const c         = a.ring_cnt[p][slot * a.world + r];
+			std::int32_t const* from = a.ring_ids[p] + slot * a.ring_cap[p] + a.seg_lo[p * a.world + r];
+			for (unsigned j = tid; j < c; j += kSinkThreads) {
+				long long const id = from[j] - c0;
+				if (id >= 0 && id < cbits)
+					atomicOr(&sink_bm[id >> 5], 1u << (id & 31));
+			}
+		}
+		__syncthreads();
+		unsigned mine = 0;
+		for (int k = 0; k < W; k++)
+			mine += __popc(sink_bm[tid * W + k]);
+		unsigned incl = mine;
+		for (int off = 1; off < 32; off <<= 1) {
+			unsigned const o = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= off)
+				incl += o;
+		}
+		if (lane == 31)
+			warp_sum[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned v = warp_sum[lane], w = v;
+			for (int off = 1; off < 32; off <<= 1) {
+				unsigned const o = __shfl_up_sync(0xffffffffu, w, off);
+				if (lane >= off)
+					w += o;
+			}
+			warp_sum[lane] = w - v; // exclusive
+			if (lane == 31)
+				total_s = w; // ids of this chunk
+		}
+		__syncthreads();
+		unsigned long long pos = base + emitted + warp_sum[warp] + (incl - mine);
+		for (int k = 0; k < W; k++) {
+			unsigned m = sink_bm[tid * W + k];
+			while (m) {
+				int const bit = __ffs(m) - 1;
+				m &= m - 1;
+				a.stage[pos % a.cap] = static_cast<std::int32_t>(c0 + (static_cast<long long>(tid) * W + k) * 32 + bit);
+				pos++;
+			}
+		}
+		emitted += total_s;
+		__syncthreads();
 	}
-	unsigned done = 0;
-	for (int r = 0; r < a.world; r++) {
-		unsigned const c          = a.ring_cnt[p][slot * a.world + r];
-		std::int32_t const* from = a.ring_ids[p] + slot * a.ring_cap[p] + a.seg_lo[p * a.world + r];
-		for (unsigned j = threadIdx.x; j < c; j += blockDim.x)
-			a.log_ids[base + done + j] = from[j];
-		done += c;
-	}
+	// coalesced copy of the sorted list into the host ring (128-byte PCIe writes)
+	for (unsigned k = tid; k < total; k += kSinkThreads)
+		a.h_ids[(base + k) % a.cap] = a.stage[(base + k) % a.cap];
 }
 
 __global__ void fill_u32(std::uint32_t* dst, long long n, std::uint32_t value) {
@@ -371,15 +452,22 @@ struct spice_ctx {
 	int* d_error                      = nullptr;
 	long long launches                = 0;
 
-	// raster
+	// spike sink (spice_raster_*)
 	bool raster_on = false;
-	long long raster_steps = 0;
-	unsigned long long* d_cursor = nullptr;
-	std::int32_t* d_log_ids      = nullptr;
-	long long log_cap            = 0;
-	long long* d_log_off         = nullptr;
-	std::int32_t* d_log_cnt      = nullptr;
-	long long log_steps_cap      = 0;
+	long long sink_steps_issued = 0, sink_steps_read = 0, sink_steps_complete = 0, sink_windows = 0;
+	unsigned long long sink_ids_read = 0;
+	long long sink_cap = 0, sink_steps_cap = 0;
+	long long* d_pop_size             = nullptr;
+	unsigned long long* d_sink_cursor = nullptr; // [2]
+	std::int32_t* d_sink_stage        = nullptr;
+	std::int32_t* h_sink_ids          = nullptr; // page-locked, mapped
+	long long* h_sink_cnt             = nullptr;
+	unsigned long long* h_sink_off    = nullptr;
+	unsigned long long* h_sink_consumed = nullptr; // [2] + error word behind it
+	int* h_sink_error                 = nullptr;
+	int sink_smem                     = 0;
+	std::deque<std::pair<long long, cudaEvent_t>> sink_marks; // (steps issued up to the event, event)
+	std::vector<cudaEvent_t> sink_pool;
 
 	// readout scratch
 	std::vector<std::vector<host_spikes>> spike_cache; // [pop][age]
@@ -618,7 +706,12 @@ int finalize(spice_ctx* ctx) {
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_cap, sizeof(long long) * std::max(np, 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_seg_lo, sizeof(long long) * std::max<size_t>(h_seg.size(), 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_peer_cnt, sizeof(void*) * std::max(np, 1) * ctx->world));
+	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pop_size, sizeof(long long) * std::max(np, 1)));
 	if (np) {
+		std::vector<long long> h_size;
+		for (auto const& p : ctx->pops)
+			h_size.push_back(p.size);
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_pop_size, h_size.data(), sizeof(long long) * np, cudaMemcpyHostToDevice));
 		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_cnt, h_cnt.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
 		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_ids, h_ids.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
 		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_ring_cap, h_cap.data(), sizeof(long long) * np, cudaMemcpyHostToDevice));
@@ -878,30 +971,46 @@ int run_window(spice_ctx* ctx, int nsteps) {
 
 	if (ctx->profile)
 		prof_mark(ctx);
-	if (ctx->raster_on) {
-		raster_args ra{};
-		ra.ring_ids      = ctx->d_ring_ids;
-		ra.ring_cnt      = ctx->d_ring_cnt;
-		ra.ring_cap      = ctx->d_ring_cap;
-		ra.seg_lo        = ctx->d_seg_lo;
-		ra.npops         = np;
-		ra.ring          = ctx->ring;
-		ra.world         = ctx->world;
-		ra.t0            = ctx->time;
-		ra.nsteps        = nsteps;
-		ra.step_index0   = ctx->raster_steps;
-		ra.cursor        = ctx->d_cursor;
-		ra.log_ids       = ctx->d_log_ids;
-		ra.log_cap       = ctx->log_cap;
-		ra.log_off       = ctx->d_log_off;
-		ra.log_cnt       = ctx->d_log_cnt;
-		ra.log_steps_cap = ctx->log_steps_cap;
-		ra.error         = ctx->d_error;
-		if (np > 0) {
-			raster_pack<<<nsteps * np, 256, 0, ctx->stream>>>(ra);
-			ctx->launches++;
-		}
-		ctx->raster_steps += nsteps;
+	if (ctx->raster_on && np > 0) {
+		sink_args sa{};
+		sa.ring_ids    = ctx->d_ring_ids;
+		sa.ring_cnt    = ctx->d_ring_cnt;
+		sa.ring_cap    = ctx->d_ring_cap;
+		sa.seg_lo      = ctx->d_seg_lo;
+		sa.pop_size    = ctx->d_pop_size;
+		sa.npops       = np;
+		sa.ring        = ctx->ring;
+		sa.world       = ctx->world;
+		sa.t0          = ctx->time;
+		sa.nsteps      = nsteps;
+		sa.parity      = static_cast<int>(ctx->sink_windows & 1);
+		sa.step_index0 = ctx->sink_steps_issued;
+		sa.cursor      = ctx->d_sink_cursor;
+		sa.stage       = ctx->d_sink_stage;
+		sa.h_ids       = ctx->h_sink_ids;
+		sa.cap         = ctx->sink_cap;
+		sa.h_cnt       = ctx->h_sink_cnt;
+		sa.h_off       = ctx->h_sink_off;
+		sa.steps_cap   = ctx->sink_steps_cap;
+		sa.h_consumed  = ctx->h_sink_consumed;
+		sa.h_error     = ctx->h_sink_error;
+		sink_pack<<<nsteps * np, kSinkThreads, ctx->sink_smem, ctx->stream>>>(sa);
+		ctx->launches++;
+		ctx->sink_windows++;
+		ctx->sink_steps_issued += nsteps;
+		// completion mark of this window: a readout waits for the event of the steps it takes, not for the stream
+		cudaEvent_t ev = nullptr;
+		if (!ctx->sink_pool.empty()) {
+			ev = ctx->sink_pool.back();
+			ctx->sink_pool.pop_back();
+		} else if (ctx->sink_marks.size() >= 4096) { // nobody is reading: keep the newest marks (a later event covers earlier steps)
+			ev = ctx->sink_marks.front().second;
+			ctx->sink_marks.pop_front();
+		} else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+			return fail(ctx, SPICE_ERR_CUDA, "cudaEventCreate (spike sink)");
+		if (cudaEventRecord(ev, ctx->stream) != cudaSuccess)
+			return fail(ctx, SPICE_ERR_CUDA, "cudaEventRecord (spike sink)");
+		ctx->sink_marks.emplace_back(ctx->sink_steps_issued, ev);
 	}
 	cudaError_t const e = cudaGetLastError();
 	if (e != cudaSuccess)
@@ -1109,10 +1218,17 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_work);
 	cudaFree(ctx->d_stats);
 	cudaFree(ctx->d_error);
-	cudaFree(ctx->d_cursor);
-	cudaFree(ctx->d_log_ids);
-	cudaFree(ctx->d_log_off);
-	cudaFree(ctx->d_log_cnt);
+	cudaFree(ctx->d_pop_size);
+	cudaFree(ctx->d_sink_cursor);
+	cudaFree(ctx->d_sink_stage);
+	cudaFreeHost(ctx->h_sink_ids);
+	cudaFreeHost(ctx->h_sink_cnt);
+	cudaFreeHost(ctx->h_sink_off);
+	cudaFreeHost(ctx->h_sink_consumed);
+	for (auto& m : ctx->sink_marks)
+		cudaEventDestroy(m.second);
+	for (auto e : ctx->sink_pool)
+		cudaEventDestroy(e);
 	for (auto e : ctx->prof_events)
 		cudaEventDestroy(e);
 	cudaGetLastError();
@@ -1486,69 +1602,114 @@ int spice_set_neurons(spice_ctx* ctx, int pop, void const* in, int64_t bytes) {
 
 int spice_raster_enable(spice_ctx* ctx, int enable) {
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-	if (enable && !ctx->d_cursor) {
-		long long total = 0;
-		for (auto const& p : ctx->pops)
+	if (enable && !ctx->finalized) {
+		int const rc = finalize(ctx);
+		if (rc != SPICE_OK)
+			return rc;
+	}
+	if (enable && !ctx->d_sink_cursor) {
+		long long total = 0, largest = 1;
+		for (auto const& p : ctx->pops) {
 			total += p.size;
-		ctx->log_steps_cap = 1 << 16;
-		ctx->log_cap       = std::max<long long>(1 << 22, std::min<long long>(total * 64, 1ll << 28));
-		int const np       = static_cast<int>(std::max<size_t>(ctx->pops.size(), 1));
-		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
-		CHECK_CUDA(ctx, cudaMemset(ctx->d_cursor, 0, sizeof(unsigned long long)));
-		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_ids, sizeof(std::int32_t) * static_cast<size_t>(ctx->log_cap)));
-		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_off, sizeof(long long) * static_cast<size_t>(ctx->log_steps_cap) * np));
-		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_log_cnt, sizeof(std::int32_t) * static_cast<size_t>(ctx->log_steps_cap) * np * ctx->world));
+			largest = std::max(largest, p.size);
+		}
+		int const np        = static_cast<int>(std::max<size_t>(ctx->pops.size(), 1));
+		ctx->sink_steps_cap = 1 << 15;
+		ctx->sink_cap       = std::max<long long>(1 << 22, std::min<long long>(total * 16, 1ll << 25));
+		if (char const* e = std::getenv("SPICE_SINK_IDS")) // ring sizes, for tests of the wrap-around
+			ctx->sink_cap = std::max<long long>(1024, std::atoll(e));
+		if (char const* e = std::getenv("SPICE_SINK_STEPS"))
+			ctx->sink_steps_cap = std::max<long long>(ctx->window, std::atoll(e));
+		long long const W   = std::min<long long>(31, ((largest + 32 * kSinkThreads - 1) / (32 * kSinkThreads)) | 1);
+		ctx->sink_smem      = static_cast<int>(W * kSinkThreads * 4);
+		CHECK_CUDA(ctx, cudaFuncSetAttribute(sink_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->sink_smem));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_sink_cursor, 2 * sizeof(unsigned long long)));
+		CHECK_CUDA(ctx, cudaMemset(ctx->d_sink_cursor, 0, 2 * sizeof(unsigned long long)));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_sink_stage, sizeof(std::int32_t) * static_cast<size_t>(ctx->sink_cap)));
+		CHECK_CUDA(ctx, cudaHostAlloc(&ctx->h_sink_ids, sizeof(std::int32_t) * static_cast<size_t>(ctx->sink_cap), cudaHostAllocMapped));
+		CHECK_CUDA(ctx, cudaHostAlloc(&ctx->h_sink_cnt, sizeof(long long) * static_cast<size_t>(ctx->sink_steps_cap) * np, cudaHostAllocMapped));
+		CHECK_CUDA(ctx, cudaHostAlloc(&ctx->h_sink_off, sizeof(unsigned long long) * static_cast<size_t>(ctx->sink_steps_cap) * np, cudaHostAllocMapped));
+		CHECK_CUDA(ctx, cudaHostAlloc(&ctx->h_sink_consumed, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+		std::memset(ctx->h_sink_consumed, 0, 4 * sizeof(unsigned long long));
+		ctx->h_sink_error = reinterpret_cast<int*>(ctx->h_sink_consumed + 2);
 	}
 	ctx->raster_on = enable != 0;
 	return SPICE_OK;
 }
 
-int spice_raster_size(spice_ctx* ctx, int64_t* n_steps_out, int64_t* n_ids_out) {
+namespace {
+// block until the first `upto` logged steps are in host memory
+int sink_wait(spice_ctx* ctx, long long upto) {
+	if (upto > ctx->sink_steps_complete) {
+		size_t k = 0; // the first mark that covers `upto` (marks are ascending)
+		while (k < ctx->sink_marks.size() && ctx->sink_marks[k].first < upto)
+			k++;
+		if (k < ctx->sink_marks.size()) {
+			CHECK_CUDA(ctx, cudaEventSynchronize(ctx->sink_marks[k].second));
+			ctx->sink_steps_complete = ctx->sink_marks[k].first;
+			for (size_t i = 0; i <= k; i++) {
+				ctx->sink_pool.push_back(ctx->sink_marks.front().second);
+				ctx->sink_marks.pop_front();
+			}
+		} else { // its mark was recycled
+			CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			ctx->sink_steps_complete = ctx->sink_steps_issued;
+		}
+	}
+	int const h = ctx->h_sink_error ? *reinterpret_cast<int volatile*>(ctx->h_sink_error) : 0;
+	if (h & 4)
+		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: step capacity exceeded (read the raster more often)");
+	if (h & 8)
+		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: id capacity exceeded (read the raster more often)");
+	return SPICE_OK;
+}
+}
+
+int spice_raster_size(spice_ctx* ctx, int64_t max_steps, int64_t* n_steps_out, int64_t* n_ids_out) {
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-	unsigned long long cur = 0;
-	if (ctx->d_cursor) {
-		int rc = check_device_error(ctx);
+	long long const avail = ctx->sink_steps_issued - ctx->sink_steps_read;
+	long long const n     = max_steps > 0 ? std::min<long long>(max_steps, avail) : avail;
+	long long ids         = 0;
+	if (n > 0) {
+		int const rc = sink_wait(ctx, ctx->sink_steps_read + n);
 		if (rc != SPICE_OK)
 			return rc;
-		CHECK_CUDA(ctx, cudaMemcpy(&cur, ctx->d_cursor, sizeof cur, cudaMemcpyDeviceToHost));
+		int const np = static_cast<int>(ctx->pops.size());
+		for (long long i = 0; i < n; i++)
+			for (int p = 0; p < np; p++)
+				ids += ctx->h_sink_cnt[((ctx->sink_steps_read + i) % ctx->sink_steps_cap) * np + p];
 	}
 	if (n_steps_out)
-		*n_steps_out = ctx->raster_steps;
+		*n_steps_out = n;
 	if (n_ids_out)
-		*n_ids_out = static_cast<int64_t>(cur);
+		*n_ids_out = ids;
 	return SPICE_OK;
 }
 
-int spice_raster_read(spice_ctx* ctx, int64_t* counts_out, int32_t* ids_out) {
+int spice_raster_read(spice_ctx* ctx, int64_t n_steps, int64_t* counts_out, int32_t* ids_out) {
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	int64_t steps = 0, nids = 0;
-	int rc = spice_raster_size(ctx, &steps, &nids);
+	int const rc = spice_raster_size(ctx, n_steps, &steps, &nids);
 	if (rc != SPICE_OK)
 		return rc;
+	PRE(ctx, n_steps <= 0 || steps == n_steps);
 	int const np = static_cast<int>(ctx->pops.size());
 	if (steps == 0 || np == 0)
 		return SPICE_OK;
-	std::vector<long long> off(static_cast<size_t>(steps) * np);
-	std::vector<std::int32_t> cnt(static_cast<size_t>(steps) * np * ctx->world);
-	std::vector<std::int32_t> raw(static_cast<size_t>(std::max<int64_t>(nids, 1)));
-	CHECK_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_log_off, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost));
-	CHECK_CUDA(ctx, cudaMemcpy(cnt.data(), ctx->d_log_cnt, sizeof(std::int32_t) * cnt.size(), cudaMemcpyDeviceToHost));
-	if (nids)
-		CHECK_CUDA(ctx, cudaMemcpy(raw.data(), ctx->d_log_ids, sizeof(std::int32_t) * static_cast<size_t>(nids), cudaMemcpyDeviceToHost));
-	long long at = 0;
-	for (long long i = 0; i < steps * np; i++) {
-		long long total = 0, from = off[static_cast<size_t>(i)];
-		for (int r = 0; r < ctx->world; r++) {
-			std::int32_t const c = cnt[static_cast<size_t>(i) * ctx->world + r];
-			std::sort(raw.begin() + from + total, raw.begin() + from + total + c);
-			total += c;
-		}
-		counts_out[i] = total;
-		std::memcpy(ids_out + at, raw.data() + from, sizeof(std::int32_t) * static_cast<size_t>(total));
-		at += total;
-	}
-	CHECK_CUDA(ctx, cudaMemset(ctx->d_cursor, 0, sizeof(unsigned long long)));
-	ctx->raster_steps = 0;
+	for (long long i = 0; i < steps; i++)
+		for (int p = 0; p < np; p++)
+			counts_out[i * np + p] = ctx->h_sink_cnt[((ctx->sink_steps_read + i) % ctx->sink_steps_cap) * np + p];
+	// the lists are consecutive in (step, population) order: one range of the ring, at most two pieces
+	unsigned long long const first = ctx->h_sink_off[(ctx->sink_steps_read % ctx->sink_steps_cap) * np];
+	unsigned long long const cap   = static_cast<unsigned long long>(ctx->sink_cap);
+	unsigned long long const at    = first % cap;
+	unsigned long long const head  = std::min<unsigned long long>(static_cast<unsigned long long>(nids), cap - at);
+	std::memcpy(ids_out, ctx->h_sink_ids + at, sizeof(std::int32_t) * head);
+	std::memcpy(ids_out + head, ctx->h_sink_ids, sizeof(std::int32_t) * (static_cast<unsigned long long>(nids) - head));
+	ctx->sink_steps_read += steps;
+	ctx->sink_ids_read = first + static_cast<unsigned long long>(nids);
+	reinterpret_cast<unsigned long long volatile*>(ctx->h_sink_consumed)[0] = static_cast<unsigned long long>(ctx->sink_steps_read);
+	reinterpret_cast<unsigned long long volatile*>(ctx->h_sink_consumed)[1] = ctx->sink_ids_read;
 	return SPICE_OK;
 }
 

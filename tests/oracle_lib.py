@@ -392,12 +392,42 @@ class RefShim:
         return self._run(fn, N, p, w_exc, w_inh, np.float32(dt), np.float32(delay), seed, steps, 3, N * 4 // 10,
                          N // 10, LIF_BRUNEL_DT, record)
 
+    def brunel_open(self, N, p, w_exc, w_inh, dt=1e-4, delay=15e-4, seed=1337):
+        """Incremental Brunel run of the compiled reference (bench.py's reference arm): -> BrunelRun."""
+        return BrunelRun(self.L, N, p, w_exc, w_inh, dt, delay, seed)
+
     def vogels(self, N=4000, p=0.02, w_exc=None, w_inh=None, dt=1e-4, delay=8e-4, seed=1337, steps=1500,
                record=True):
         w_exc = np.float32(6.4e6 / (N * N)) if w_exc is None else np.float32(w_exc)
         w_inh = np.float32(8.16e7 / (N * N)) if w_inh is None else np.float32(w_inh)
         return self._run("ref_vogels_run", N, p, w_exc, w_inh, np.float32(dt), np.float32(delay), seed, steps, 2,
                          N * 8 // 10, N * 2 // 10, LIF_VOGELS_DT, record)
+
+
+class BrunelRun:
+    """ref_brunel_open / ref_brunel_advance / ref_brunel_close (oracle/ref_shim.cpp)."""
+
+    def __init__(self, L, N, p, w_exc, w_inh, dt, delay, seed):
+        self.L = L
+        L.ref_brunel_open.restype = C.c_void_p
+        b = C.c_double()
+        self.h = C.c_void_p(L.ref_brunel_open(C.c_int64(N), C.c_double(p), C.c_float(w_exc), C.c_float(w_inh), C.c_float(dt),
+                                              C.c_float(delay), C.c_uint32(seed), C.byref(b)))
+        self.build_seconds = b.value
+
+    def advance(self, steps):
+        """-> (seconds inside snn::step(), Syn::deliver invocations, spikes emitted) for `steps` time steps"""
+        s, ev, sp = C.c_double(), C.c_int64(), C.c_int64()
+        self.L.ref_brunel_advance(self.h, C.c_int64(steps), C.byref(s), C.byref(ev), C.byref(sp))
+        return s.value, ev.value, sp.value
+
+    def close(self):
+        if self.h:
+            self.L.ref_brunel_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 def flatten_raster(rows):

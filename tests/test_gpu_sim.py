@@ -235,3 +235,53 @@ def test_device_libm_matches_host_pins(sp):
     py = np.zeros_like(px)
     assert sp.lib().spice_selftest_libm(0, 1, px.ctypes.data, pn.ctypes.data, py.ctypes.data, len(px)) == 0
     assert np.array_equal(py.view(np.uint64), z["pow_y"].astype(np.float64).view(np.uint64))
+
+
+def test_sink_partial_reads_and_wraparound(sp, orc, monkeypatch):
+    """The spike sink (spice_raster_*): readouts of any length, issued while later batches are still
+    queued, return the same lists as one big readout; the host ring wraps around."""
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=4000, p=0.1, w_exc=np.float32(2.0 / 400), w_inh=np.float32(-10.0 / 400))
+    net, _ = brunel(**kw)
+    counts0, ids0 = gpu_raster(net, 600, 600)
+    monkeypatch.setenv("SPICE_SINK_IDS", "4096")  # ~13 ids per step: the id ring wraps several times
+    monkeypatch.setenv("SPICE_SINK_STEPS", "128")
+    net, _ = brunel(**kw)
+    net.raster_enable(True)
+    got_c, got_i = [], []
+    issued = read = 0
+    rng = np.random.default_rng(5)
+    while read < 600:
+        while issued < 600 and issued - read < 45:
+            k = int(min(rng.integers(1, 31), 600 - issued))
+            net.step(k)
+            issued += k
+        k = int(min(rng.integers(1, 40), issued - read))
+        c, i = net.raster_read(k)
+        assert c.shape[0] == k
+        got_c.append(c)
+        got_i.append(i)
+        read += k
+    assert np.array_equal(np.concatenate(got_c), counts0)
+    assert np.array_equal(np.concatenate(got_i), ids0)
+    # an unread log that outgrows the ring is reported, not overwritten silently
+    net.step(300)
+    with pytest.raises(sp.SpiceError):
+        net.raster_read()
+
+
+def test_sink_large_population_sorted(sp):
+    """A population wider than one bitmap chunk (> 1,015,808 neurons): lists stay ascending and equal spikes(0)."""
+    net = sp.snn(1e-4, 15e-4, (7,))
+    P = net.add_population("brunel.poisson", 2_300_000)
+    net.raster_enable(True)
+    per_step = []
+    for _ in range(5):
+        net.step(1)
+        per_step.append(np.array(P.spikes(0)))
+    counts, ids = net.raster_read()
+    assert [int(c) for c in counts[:, 0]] == [len(x) for x in per_step]
+    assert np.array_equal(ids, np.concatenate(per_step))
+    for x in per_step:
+        assert len(x) > 3000 and np.all(np.diff(x) > 0)
