@@ -22,10 +22,13 @@
 //     costs ~3.1 shared-memory wavefronts per instruction instead of 1 and made the first
 //     version of this kernel LSU-bound at 39 % of the HBM roofline.  So every target has TWO
 //     u8 counters (arrays A and B, whose bank assignments differ by a per-row rotation), and
-//     once per connection arrange_runs() rewrites each run: every entry becomes the byte
-//     address of one of its target's two counters, chosen (2-choice balancing) and ordered so
-//     that the lanes of one instruction fall into different banks.  The canonical ascending
-//     order of a run is recovered by decoding and sorting (restore_runs);
+//     once per connection pack_runs() rewrites each run into the kernel's own stream format:
+//     every entry becomes the byte address of one of its target's two counters, chosen
+//     (2-choice balancing) and ordered so that the lanes of one instruction fall into
+//     different banks; a run is padded to whole 16-byte groups with addresses of a 128-byte
+//     dump area (in banks the instruction does not use), so the counting code needs no length,
+//     no alignment and no per-entry predicate: a lane either holds a whole group or nothing.
+//     The canonical ascending CSR row is recovered by decoding and sorting (unpack_rows);
 //   * a u8 counter holds 255: a warp counts at most 224 runs (7 batches) per round; after each
 //     round the CTA adds its 4 x 2 arrays and stores (first round) or adds (later rounds) the
 //     tile's counters to counts[slot(step + delay)][tile] with plain vector accesses: it is the
@@ -35,6 +38,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+
+#include <cub/device/device_scan.cuh>
 
 #include "deliver.h"
 
@@ -47,23 +52,16 @@ constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane a
 constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
 constexpr unsigned kFull   = 0xffffffffu;
 
-// count the (up to 4) entries of `v` that lie inside the run: entry i has index e0 + i, valid
-// when 0 <= e0 + i < len.  Entries are counter addresses (arrange_runs); the four targets are
-// distinct, so the loads may all precede the stores.
-__device__ __forceinline__ void tally(unsigned char* cnt, int4 v, int e0, int len) {
-	bool const p0 = static_cast<unsigned>(e0) < static_cast<unsigned>(len);
-	bool const p1 = static_cast<unsigned>(e0 + 1) < static_cast<unsigned>(len);
-	bool const p2 = static_cast<unsigned>(e0 + 2) < static_cast<unsigned>(len);
-	bool const p3 = static_cast<unsigned>(e0 + 3) < static_cast<unsigned>(len);
-	unsigned char c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-	if (p0) c0 = cnt[v.x];
-	if (p1) c1 = cnt[v.y];
-	if (p2) c2 = cnt[v.z];
-	if (p3) c3 = cnt[v.w];
-	if (p0) cnt[v.x] = c0 + 1;
-	if (p1) cnt[v.y] = c1 + 1;
-	if (p2) cnt[v.z] = c2 + 1;
-	if (p3) cnt[v.w] = c3 + 1;
+// count the 4 entries of `v` (counter addresses of 4 distinct targets, so the loads may all
+// precede the stores); a lane without a group holds v.x < 0
+__device__ __forceinline__ void tally(unsigned char* cnt, int4 v) {
+	if (v.x >= 0) {
+		unsigned char const c0 = cnt[v.x], c1 = cnt[v.y], c2 = cnt[v.z], c3 = cnt[v.w];
+		cnt[v.x] = c0 + 1;
+		cnt[v.y] = c1 + 1;
+		cnt[v.z] = c2 + 1;
+		cnt[v.w] = c3 + 1;
+	}
 }
 
 // zero counters [0, bytes) of array A and of array B (bytes a multiple of 128)
@@ -83,17 +81,17 @@ __device__ __forceinline__ int4 ldg_stream(void const* p) {
 	return v;
 }
 
-// One run (a tile's share of one spiking source's row) as the pipeline sees it.
+// One run (a tile's share of one spiking source's row) as the pipeline sees it: groups
+// [g0, g0 + ng) of the connection's packed stream (a group = 16 bytes = 4 entries).
 struct run_desc {
-	unsigned long long at; // address of the 16-byte group that holds the run's first entry
-	int len;               // entries in the run (0: nothing to do)
-	int mis;               // entries of that group that precede the run (0..3)
+	unsigned g0, ng;
 };
 
-// shared memory of one warp: [descriptors: 2 batches x 32 x 16 B][counters: 2 arrays x tile_cap x 1 B]
+// shared memory of one warp: [descriptors: 2 batches x 32 x 8 B][counters: 2 arrays x tile_cap x 1 B][dump: 128 B]
 constexpr int kDescBytes = 2 * 32 * static_cast<int>(sizeof(run_desc));
+constexpr int kDumpBytes = 128;
 __host__ __device__ constexpr size_t warp_smem(int tile_cap) {
-	return static_cast<size_t>(kDescBytes) + 2 * static_cast<size_t>(tile_cap);
+	return static_cast<size_t>(kDescBytes) + 2 * static_cast<size_t>(tile_cap) + kDumpBytes;
 }
 
 // What a unit needs to know, worked out once per CTA.
@@ -102,8 +100,9 @@ struct unit_info {
 	int lo, width;            // the tile's targets [lo, lo + width) (local indices)
 	std::uint32_t* out;       // counts[slot(step + delay)] + lo
 	std::int32_t const* ids0; // the step's slot of the source population's spike ring
-	long long const* tile_ptr;
-	int stride;               // tiles + 1
+	unsigned const* gp;       // run_ptr + tile index: run of source i = groups [gp[i * tiles], gp[i * tiles + 1])
+	long long const* tile_ptr; // plain connections: tile_ptr + tile index, stride tiles + 1
+	int stride;               // tiles (packed) / tiles + 1 (plain)
 	unsigned total;           // spikes of the step (all ranks)
 	long long ring_slot;
 };
@@ -111,10 +110,10 @@ struct unit_info {
 // One warp's pipeline over its share of a unit: the batches b = first, first + step, ... of the
 // step's spike list (a batch = 32 consecutive spikes = 32 runs, padded with empty runs).
 // In flight at any time:
-//   * registers: the spike ids of the batch after next, the tile pointers of the next batch;
+//   * registers: the spike ids of the batch after next, the run pointers of the next batch;
 //   * shared memory: the descriptors of the current and the next batch;
-//   * registers: the column indices of the next kRing runs on their way from HBM (one 16-byte
-//     load per lane and run), and the run being counted.
+//   * registers: the entries of the next kRing runs on their way from HBM (one 16-byte load per
+//     lane and run), and the run being counted.
 // The loop over a half batch is fully unrolled, so the kRing landing slots are plain registers.
 // One call counts the batches of one round (at most kRoundBatches, so no u8 counter can wrap).
 struct unit_walker {
@@ -123,11 +122,10 @@ struct unit_walker {
 	unsigned char* smem; // this warp's
 	int lane;
 	unsigned char* cnt;
+	int4 const* stream;  // the connection's packed stream
 	unsigned my_n, my_first;
-	long long p_beg; // this lane's run of the batch whose descriptors are written next
-	int p_len;
+	unsigned p_g0, p_ng; // this lane's run of the batch whose descriptors are written next
 	std::int32_t id_next; // this lane's spike of the batch after that
-	long long ev;
 
 	__device__ __forceinline__ std::int32_t spike_id(unsigned q) const { // flat index -> source neuron (0 when q >= total)
 		int r       = 0;
@@ -143,44 +141,37 @@ struct unit_walker {
 		return q < U.total ? U.ids0[U.C->seg_lo[r] + (q - f0)] : 0;
 	}
 	__device__ __forceinline__ void load_ptrs(unsigned q, std::int32_t id) {
-		p_beg = 0, p_len = 0;
+		p_g0 = 0, p_ng = 0;
 		if (q < U.total) {
-			long long const* p = U.tile_ptr + static_cast<long long>(id) * U.stride;
-			p_beg              = p[0];
-			p_len              = static_cast<int>(p[1] - p_beg);
+			unsigned const* p = U.gp + static_cast<long long>(id) * U.stride;
+			p_g0              = p[0];
+			p_ng              = p[1] - p_g0;
 		}
 	}
-	// publish the descriptors of the i-th batch of this warp (from p_beg / p_len), then start
+	// publish the descriptors of the i-th batch of this warp (from p_g0 / p_ng), then start
 	// fetching the pointers of batch `b_next` and the ids of batch `b_next + step`
 	__device__ __forceinline__ void write_desc(unsigned i, unsigned b_next, unsigned step) {
-		ev += p_len;
-		int const mis = static_cast<int>(p_beg & 3);
-		run_desc d;
-		d.at  = reinterpret_cast<unsigned long long>(U.C->neighbors + (p_beg - mis));
-		d.len = p_len;
-		d.mis = mis;
-		reinterpret_cast<run_desc*>(smem)[(i & 1) * 32 + lane] = d;
+		reinterpret_cast<run_desc*>(smem)[(i & 1) * 32 + lane] = run_desc{p_g0, p_ng};
 		unsigned const q = b_next * 32 + lane;
 		load_ptrs(q, id_next);
 		id_next = spike_id(q + step * 32);
 		__syncwarp();
 	}
 
-	// start fetching the run described by `d`; returns this lane's 16 bytes of it (in flight)
+	// start fetching the run described by `d`; returns this lane's group of it (in flight)
 	__device__ __forceinline__ int4 issue(run_desc const* d) {
-		run_desc const r       = *d;
-		int const e0           = lane * 4 - r.mis; // index inside the run of this lane's first entry
-		unsigned char const* g = reinterpret_cast<unsigned char const*>(r.at) + lane * 16;
-		int4 v                 = make_int4(0, 0, 0, 0);
-		if (e0 < r.len)
+		run_desc const r = *d;
+		int4 const* g    = stream + r.g0 + lane;
+		int4 v           = make_int4(-1, 0, 0, 0);
+		if (static_cast<unsigned>(lane) < r.ng)
 			v = ldg_stream(g);
-		if (128 - r.mis < r.len) { // run longer than one warp-wide load (rare: tiles are sized for ~100 entries):
-			__syncwarp();          // count the rest right away, between two other runs' turns
-			for (int off = 128; off - r.mis < r.len; off += 128) {
-				int4 w = make_int4(0, 0, 0, 0);
-				if (e0 + off < r.len)
-					w = ldg_stream(g + off * 4);
-				tally(cnt, w, e0 + off, r.len);
+		if (r.ng > 32) { // run longer than one warp-wide load (rare: tiles are sized for ~100 entries):
+			__syncwarp(); // count the rest right away, between two other runs' turns
+			for (unsigned off = 32; off < r.ng; off += 32) {
+				int4 w = make_int4(-1, 0, 0, 0);
+				if (off + lane < r.ng)
+					w = ldg_stream(g + off);
+				tally(cnt, w);
 			}
 			__syncwarp();
 		}
@@ -189,7 +180,8 @@ struct unit_walker {
 
 	// batches first, first + step, ... (< nbatch)
 	__device__ __forceinline__ void run(unsigned first, unsigned step, unsigned nbatch) {
-		cnt = smem + kDescBytes;
+		cnt    = smem + kDescBytes;
+		stream = reinterpret_cast<int4 const*>(U.C->packed);
 		// the step's spike list: one segment per rank; lane r keeps segment r's start in the flat order
 		my_n = 0;
 		if (lane < a.world)
@@ -203,7 +195,6 @@ struct unit_walker {
 		my_first -= my_n; // exclusive prefix
 
 		zero_tile(cnt, a.tile_cap, (U.width + 127) & ~127, lane);
-		ev = 0;
 		unsigned const mine = first < nbatch ? (nbatch - first + step - 1) / step : 0; // batches of this warp
 		if (mine > 0) {
 			id_next = spike_id(first * 32 + lane);
@@ -222,21 +213,15 @@ struct unit_walker {
 					unsigned const i = (h + 1) >> 1; // its descriptors come from batch first + i * step
 					write_desc(i, first + (i + 1) * step, step);
 				}
-				run_desc const* const cd = desc + ((h >> 1) & 1) * 32 + (h & 1) * 16;
 				run_desc const* const id = desc + (((h + 1) >> 1) & 1) * 32 + ((h + 1) & 1) * 16;
 #pragma unroll
 				for (int j = 0; j < kRing; j++) {
-					int2 const m = *reinterpret_cast<int2 const*>(&cd[j].len);
-					tally(cnt, v[j], lane * 4 - m.y, m.x);
+					tally(cnt, v[j]);
 					__syncwarp();
 					v[j] = issue(id + j);
 				}
 			}
 		}
-		for (int off = 16; off; off >>= 1)
-			ev += __shfl_xor_sync(kFull, ev, off);
-		if (lane == 0 && ev)
-			atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
 	}
 };
 
@@ -288,8 +273,9 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				U.out       = C.counts + ((t + C.delay) % C.cring) * C.cstride + U.lo;
 				U.ring_slot = t % a.ring;
 				U.ids0      = C.ring_ids + U.ring_slot * C.ring_cap;
+				U.gp        = C.run_ptr + k;
 				U.tile_ptr  = C.tile_ptr + k;
-				U.stride    = C.tiles + 1;
+				U.stride    = C.arranged ? C.tiles : C.tiles + 1;
 				unsigned total = 0;
 				for (int r = 0; r < a.world; r++)
 					total += C.ring_cnt[U.ring_slot * a.world + r];
@@ -321,8 +307,10 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 			__syncthreads();
 			// add the warps' arrays and store / accumulate: this CTA is the only writer of the range.
 			// Word wd of array A holds targets 4 wd .. 4 wd + 3; their B counters sit in the same
-			// 128-byte row r = wd / 32, rotated by r words.
-			uint4* o = reinterpret_cast<uint4*>(U.out);
+			// 128-byte row r = wd / 32, rotated by r words.  The sum of all counters is the number
+			// of Syn::deliver invocations this round stands for.
+			uint4* o    = reinterpret_cast<uint4*>(U.out);
+			unsigned ev = 0;
 			for (int wd = threadIdx.x; wd < words; wd += kWarps * 32) {
 				int const r = wd >> 5;
 				int const wb = (wd & ~31) | ((wd + r) & 31);
@@ -336,32 +324,52 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 					odd += ((ca >> 8) & 0x00ff00ffu) + ((cb >> 8) & 0x00ff00ffu);
 				}
 				uint4 c = make_uint4(even & 0xffffu, odd & 0xffffu, even >> 16, odd >> 16);
+				ev += c.x + c.y + c.z + c.w;
 				if (round) {
 					uint4 const prev = o[wd];
 					c.x += prev.x, c.y += prev.y, c.z += prev.z, c.w += prev.w;
 				}
 				o[wd] = c;
 			}
+			for (int off = 16; off; off >>= 1)
+				ev += __shfl_xor_sync(kFull, ev, off);
+			if (lane == 0 && ev)
+				atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
 			__syncthreads();
 		}
 	}
 }
 
-// ---- arrange_runs / restore_runs -----------------------------------------------------------------
+// ---- pack_runs / unpack_rows ---------------------------------------------------------------------
 // Counter addresses of local target t of a tile (t < cap, cap a multiple of 128):
 //   array A: t                       (bank (t >> 2) & 31)
 //   array B: cap + rot(t),  rot(t) = t with its bank field rotated by the 128-byte row number
 //                                      (bank ((t >> 2) + (t >> 7)) & 31)
+//   dump:    2 cap + 4 bank + byte   (never read back)
 // Two targets that share a bank in A never share one in B (for tiles of <= 32 rows), which is what
 // makes the 2-choice balancing effective.
 __host__ __device__ __forceinline__ int rot_fwd(int t) { return (t & ~0x7c) | ((t + ((t >> 7) << 2)) & 0x7c); }
 __host__ __device__ __forceinline__ int rot_inv(int u) { return (u & ~0x7c) | ((u - ((u >> 7) << 2)) & 0x7c); }
 
-// One thread per run.  A run is processed in chunks of <= 128 entries aligned like the delivery
-// kernel's 16-byte loads: the entry at global position g is counted by instruction (g & 3) of its
-// chunk, together with the entries at g +- 4, +- 8, ... — those must fall into different banks.
-__global__ void __launch_bounds__(128) arrange_kernel(std::int32_t* nb, long long const* tile_ptr, long long n_runs, int tiles,
-                                                      int tile, int cap) {
+// groups of every run: run_ptr[id] = ceil(len / 4) (scanned afterwards); id = row * tiles + k
+__global__ void __launch_bounds__(256) run_groups_kernel(long long const* tile_ptr, long long n_runs, int tiles, unsigned* run_ptr) {
+	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (id > n_runs)
+		return;
+	unsigned g = 0;
+	if (id < n_runs) {
+		long long const row = id / tiles;
+		int const k         = static_cast<int>(id % tiles);
+		g = static_cast<unsigned>((tile_ptr[row * (tiles + 1) + k + 1] - tile_ptr[row * (tiles + 1) + k] + 3) >> 2);
+	}
+	run_ptr[id] = g;
+}
+
+// One thread per run.  A run is packed in chunks of <= 128 entries = 32 groups: the entry at
+// position p of a chunk is counted by lane p >> 2 in instruction p & 3, together with the entries
+// at p +- 4, +- 8, ... — those must fall into different banks.
+__global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long long const* tile_ptr, unsigned const* run_ptr,
+                                                   long long n_runs, int tiles, int tile, int cap, std::int32_t* packed) {
 	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (id >= n_runs)
 		return;
@@ -369,14 +377,14 @@ __global__ void __launch_bounds__(128) arrange_kernel(std::int32_t* nb, long lon
 	int const k         = static_cast<int>(id % tiles);
 	long long const beg = tile_ptr[row * (tiles + 1) + k], end = tile_ptr[row * (tiles + 1) + k + 1];
 	int const lo        = k * tile;
+	std::int32_t* out   = packed + static_cast<long long>(run_ptr[id]) * 4;
 	unsigned short t[128];
 	unsigned char bank[128]; // chosen bank | array << 7
 	unsigned char order[128];
 	unsigned char load[32], first[33];
-	for (long long cb = beg & ~3ll; cb < end; cb += 128) {
-		long long const g0 = cb > beg ? cb : beg;
-		long long const g1 = cb + 128 < end ? cb + 128 : end;
-		int const m        = static_cast<int>(g1 - g0);
+	for (long long g0 = beg; g0 < end; g0 += 128, out += 128) {
+		int const m     = static_cast<int>(end - g0 < 128 ? end - g0 : 128);
+		int const slots = (m + 3) & ~3;
 		for (int b = 0; b < 32; b++)
 			load[b] = 0;
 		// 2-choice greedy, then two passes that move entries out of banks more than one fuller than their alternative
@@ -416,13 +424,13 @@ __global__ void __launch_bounds__(128) arrange_kernel(std::int32_t* nb, long lon
 			order[first[b] + load[b]] = static_cast<unsigned char>(j);
 			load[b]++;
 		}
-		// the four instructions of the chunk: how many positions each has, and its next free position
-		int rem[4];
-		long long next[4];
+		// the four instructions of the chunk: free positions, the next free position, the banks in use
+		int rem[4], next[4];
+		unsigned used_banks[4];
 		for (int c = 0; c < 4; c++) {
-			long long const f = g0 + ((c - g0) & 3); // first position >= g0 with (g & 3) == c
-			next[c]           = f;
-			rem[c]            = f < g1 ? static_cast<int>((g1 - f + 3) >> 2) : 0;
+			next[c]       = c;
+			rem[c]        = slots >> 2;
+			used_banks[c] = 0;
 		}
 		// fullest banks first; the entries of one bank go to different instructions, the emptiest first
 		for (int L = maxload; L >= 1; L--)
@@ -442,42 +450,53 @@ __global__ void __launch_bounds__(128) arrange_kernel(std::int32_t* nb, long lon
 								best = c;
 					}
 					used |= 1u << best;
+					used_banks[best] |= 1u << b;
 					rem[best]--;
 					int const j  = order[first[b] + i];
 					int const tt = t[j];
-					nb[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
+					out[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
 					next[best] += 4;
 				}
+			}
+		// pad to whole groups with dump addresses in banks the instruction does not use
+		for (int c = 0; c < 4; c++)
+			for (; rem[c] > 0; rem[c]--, next[c] += 4) {
+				unsigned const free_banks = ~used_banks[c];
+				int const b               = free_banks ? __ffs(free_banks) - 1 : 0;
+				used_banks[c] |= 1u << b;
+				out[next[c]] = 2 * cap + 4 * b + c;
 			}
 	}
 }
 
-// One thread per run: decode the counter addresses back to local columns and emit them ascending.
-__global__ void __launch_bounds__(128) restore_kernel(std::int32_t const* nb, long long const* tile_ptr, long long n_runs, int tiles,
-                                                      int tile, int cap, std::int32_t* out) {
-	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (id >= n_runs)
+// One thread per row: decode the counter addresses of the row's runs back to local columns and
+// emit them ascending (tiles in order, a bitmap per tile).
+__global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets,
+                                                     long long n_rows, int tiles, int tile, int cap, std::int32_t* out) {
+	long long const row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (row >= n_rows)
 		return;
-	long long const row = id / tiles;
-	int const k         = static_cast<int>(id % tiles);
-	long long const beg = tile_ptr[row * (tiles + 1) + k], end = tile_ptr[row * (tiles + 1) + k + 1];
-	int const lo        = k * tile;
 	unsigned present[kTileMax / 32];
 	int const words = (tile + 31) / 32;
-	for (int i = 0; i < words; i++)
-		present[i] = 0;
-	for (long long e = beg; e < end; e++) {
-		int const v = nb[e];
-		int const t = v < cap ? v : rot_inv(v - cap);
-		present[t >> 5] |= 1u << (t & 31);
-	}
-	long long o = beg;
-	for (int i = 0; i < words; i++) {
-		unsigned m = present[i];
-		while (m) {
-			int const bit = __ffs(m) - 1;
-			m &= m - 1;
-			out[o++] = lo + i * 32 + bit;
+	long long o     = offsets[row];
+	for (int k = 0; k < tiles; k++) {
+		for (int i = 0; i < words; i++)
+			present[i] = 0;
+		long long const beg = static_cast<long long>(run_ptr[row * tiles + k]) * 4, end = static_cast<long long>(run_ptr[row * tiles + k + 1]) * 4;
+		for (long long e = beg; e < end; e++) {
+			int const v = packed[e];
+			if (v >= 2 * cap)
+				continue;
+			int const t = v < cap ? v : rot_inv(v - cap);
+			present[t >> 5] |= 1u << (t & 31);
+		}
+		for (int i = 0; i < words; i++) {
+			unsigned m = present[i];
+			while (m) {
+				int const bit = __ffs(m) - 1;
+				m &= m - 1;
+				out[o++] = k * tile + i * 32 + bit;
+			}
 		}
 	}
 }
@@ -515,21 +534,46 @@ int build_tile_ptr(void* stream, long long const* offsets, std::int32_t const* n
 	return static_cast<int>(cudaGetLastError());
 }
 
-int arrange_runs(void* stream, std::int32_t* neighbors, long long const* tile_ptr, long long src_count, int tile, int tiles,
-                 int cap) {
+int count_groups(void* stream, long long const* tile_ptr, long long src_count, int tiles, unsigned* run_ptr, long long* groups_out) {
+	auto st           = static_cast<cudaStream_t>(stream);
+	long long const n = src_count * tiles;
+	run_groups_kernel<<<static_cast<unsigned>((n + 1 + 255) / 256), 256, 0, st>>>(tile_ptr, n, tiles, run_ptr);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return static_cast<int>(e);
+	void* tmp    = nullptr;
+	size_t bytes = 0;
+	e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, run_ptr, run_ptr, static_cast<long long>(n + 1), st);
+	if (e != cudaSuccess)
+		return static_cast<int>(e);
+	e = cudaMalloc(&tmp, std::max<size_t>(bytes, 16));
+	if (e != cudaSuccess)
+		return static_cast<int>(e);
+	e = cub::DeviceScan::ExclusiveSum(tmp, bytes, run_ptr, run_ptr, static_cast<long long>(n + 1), st);
+	unsigned total = 0;
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&total, run_ptr + n, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cudaFree(tmp);
+	*groups_out = total;
+	return static_cast<int>(e);
+}
+
+int pack_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, unsigned const* run_ptr, long long src_count,
+              int tile, int tiles, int cap, std::int32_t* packed) {
 	long long const n = src_count * tiles;
 	if (n > 0)
-		arrange_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, n, tiles,
-		                                                                                                    tile, cap);
+		pack_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, run_ptr, n,
+		                                                                                                 tiles, tile, cap, packed);
 	return static_cast<int>(cudaGetLastError());
 }
 
-int restore_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, long long src_count, int tile,
-                 int tiles, int cap, std::int32_t* out) {
-	long long const n = src_count * tiles;
-	if (n > 0)
-		restore_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, n, tiles,
-		                                                                                                    tile, cap, out);
+int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets, long long src_count,
+                int tile, int tiles, int cap, std::int32_t* out) {
+	if (src_count > 0)
+		unpack_kernel<<<static_cast<unsigned>((src_count + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+		    packed, run_ptr, offsets, src_count, tiles, tile, cap, out);
 	return static_cast<int>(cudaGetLastError());
 }
 

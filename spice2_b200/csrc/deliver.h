@@ -16,8 +16,10 @@ struct conn_desc {
 	std::uint32_t const* ring_cnt; // [ring][world]
 	long long ring_cap;
 	long long seg_lo[spice::detail::kMaxWorld]; // first source neuron of every rank's segment of a ring slot
-	std::int32_t const* neighbors; // CSR entries: arranged connections hold counter addresses (see arrange_runs), others local columns
-	long long const* tile_ptr;     // [src][tiles + 1]: where each tile's share of the row starts
+	std::int32_t const* packed;    // arranged connections: the delivery stream (see pack_runs)
+	unsigned const* run_ptr;       // arranged connections: [src * tiles + 1] first 16-byte group of every run
+	std::int32_t const* neighbors; // plain connections: CSR entries (local columns)
+	long long const* tile_ptr;     // plain connections: [src][tiles + 1]: where each tile's share of the row starts
 	std::uint32_t* counts;         // [cring][cstride] event counters of the TARGET population
 	long long n_dst;               // local targets
 	long long cstride;             // multiple of 8, >= n_dst
@@ -26,7 +28,7 @@ struct conn_desc {
 	std::int32_t tiles;            // number of target tiles
 	std::int32_t tile;             // targets per tile (multiple of 256, <= kTileMax)
 	std::int32_t tile_prefix;      // tiles of the connections scheduled before this one
-	std::int32_t arranged;         // 1: entries were rewritten by arrange_runs (fast path); 0: plain columns, counted with
+	std::int32_t arranged;         // 1: packed stream (fast path); 0: plain columns, counted with
 	                               //    global atomics (rows that may hold duplicate targets: adj_list multapses)
 	std::int32_t pad;
 };
@@ -49,16 +51,19 @@ struct tiles_args {
 int build_tile_ptr(void* stream, long long const* offsets, std::int32_t const* neighbors, long long src_count, int tile,
                    int tiles, long long* tile_ptr);
 
-// Rewrite the entries of every run (a tile's share of a row) for the fast delivery path: each entry
-// becomes the byte address of one of its target's two u8 counters (array A at [0, cap), array B at
-// [cap, 2 cap) with the bank rotated by the 128-byte row), and the entries of a run are permuted so
-// that the 32 lanes of one counting instruction hit 32 different shared-memory banks.  The rows of
-// the connection must be free of duplicate targets.  `cap` must equal tiles_args::tile_cap.
-// restore_runs writes the canonical (ascending, local column) entries of [0, edges) into `out`.
-int arrange_runs(void* stream, std::int32_t* neighbors, long long const* tile_ptr, long long src_count, int tile, int tiles,
-                 int cap);
-int restore_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, long long src_count, int tile,
-                 int tiles, int cap, std::int32_t* out);
+// The fast path's own stream format, built once per duplicate-free connection from its CSR:
+// every run (a tile's share of a row) becomes whole 16-byte groups of counter byte addresses —
+// array A at [0, cap), array B at [cap, 2 cap) with the bank rotated by the 128-byte row, a dump
+// area at [2 cap, 2 cap + 128) for padding — permuted so that the 32 lanes of one counting
+// instruction hit 32 different shared-memory banks.  `cap` must equal tiles_args::tile_cap.
+//   count_groups: run_ptr[src * tiles + 1] (exclusive scan of the runs' group counts) and their sum;
+//   pack_runs:    fills `packed` (4 * groups entries);
+//   unpack_rows:  the canonical (ascending, local column) CSR entries of [0, edges) into `out`.
+int count_groups(void* stream, long long const* tile_ptr, long long src_count, int tiles, unsigned* run_ptr, long long* groups_out);
+int pack_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, unsigned const* run_ptr, long long src_count,
+              int tile, int tiles, int cap, std::int32_t* packed);
+int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets, long long src_count,
+                int tile, int tiles, int cap, std::int32_t* out);
 
 // One launch delivers every spike of the window on every connection.  `blocks` <= 0 picks a
 // persistent grid filling the device.  Returns a cudaError_t as int.

@@ -389,7 +389,9 @@ struct connection {
 	long long* tile_ptr       = nullptr; // [src][tiles + 1]
 	int tile = 0, tiles = 0;
 	bool duplicates           = false;   // rows may repeat a target (adj_list)
-	bool arranged             = false;   // neighbors hold counter addresses (deliver::arrange_runs), not columns
+	bool arranged             = false;   // the CSR entries were replaced by the delivery stream (deliver::pack_runs)
+	std::int32_t* packed      = nullptr; // arranged: 4 * groups entries
+	unsigned* run_ptr         = nullptr; // arranged: [src * tiles + 1]
 	// stateful / plastic synapses (window = 1 step; spice/detail/model_ops.cuh)
 	bool stateful = false, plastic = false;
 	std::uint32_t* syn        = nullptr; // word-SoA synapse state, parallel to neighbors
@@ -608,9 +610,6 @@ int finalize(spice_ctx* ctx) {
 			c.tiles              = static_cast<int>((n + b - 1) / b);
 			c.tile               = static_cast<int>(std::min<long long>(b, static_cast<long long>(align_up(static_cast<size_t>((n + c.tiles - 1) / c.tiles), 256))));
 			c.tiles              = static_cast<int>((n + c.tile - 1) / c.tile);
-			CHECK_CUDA(ctx, cudaMalloc(&c.tile_ptr, sizeof(long long) * static_cast<size_t>(src.size) * static_cast<size_t>(c.tiles + 1)));
-			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::build_tile_ptr(ctx->stream, c.offsets, c.neighbors, src.size, c.tile, c.tiles, c.tile_ptr)));
-			ctx->launches++;
 		}
 	}
 	if (ctx->tiled) {
@@ -620,6 +619,34 @@ int finalize(spice_ctx* ctx) {
 			if (ctx->conns[ci].tiles > 0)
 				order.push_back(static_cast<int>(ci));
 		std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->pops[ctx->conns[x].src].size > ctx->pops[ctx->conns[y].src].size; });
+		for (int ci : order)
+			ctx->tile_cap = std::max(ctx->tile_cap, static_cast<int>(align_up(static_cast<size_t>(ctx->conns[ci].tile), 128)));
+		// where each tile's share of a row starts; duplicate-free connections are then rewritten into
+		// the delivery kernel's own stream (bank-balanced counter addresses in whole 16-byte groups,
+		// deliver.h) and give their CSR entries back
+		for (int ci : order) {
+			connection& c         = ctx->conns[ci];
+			long long const n_src = ctx->pops[c.src].size;
+			CHECK_CUDA(ctx, cudaMalloc(&c.tile_ptr, sizeof(long long) * static_cast<size_t>(n_src) * static_cast<size_t>(c.tiles + 1)));
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::build_tile_ptr(ctx->stream, c.offsets, c.neighbors, n_src, c.tile, c.tiles, c.tile_ptr)));
+			ctx->launches++;
+			long long const n_runs = n_src * c.tiles;
+			if (c.duplicates || c.edges / 4 + n_runs >= (1ll << 32)) // multapses / more groups than 32-bit run pointers address
+				continue;
+			CHECK_CUDA(ctx, cudaMalloc(&c.run_ptr, sizeof(unsigned) * static_cast<size_t>(n_runs + 1)));
+			long long groups = 0;
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::count_groups(ctx->stream, c.tile_ptr, n_src, c.tiles, c.run_ptr, &groups)));
+			CHECK_CUDA(ctx, cudaMalloc(&c.packed, sizeof(std::int32_t) * 4 * static_cast<size_t>(std::max<long long>(groups, 1))));
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::pack_runs(ctx->stream, c.neighbors, c.tile_ptr, c.run_ptr, n_src, c.tile, c.tiles,
+			                                                           ctx->tile_cap, c.packed)));
+			ctx->launches += 3;
+			CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			CHECK_CUDA(ctx, cudaFree(c.neighbors));
+			CHECK_CUDA(ctx, cudaFree(c.tile_ptr));
+			c.neighbors = nullptr;
+			c.tile_ptr  = nullptr;
+			c.arranged  = true;
+		}
 		std::vector<deliver::conn_desc> descs;
 		for (int ci : order) {
 			connection const& c = ctx->conns[ci];
@@ -631,6 +658,8 @@ int finalize(spice_ctx* ctx) {
 			d.ring_cap = std::max<long long>(src.size, 1);
 			for (int r = 0; r < ctx->world; r++)
 				d.seg_lo[r] = src.size * r / ctx->world;
+			d.packed      = c.packed;
+			d.run_ptr     = c.run_ptr;
 			d.neighbors   = c.neighbors;
 			d.tile_ptr    = c.tile_ptr;
 			d.counts      = c.counts;
@@ -641,20 +670,9 @@ int finalize(spice_ctx* ctx) {
 			d.tiles       = c.tiles;
 			d.tile        = c.tile;
 			d.tile_prefix = ctx->total_tiles;
-			d.arranged    = c.duplicates ? 0 : 1;
+			d.arranged    = c.arranged ? 1 : 0;
 			ctx->total_tiles += c.tiles;
-			ctx->tile_cap = std::max(ctx->tile_cap, static_cast<int>(align_up(static_cast<size_t>(c.tile), 128)));
 			descs.push_back(d);
-		}
-		// fast path: rewrite every run of the duplicate-free connections as bank-balanced counter addresses (deliver.h)
-		for (int ci : order) {
-			connection& c = ctx->conns[ci];
-			if (c.duplicates)
-				continue;
-			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::arrange_runs(ctx->stream, c.neighbors, c.tile_ptr, ctx->pops[c.src].size, c.tile,
-			                                                              c.tiles, ctx->tile_cap)));
-			c.arranged = true;
-			ctx->launches++;
 		}
 		if (!descs.empty()) {
 			CHECK_CUDA(ctx, cudaMalloc(&ctx->d_conn_desc, sizeof(deliver::conn_desc) * descs.size()));
@@ -1194,6 +1212,8 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 		cudaFree(c.neighbors);
 		cudaFree(c.counts);
 		cudaFree(c.tile_ptr);
+		cudaFree(c.packed);
+		cudaFree(c.run_ptr);
 		cudaFree(c.syn);
 		cudaFree(c.ages);
 		cudaFree(c.evt_cnt);
@@ -1386,12 +1406,12 @@ int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t
 	if (neighbors_out && c.edges) {
 		std::int32_t const* from = c.neighbors;
 		std::int32_t* tmp        = nullptr;
-		if (c.arranged) { // the delivery kernel's layout -> ascending local columns
+		if (c.arranged) { // the delivery kernel's stream -> ascending local columns
 			CHECK_CUDA(ctx, cudaMalloc(&tmp, sizeof(std::int32_t) * static_cast<size_t>(c.edges)));
-			int const e = deliver::restore_runs(ctx->stream, c.neighbors, c.tile_ptr, ctx->pops[c.src].size, c.tile, c.tiles, ctx->tile_cap, tmp);
+			int const e = deliver::unpack_rows(ctx->stream, c.packed, c.run_ptr, c.offsets, ctx->pops[c.src].size, c.tile, c.tiles, ctx->tile_cap, tmp);
 			if (e != 0) {
 				cudaFree(tmp);
-				return fail(ctx, SPICE_ERR_CUDA, std::string("restore_runs: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+				return fail(ctx, SPICE_ERR_CUDA, std::string("unpack_rows: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
 			}
 			from = tmp;
 		}
