@@ -52,15 +52,30 @@ constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane a
 constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
 constexpr unsigned kFull   = 0xffffffffu;
 
-// count the 4 entries of `v` (counter addresses of 4 distinct targets, so the loads may all
-// precede the stores); a lane without a group holds v.x < 0
+// A stream entry names one u8 counter by the byte offset of its 32-bit word (bits 31..16) and, in
+// bits 15..0, the PRMT selector that turns the constant 1 into "+1 in that byte": 0x4444 with the
+// byte's nibble cleared.  So the counting code forms address and increment with one instruction each.
+__host__ __device__ __forceinline__ std::int32_t encode_entry(int byte_addr) {
+	return static_cast<std::int32_t>((static_cast<unsigned>(byte_addr & ~3) << 16) | (0x4444u & ~(0xfu << (4 * (byte_addr & 3)))));
+}
+__host__ __device__ __forceinline__ int decode_entry(std::int32_t e) { // -> byte offset of the counter
+	unsigned const free_nibble = ~static_cast<unsigned>(e) & 0x4444u;  // bit 4 k + 2
+	int k = 0;
+	while (k < 3 && !((free_nibble >> (4 * k + 2)) & 1u))
+		k++;
+	return static_cast<int>(static_cast<unsigned>(e) >> 16) + k;
+}
+
+// count the 4 entries of `v` (counters of 4 distinct targets, so the loads may all precede the
+// stores); a lane without a group holds v.x < 0
 __device__ __forceinline__ void tally(unsigned char* cnt, int4 v) {
 	if (v.x >= 0) {
-		unsigned char const c0 = cnt[v.x], c1 = cnt[v.y], c2 = cnt[v.z], c3 = cnt[v.w];
-		cnt[v.x] = c0 + 1;
-		cnt[v.y] = c1 + 1;
-		cnt[v.z] = c2 + 1;
-		cnt[v.w] = c3 + 1;
+		int const a0 = decode_entry(v.x), a1 = decode_entry(v.y), a2 = decode_entry(v.z), a3 = decode_entry(v.w);
+		unsigned char const c0 = cnt[a0], c1 = cnt[a1], c2 = cnt[a2], c3 = cnt[a3];
+		cnt[a0] = c0 + 1;
+		cnt[a1] = c1 + 1;
+		cnt[a2] = c2 + 1;
+		cnt[a3] = c3 + 1;
 	}
 }
 
@@ -77,13 +92,14 @@ __device__ __forceinline__ void zero_tile(unsigned char* cnt, int cap, int bytes
 
 __device__ __forceinline__ int4 ldg_stream(void const* p) {
 	int4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	// "memory": the load keeps its place between the counting code around it — that order IS the software pipeline
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
 	return v;
 }
 
 // One run (a tile's share of one spiking source's row) as the pipeline sees it: groups
 // [g0, g0 + ng) of the connection's packed stream (a group = 16 bytes = 4 entries).
-struct run_desc {
+struct alignas(8) run_desc {
 	unsigned g0, ng;
 };
 
@@ -340,6 +356,29 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 	}
 }
 
+// ---- deliver_stream: producer/consumer variants (deliver_stream.inc) --------------------------------
+#define SK_NS sk8x4
+#define SK_FLIGHT 8
+#define SK_CTAS 4
+#include "deliver_stream.inc"
+#undef SK_NS
+#undef SK_FLIGHT
+#undef SK_CTAS
+#define SK_NS sk12x4
+#define SK_FLIGHT 12
+#define SK_CTAS 4
+#include "deliver_stream.inc"
+#undef SK_NS
+#undef SK_FLIGHT
+#undef SK_CTAS
+#define SK_NS sk16x3
+#define SK_FLIGHT 16
+#define SK_CTAS 3
+#include "deliver_stream.inc"
+#undef SK_NS
+#undef SK_FLIGHT
+#undef SK_CTAS
+
 // ---- pack_runs / unpack_rows ---------------------------------------------------------------------
 // Counter addresses of local target t of a tile (t < cap, cap a multiple of 128):
 //   array A: t                       (bank (t >> 2) & 31)
@@ -454,7 +493,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 					rem[best]--;
 					int const j  = order[first[b] + i];
 					int const tt = t[j];
-					out[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
+					out[next[best]] = encode_entry((bank[j] & 0x80) ? cap + rot_fwd(tt) : tt);
 					next[best] += 4;
 				}
 			}
@@ -464,7 +503,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 				unsigned const free_banks = ~used_banks[c];
 				int const b               = free_banks ? __ffs(free_banks) - 1 : 0;
 				used_banks[c] |= 1u << b;
-				out[next[c]] = 2 * cap + 4 * b + c;
+				out[next[c]] = encode_entry(2 * cap + 4 * b + c);
 			}
 	}
 }
@@ -484,7 +523,7 @@ __global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed,
 			present[i] = 0;
 		long long const beg = static_cast<long long>(run_ptr[row * tiles + k]) * 4, end = static_cast<long long>(run_ptr[row * tiles + k + 1]) * 4;
 		for (long long e = beg; e < end; e++) {
-			int const v = packed[e];
+			int const v = decode_entry(packed[e]);
 			if (v >= 2 * cap)
 				continue;
 			int const t = v < cap ? v : rot_inv(v - cap);
@@ -577,7 +616,52 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
 	return static_cast<int>(cudaGetLastError());
 }
 
+#define SPICE_DEFINE_LAUNCH_STREAM(NS)                                                                                        \
+	int launch_stream_##NS(void* stream, tiles_args const& a, int device) {                                                    \
+		static int blocks_per_sm[64] = {};                                                                                    \
+		static int sms[64]           = {};                                                                                    \
+		static int smem_set[64]      = {};                                                                                    \
+		size_t const smem = NS::stream_smem(a.tile_cap);                                                                       \
+		int const threads = (NS::kConsumers + 1) * 32;                                                                         \
+		if (device < 0 || device >= 64)                                                                                       \
+			return static_cast<int>(cudaErrorInvalidDevice);                                                                  \
+		if (smem_set[device] < static_cast<int>(smem)) {                                                                      \
+			cudaError_t e = cudaFuncSetAttribute(NS::deliver_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+			if (e != cudaSuccess)                                                                                             \
+				return static_cast<int>(e);                                                                                   \
+			e = cudaFuncSetAttribute(NS::deliver_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+			if (e != cudaSuccess)                                                                                             \
+				return static_cast<int>(e);                                                                                   \
+			int nb = 0;                                                                                                       \
+			e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, NS::deliver_stream, threads, smem);                    \
+			if (e != cudaSuccess)                                                                                             \
+				return static_cast<int>(e);                                                                                   \
+			cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);                                     \
+			blocks_per_sm[device] = std::max(nb, 1);                                                                          \
+			smem_set[device]      = static_cast<int>(smem);                                                                   \
+		}                                                                                                                     \
+		long long const units = static_cast<long long>(a.total_tiles) * a.nsteps;                                             \
+		if (units <= 0)                                                                                                       \
+			return 0;                                                                                                         \
+		int const grid = static_cast<int>(std::min<long long>(units, static_cast<long long>(sms[device]) * blocks_per_sm[device])); \
+		NS::deliver_stream<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);                                     \
+		return static_cast<int>(cudaGetLastError());                                                                          \
+	}
+SPICE_DEFINE_LAUNCH_STREAM(sk8x4)
+SPICE_DEFINE_LAUNCH_STREAM(sk12x4)
+SPICE_DEFINE_LAUNCH_STREAM(sk16x3)
+
+int launch_stream(void* stream, tiles_args const& a, int device) {
+	switch (a.variant) {
+	case 12: return launch_stream_sk12x4(stream, a, device);
+	case 16: return launch_stream_sk16x3(stream, a, device);
+	default: return launch_stream_sk8x4(stream, a, device);
+	}
+}
+
 int launch_tiles(void* stream, tiles_args const& a, int device) {
+	if (a.all_arranged && !a.force_tiles)
+		return launch_stream(stream, a, device);
 	static int blocks_per_sm[64] = {};
 	static int sms[64]           = {};
 	static int smem_set[64]      = {};
