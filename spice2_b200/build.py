@@ -29,7 +29,7 @@ UNITS = [("runtime.cu", []), ("deliver.cu", ["-Xptxas", "-v"]), ("generator.cu",
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.inc")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.h")) +
+    for p in sorted(list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.h")) +
                     list(CSRC.rglob("*.cpp")) + [ROOT / "include" / "spice_b200.h", Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())

@@ -52,30 +52,15 @@ constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane a
 constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
 constexpr unsigned kFull   = 0xffffffffu;
 
-// A stream entry names one u8 counter by the byte offset of its 32-bit word (bits 31..16) and, in
-// bits 15..0, the PRMT selector that turns the constant 1 into "+1 in that byte": 0x4444 with the
-// byte's nibble cleared.  So the counting code forms address and increment with one instruction each.
-__host__ __device__ __forceinline__ std::int32_t encode_entry(int byte_addr) {
-	return static_cast<std::int32_t>((static_cast<unsigned>(byte_addr & ~3) << 16) | (0x4444u & ~(0xfu << (4 * (byte_addr & 3)))));
-}
-__host__ __device__ __forceinline__ int decode_entry(std::int32_t e) { // -> byte offset of the counter
-	unsigned const free_nibble = ~static_cast<unsigned>(e) & 0x4444u;  // bit 4 k + 2
-	int k = 0;
-	while (k < 3 && !((free_nibble >> (4 * k + 2)) & 1u))
-		k++;
-	return static_cast<int>(static_cast<unsigned>(e) >> 16) + k;
-}
-
-// count the 4 entries of `v` (counters of 4 distinct targets, so the loads may all precede the
-// stores); a lane without a group holds v.x < 0
+// count the 4 entries of `v` (counter addresses of 4 distinct targets, so the loads may all
+// precede the stores); a lane without a group holds v.x < 0
 __device__ __forceinline__ void tally(unsigned char* cnt, int4 v) {
 	if (v.x >= 0) {
-		int const a0 = decode_entry(v.x), a1 = decode_entry(v.y), a2 = decode_entry(v.z), a3 = decode_entry(v.w);
-		unsigned char const c0 = cnt[a0], c1 = cnt[a1], c2 = cnt[a2], c3 = cnt[a3];
-		cnt[a0] = c0 + 1;
-		cnt[a1] = c1 + 1;
-		cnt[a2] = c2 + 1;
-		cnt[a3] = c3 + 1;
+		unsigned char const c0 = cnt[v.x], c1 = cnt[v.y], c2 = cnt[v.z], c3 = cnt[v.w];
+		cnt[v.x] = c0 + 1;
+		cnt[v.y] = c1 + 1;
+		cnt[v.z] = c2 + 1;
+		cnt[v.w] = c3 + 1;
 	}
 }
 
@@ -92,9 +77,20 @@ __device__ __forceinline__ void zero_tile(unsigned char* cnt, int cap, int bytes
 
 __device__ __forceinline__ int4 ldg_stream(void const* p) {
 	int4 v;
-	// "memory": the load keeps its place between the counting code around it — that order IS the software pipeline
-	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
 	return v;
+}
+
+// groups [32, ng) of a long run; out of line: the pipeline's loop is unrolled 32 times and should stay small
+__device__ __noinline__ void tally_rest(unsigned char* cnt, int4 const* g, unsigned ng, int lane) {
+	__syncwarp();
+	for (unsigned off = 32; off < ng; off += 32) {
+		int4 w = make_int4(-1, 0, 0, 0);
+		if (off + lane < ng)
+			w = ldg_stream(g + off);
+		tally(cnt, w);
+	}
+	__syncwarp();
 }
 
 // One run (a tile's share of one spiking source's row) as the pipeline sees it: groups
@@ -121,6 +117,7 @@ struct unit_info {
 	int stride;               // tiles (packed) / tiles + 1 (plain)
 	unsigned total;           // spikes of the step (all ranks)
 	long long ring_slot;
+	unsigned seg_n[spice::detail::kMaxWorld], seg_first[spice::detail::kMaxWorld]; // per rank: spikes, start in the flat order
 };
 
 // One warp's pipeline over its share of a unit: the batches b = first, first + step, ... of the
@@ -181,16 +178,8 @@ struct unit_walker {
 		int4 v           = make_int4(-1, 0, 0, 0);
 		if (static_cast<unsigned>(lane) < r.ng)
 			v = ldg_stream(g);
-		if (r.ng > 32) { // run longer than one warp-wide load (rare: tiles are sized for ~100 entries):
-			__syncwarp(); // count the rest right away, between two other runs' turns
-			for (unsigned off = 32; off < r.ng; off += 32) {
-				int4 w = make_int4(-1, 0, 0, 0);
-				if (off + lane < r.ng)
-					w = ldg_stream(g + off);
-				tally(cnt, w);
-			}
-			__syncwarp();
-		}
+		if (r.ng > 32) // run longer than one warp-wide load (rare: tiles are sized for ~100 entries):
+			tally_rest(cnt, g, r.ng, lane); // count the rest right away, between two other runs' turns
 		return v;
 	}
 
@@ -198,17 +187,13 @@ struct unit_walker {
 	__device__ __forceinline__ void run(unsigned first, unsigned step, unsigned nbatch) {
 		cnt    = smem + kDescBytes;
 		stream = reinterpret_cast<int4 const*>(U.C->packed);
-		// the step's spike list: one segment per rank; lane r keeps segment r's start in the flat order
-		my_n = 0;
-		if (lane < a.world)
-			my_n = U.C->ring_cnt[U.ring_slot * a.world + lane];
-		my_first = my_n;
-		for (int off = 1; off < 32; off <<= 1) {
-			unsigned const o = __shfl_up_sync(kFull, my_first, off);
-			if (lane >= off)
-				my_first += o;
+		// the step's spike list: one segment per rank; lane r keeps segment r's size and its start in
+		// the flat order (read once per unit by the claiming thread: one global round trip less per warp)
+		my_n = 0, my_first = 0;
+		if (lane < a.world) {
+			my_n     = U.seg_n[lane];
+			my_first = U.seg_first[lane];
 		}
-		my_first -= my_n; // exclusive prefix
 
 		zero_tile(cnt, a.tile_cap, (U.width + 127) & ~127, lane);
 		unsigned const mine = first < nbatch ? (nbatch - first + step - 1) / step : 0; // batches of this warp
@@ -293,8 +278,12 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				U.tile_ptr  = C.tile_ptr + k;
 				U.stride    = C.arranged ? C.tiles : C.tiles + 1;
 				unsigned total = 0;
-				for (int r = 0; r < a.world; r++)
-					total += C.ring_cnt[U.ring_slot * a.world + r];
+				for (int r = 0; r < a.world; r++) {
+					unsigned const n = C.ring_cnt[U.ring_slot * a.world + r];
+					U.seg_n[r]       = n;
+					U.seg_first[r]   = total;
+					total += n;
+				}
 				U.total = total;
 				if (k == 0 && total)
 					atomicAdd(a.stats + 1, static_cast<unsigned long long>(total));
@@ -355,29 +344,6 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 		}
 	}
 }
-
-// ---- deliver_stream: producer/consumer variants (deliver_stream.inc) --------------------------------
-#define SK_NS sk8x4
-#define SK_FLIGHT 8
-#define SK_CTAS 4
-#include "deliver_stream.inc"
-#undef SK_NS
-#undef SK_FLIGHT
-#undef SK_CTAS
-#define SK_NS sk12x4
-#define SK_FLIGHT 12
-#define SK_CTAS 4
-#include "deliver_stream.inc"
-#undef SK_NS
-#undef SK_FLIGHT
-#undef SK_CTAS
-#define SK_NS sk16x3
-#define SK_FLIGHT 16
-#define SK_CTAS 3
-#include "deliver_stream.inc"
-#undef SK_NS
-#undef SK_FLIGHT
-#undef SK_CTAS
 
 // ---- pack_runs / unpack_rows ---------------------------------------------------------------------
 // Counter addresses of local target t of a tile (t < cap, cap a multiple of 128):
@@ -493,7 +459,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 					rem[best]--;
 					int const j  = order[first[b] + i];
 					int const tt = t[j];
-					out[next[best]] = encode_entry((bank[j] & 0x80) ? cap + rot_fwd(tt) : tt);
+					out[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
 					next[best] += 4;
 				}
 			}
@@ -503,7 +469,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 				unsigned const free_banks = ~used_banks[c];
 				int const b               = free_banks ? __ffs(free_banks) - 1 : 0;
 				used_banks[c] |= 1u << b;
-				out[next[c]] = encode_entry(2 * cap + 4 * b + c);
+				out[next[c]] = 2 * cap + 4 * b + c;
 			}
 	}
 }
@@ -523,7 +489,7 @@ __global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed,
 			present[i] = 0;
 		long long const beg = static_cast<long long>(run_ptr[row * tiles + k]) * 4, end = static_cast<long long>(run_ptr[row * tiles + k + 1]) * 4;
 		for (long long e = beg; e < end; e++) {
-			int const v = decode_entry(packed[e]);
+			int const v = packed[e];
 			if (v >= 2 * cap)
 				continue;
 			int const t = v < cap ? v : rot_inv(v - cap);
@@ -616,52 +582,7 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
 	return static_cast<int>(cudaGetLastError());
 }
 
-#define SPICE_DEFINE_LAUNCH_STREAM(NS)                                                                                        \
-	int launch_stream_##NS(void* stream, tiles_args const& a, int device) {                                                    \
-		static int blocks_per_sm[64] = {};                                                                                    \
-		static int sms[64]           = {};                                                                                    \
-		static int smem_set[64]      = {};                                                                                    \
-		size_t const smem = NS::stream_smem(a.tile_cap);                                                                       \
-		int const threads = (NS::kConsumers + 1) * 32;                                                                         \
-		if (device < 0 || device >= 64)                                                                                       \
-			return static_cast<int>(cudaErrorInvalidDevice);                                                                  \
-		if (smem_set[device] < static_cast<int>(smem)) {                                                                      \
-			cudaError_t e = cudaFuncSetAttribute(NS::deliver_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-			if (e != cudaSuccess)                                                                                             \
-				return static_cast<int>(e);                                                                                   \
-			e = cudaFuncSetAttribute(NS::deliver_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-			if (e != cudaSuccess)                                                                                             \
-				return static_cast<int>(e);                                                                                   \
-			int nb = 0;                                                                                                       \
-			e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, NS::deliver_stream, threads, smem);                    \
-			if (e != cudaSuccess)                                                                                             \
-				return static_cast<int>(e);                                                                                   \
-			cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);                                     \
-			blocks_per_sm[device] = std::max(nb, 1);                                                                          \
-			smem_set[device]      = static_cast<int>(smem);                                                                   \
-		}                                                                                                                     \
-		long long const units = static_cast<long long>(a.total_tiles) * a.nsteps;                                             \
-		if (units <= 0)                                                                                                       \
-			return 0;                                                                                                         \
-		int const grid = static_cast<int>(std::min<long long>(units, static_cast<long long>(sms[device]) * blocks_per_sm[device])); \
-		NS::deliver_stream<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);                                     \
-		return static_cast<int>(cudaGetLastError());                                                                          \
-	}
-SPICE_DEFINE_LAUNCH_STREAM(sk8x4)
-SPICE_DEFINE_LAUNCH_STREAM(sk12x4)
-SPICE_DEFINE_LAUNCH_STREAM(sk16x3)
-
-int launch_stream(void* stream, tiles_args const& a, int device) {
-	switch (a.variant) {
-	case 12: return launch_stream_sk12x4(stream, a, device);
-	case 16: return launch_stream_sk16x3(stream, a, device);
-	default: return launch_stream_sk8x4(stream, a, device);
-	}
-}
-
 int launch_tiles(void* stream, tiles_args const& a, int device) {
-	if (a.all_arranged && !a.force_tiles)
-		return launch_stream(stream, a, device);
 	static int blocks_per_sm[64] = {};
 	static int sms[64]           = {};
 	static int smem_set[64]      = {};

@@ -44,10 +44,6 @@ struct tiles_args {
 	unsigned long long* stats; // [0] events, [1] spikes
 	int* error;                // bit 16: internal error in the delivery kernel
 	int tile_cap;              // targets per warp-private counter array (max conns[].tile rounded up to 128)
-	int all_arranged;          // every connection has a packed stream: the producer/consumer kernel applies
-	int variant;               // SPICE_STREAM=8|12|16: runs in flight per consumer warp
-	int prefetch;              // SPICE_PREFETCH=1: the producer asks L2 to prefetch every run it describes
-	int force_tiles;           // SPICE_DELIVER=tiles: keep the statically split kernel (A/B measurements)
 };
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile

@@ -442,8 +442,6 @@ struct spice_ctx {
 	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
 	unsigned* d_work                  = nullptr;
 	int total_tiles = 0, tile_cap = 0, n_desc = 0;
-	bool all_arranged = true, force_tiles = false, prefetch = false;
-	int stream_variant = 8;
 
 	// device tables
 	std::uint32_t** d_ring_cnt        = nullptr; // [npops]
@@ -568,11 +566,6 @@ int finalize(spice_ctx* ctx) {
 	{
 		char const* dm = std::getenv("SPICE_DELIVER");
 		ctx->tiled     = !(dm && std::string(dm) == "atomic");
-		ctx->force_tiles = dm && std::string(dm) == "tiles";
-		if (char const* sv = std::getenv("SPICE_STREAM"))
-			ctx->stream_variant = std::atoi(sv);
-		if (char const* pf = std::getenv("SPICE_PREFETCH"))
-			ctx->prefetch = std::atoi(pf) != 0;
 	}
 	long long target_len = 100; // column indices one warp-wide pass of the tiled kernel should find per row and tile
 	if (char const* tl = std::getenv("SPICE_TILE_LEN"))
@@ -678,7 +671,6 @@ int finalize(spice_ctx* ctx) {
 			d.tile        = c.tile;
 			d.tile_prefix = ctx->total_tiles;
 			d.arranged    = c.arranged ? 1 : 0;
-			ctx->all_arranged = ctx->all_arranged && c.arranged;
 			ctx->total_tiles += c.tiles;
 			descs.push_back(d);
 		}
@@ -960,10 +952,6 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ta.stats       = ctx->d_stats;
 			ta.error       = ctx->d_error;
 			ta.tile_cap    = ctx->tile_cap;
-			ta.all_arranged = ctx->all_arranged ? 1 : 0;
-			ta.force_tiles  = ctx->force_tiles ? 1 : 0;
-			ta.prefetch     = ctx->prefetch ? 1 : 0;
-			ta.variant      = ctx->stream_variant;
 			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device);
 			if (e != 0)
 				return fail(ctx, SPICE_ERR_CUDA, std::string("delivery launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
