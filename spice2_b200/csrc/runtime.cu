@@ -237,7 +237,7 @@ struct sink_args {
 	long long* h_cnt;                    // [steps_cap][npops] (mapped)
 	unsigned long long* h_off;           // [steps_cap][npops] (mapped) monotonic position of the list
 	long long steps_cap;
-	unsigned long long const volatile* h_consumed; // [2] steps, ids the host has taken (mapped, host-written)
+	unsigned long long consumed_steps, consumed_ids; // what the host had taken when the window was enqueued (a lower bound)
 	int* h_error;                        // mapped
 };
 
@@ -271,9 +271,9 @@ __global__ void __launch_bounds__(kSinkThreads) sink_pack(sink_args a) {
 		if (blockIdx.x == gridDim.x - 1)
 			a.cursor[a.parity ^ 1] = base + total_s;
 		int ok = 1;
-		if (static_cast<unsigned long long>(si) - a.h_consumed[0] >= static_cast<unsigned long long>(a.steps_cap))
+		if (static_cast<unsigned long long>(si) - a.consumed_steps >= static_cast<unsigned long long>(a.steps_cap))
 			*a.h_error = 4, ok = 0;
-		else if (base + total_s - a.h_consumed[1] > static_cast<unsigned long long>(a.cap))
+		else if (base + total_s - a.consumed_ids > static_cast<unsigned long long>(a.cap))
 			*a.h_error = 8, ok = 0;
 		if (ok) {
 			a.h_cnt[(si % a.steps_cap) * a.npops + p] = total_s;
@@ -1010,7 +1010,8 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		sa.h_cnt       = ctx->h_sink_cnt;
 		sa.h_off       = ctx->h_sink_off;
 		sa.steps_cap   = ctx->sink_steps_cap;
-		sa.h_consumed  = ctx->h_sink_consumed;
+		sa.consumed_steps = static_cast<unsigned long long>(ctx->sink_steps_read);
+		sa.consumed_ids   = ctx->sink_ids_read;
 		sa.h_error     = ctx->h_sink_error;
 		sink_pack<<<nsteps * np, kSinkThreads, ctx->sink_smem, ctx->stream>>>(sa);
 		ctx->launches++;
