@@ -178,6 +178,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "ERROR")  # keeps NCCL's version banner off stdout: rank 0 prints ONE line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
