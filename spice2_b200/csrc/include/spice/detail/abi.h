@@ -166,5 +166,9 @@ struct spice_synapse_ops {
 	                  std::int64_t n_src, std::uint64_t seed_lo, std::uint64_t seed_hi);
 	int (*get_apply_events)(spice::detail::apply_events_fn* out);
 	int (*launch_stateful)(spice::detail::stateful_args const*);
+	// stateless synapses: the target model's update kernel with this synapse's deliver() inlined; the
+	// same address for every source type, so the runtime can tell that all incoming connections of a
+	// population agree (null: not available)
+	int (*launch_update_fused)(spice::detail::update_args const*);
 };
 }

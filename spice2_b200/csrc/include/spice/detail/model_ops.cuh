@@ -89,24 +89,28 @@ struct counting_rng {
 };
 
 // ---- apply: k deliveries of a stateless synapse to one neuron ------------------------------------
+// k sequential deliveries on a register copy of the neuron: the remainder first (predicated), then
+// groups of 8 back to back — a dependent chain of the functor's own float operations, nothing else
+template <class Syn, class N>
+__device__ __forceinline__ void deliver_k(Syn const& syn, N& n, unsigned k) {
+#pragma unroll
+	for (unsigned u = 1; u < 8; u++)
+		if (u <= (k & 7u))
+			syn.deliver(n);
+	for (unsigned j = k >> 3; j; j--) {
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			syn.deliver(n);
+	}
+}
+
 template <class Syn, class DstNeur>
 __device__ void apply_impl(void const* functor, void* neuron, unsigned k) {
 	if constexpr (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
-		// work on register copies: the k deliveries are a dependent chain of the functor's own
-		// float operations, nothing else
 		using N       = typename DstNeur::neuron;
 		Syn const syn = *static_cast<Syn const*>(functor);
 		N n           = *static_cast<N*>(neuron);
-		// k sequential deliveries: the remainder first (predicated), then groups of 8 back to back
-#pragma unroll
-		for (unsigned u = 1; u < 8; u++)
-			if (u <= (k & 7u))
-				syn.deliver(n);
-		for (unsigned j = k >> 3; j; j--) {
-#pragma unroll
-			for (int u = 0; u < 8; u++)
-				syn.deliver(n);
-		}
+		deliver_k(syn, n, k);
 		*static_cast<N*>(neuron) = n;
 	}
 }
@@ -260,7 +264,17 @@ __global__ void __launch_bounds__(256) stateful_fill_kernel(stateful_args a) {
 // (counters never need zeroing) — the common case, with nothing but the loads, the calls and the
 // model's own arithmetic left in the loop.  Generic = true handles everything else (stateful
 // synapses' event lists, the atomic delivery mode, up to kMaxIncoming connections).
-template <class Neur, int NIN, bool Generic>
+template <class FSyn, int C>
+struct fused_synapses {
+	FSyn v[C];
+};
+template <int C>
+struct fused_synapses<void, C> {};
+
+//
+// FSyn != void: every incoming connection carries the same stateless synapse type, whose deliver()
+// is inlined (the type-erased apply is an indirect call that moves the neuron through local memory).
+template <class Neur, int NIN, bool Generic, class FSyn = void>
 __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) {
 	using N                  = typename Neur::neuron;
 	std::int64_t const i     = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -289,6 +303,14 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 		}
 	}
 	int cslot = a.cslot0, rslot = a.rslot0;
+	// the connections' synapse objects (their parameters), read once
+	fused_synapses<FSyn, C> fsyn;
+	if constexpr (!std::is_void_v<FSyn>) {
+#pragma unroll
+		for (int c = 0; c < C; c++)
+			if (c < NIN)
+				fsyn.v[c] = *static_cast<FSyn const*>(a.in[c].functor);
+	}
 
 	for (int s = 0; s < a.nsteps; s++) {
 		int const cnext = cslot + 1 == a.cring ? 0 : cslot + 1;
@@ -307,7 +329,10 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 				if constexpr (Generic)
 					if (in.zero_after_read)
 						in.counts[cslot * in.cstride + ii] = 0;
-				in.apply(in.functor, &n, kk[c]);
+				if constexpr (std::is_void_v<FSyn>)
+					in.apply(in.functor, &n, kk[c]);
+				else
+					deliver_k(fsyn.v[c], n, kk[c]);
 			}
 			if constexpr (Generic) {
 				if (c < a.n_in && a.in[c].evt_cnt && active) { // stateful synapses: this step's event list (window = 1 step)
@@ -533,6 +558,27 @@ spice_neuron_ops const* neuron_ops(char const* name = "user") {
 	return &ops;
 }
 
+// update kernel of DstNeur with Syn::deliver inlined, for populations whose incoming connections all
+// carry this synapse type (whatever their sources): one function, hence one address, per (Syn, DstNeur)
+template <class Syn, StatefulNeuron DstNeur>
+int launch_update_fused(update_args const* a) {
+	if constexpr (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur> && rng_draws_v<DstNeur> == 0) {
+		auto stream    = static_cast<cudaStream_t>(a->stream);
+		int const grid = grid_for(a->n_local, 128);
+		if (a->n_local > 0)
+			switch (a->n_in) {
+			case 1: update_stateful_kernel<DstNeur, 1, false, Syn><<<grid, 128, 0, stream>>>(*a); break;
+			case 2: update_stateful_kernel<DstNeur, 2, false, Syn><<<grid, 128, 0, stream>>>(*a); break;
+			case 3: update_stateful_kernel<DstNeur, 3, false, Syn><<<grid, 128, 0, stream>>>(*a); break;
+			default: update_stateful_kernel<DstNeur, 4, false, Syn><<<grid, 128, 0, stream>>>(*a); break;
+			}
+		return static_cast<int>(cudaGetLastError());
+	} else {
+		(void)a;
+		return -1;
+	}
+}
+
 template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
 requires Synapse<Syn, SrcNeur, DstNeur>
 spice_synapse_ops const* synapse_ops(char const* name = "user") {
@@ -598,7 +644,8 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 	                                   PerSynapseInit<Syn> ? 1u : 0u,
 	                                   &B::init_host,
 	                                   &B::get_apply_events,
-	                                   &B::launch_stateful};
+	                                   &B::launch_stateful,
+	                                   (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) ? &launch_update_fused<Syn, DstNeur> : nullptr};
 	return &ops;
 }
 }

@@ -854,7 +854,21 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		ua.rng.nib   = ctx->d_nib;
 		ua.jump_poly = p.jump_poly;
 		if (ua.n_local > 0) {
-			int const e = p.ops->launch_update(&ua);
+			// all incoming connections stateless, fed by the tiled delivery and of one synapse type: the
+			// update kernel with that type's deliver() inlined
+			int (*fused)(update_args const*) = nullptr;
+			if (ua.n_in >= 1 && ua.n_in <= 4 && ctx->tiled && !std::getenv("SPICE_UPDATE_GENERIC")) {
+				fused = ctx->conns[p.incoming[0]].ops->launch_update_fused;
+				for (int ci : p.incoming) {
+					connection const& c = ctx->conns[ci];
+					if (c.stateful || c.ops->launch_update_fused != fused)
+						fused = nullptr;
+				}
+				for (int c = 0; c < ua.n_in; c++)
+					if (ua.in[c].evt_cnt || ua.in[c].zero_after_read)
+						fused = nullptr;
+			}
+			int const e = fused ? fused(&ua) : p.ops->launch_update(&ua);
 			if (e != 0)
 				return fail(ctx, SPICE_ERR_CUDA, std::string("update launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
 			ctx->launches++;
