@@ -58,6 +58,9 @@ namespace ref_brunel_plus {
 namespace ref_vogels {
 #include "vogels.cpp"
 }
+namespace ref_sssp {
+#include "sssp.cpp"
+}
 
 namespace {
 using clk = std::chrono::steady_clock;
@@ -314,6 +317,27 @@ int ref_brunel_advance(void* handle, std::int64_t steps, double* sim_seconds, st
 }
 
 void ref_brunel_close(void* handle) { delete static_cast<ref_brunel_net*>(handle); }
+
+// ---- SSSP (samples/sssp.cpp:100-116): the reference's own vertex / edge models on its own graph ----
+// distances[7] after vertices - 1 steps (DeliverFromTo synapses, per-synapse and per-population init)
+int ref_sssp_distances(std::int64_t* distances) {
+	using namespace ref_sssp;
+	spice::snn sssp(1, 1, {1337});
+	auto vertices = sssp.add_population<vertex>(7, {0});
+	spice::adj_list adj;
+	for (Int src : range(7))
+		for (Int dst : range(7))
+			if (adj_matrix[src][dst])
+				adj.connect(src, dst);
+	sssp.connect<edge>(vertices, vertices, adj, 1);
+	for (Int i : range(vertices->size() - 1)) {
+		sssp.step();
+		(void)i;
+	}
+	for (int v = 0; v < 7; v++)
+		distances[v] = vertices->get_neurons()[v].distance;
+	return 0;
+}
 
 // ---- Brunel+ (samples/brunel+.cpp:102-117): E->E plastic -------------------------------------
 int ref_brunel_plus_run(std::int64_t N, double p, float w_exc, float w_inh, float dt, float delay,

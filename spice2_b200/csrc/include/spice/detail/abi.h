@@ -28,8 +28,19 @@ using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
 // one neuron: `list` holds the edge indices (arrival order); it is sorted ascending — the
 // reference's (source, row) order (synapse_population.h:88,99) — and Syn::deliver(synapse, neuron)
 // is called for each, reading the synapse state word-SoA (word w of edge e at syn[w*stride + e]).
+//
+// Synapses whose deliver() also takes the SOURCE neuron (concepts.h DeliverFromTo;
+// synapse_population.h:125-131) find it through `from`: the source of edge e is the row that holds e
+// (binary search in offsets), its state is read from a snapshot of the source population taken at the
+// end of the step in which the spike was emitted (from.state == null for all other synapses).
+struct from_ctx {
+	std::uint32_t const* state; // word-SoA snapshot of the source population
+	std::int64_t stride;
+	std::int64_t const* offsets; // CSR row offsets of the connection
+	std::int64_t n_src;
+};
 using apply_events_fn = void (*)(void const* functor, void* neuron, std::uint32_t const* syn, std::int64_t syn_stride,
-                                 std::int32_t* list, unsigned n);
+                                 std::int32_t* list, unsigned n, from_ctx const* from);
 
 // One incoming connection as the target population's update kernel sees it.
 struct incoming {
@@ -47,6 +58,7 @@ struct incoming {
 	std::uint32_t const* syn;      // synapse state, word-SoA
 	std::int64_t syn_stride;
 	apply_events_fn apply_events;
+	from_ctx from;
 };
 
 // One step of a stateful connection (launched by the runtime through spice_synapse_ops).
@@ -156,7 +168,7 @@ struct spice_synapse_ops {
 	std::uint32_t functor_bytes; // sizeof(Syn)
 	std::uint32_t dst_neuron_bytes;
 	std::uint32_t plastic;         // has update()/skip()
-	std::uint32_t deliver_from_to; // deliver takes the source neuron (unsupported on this path yet)
+	std::uint32_t deliver_from_to; // deliver takes the source neuron (stateful synapses, single rank: see from_ctx)
 	// device function pointer of apply<Syn, DstNeur>, fetched from the module that holds the kernels
 	int (*get_apply)(spice::detail::apply_fn* out);
 	// stateful synapses: default-construct `n_edges` synapses (AoS) and run the model's init hook, if any,

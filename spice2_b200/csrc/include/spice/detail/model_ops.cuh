@@ -40,8 +40,7 @@ namespace spice::detail {
 template <class T>
 struct words_of {
 	static_assert(std::is_trivially_copyable_v<T>, "neuron / synapse state must be trivially copyable");
-	static_assert(sizeof(T) % 4 == 0, "neuron / synapse state must be a multiple of 4 bytes");
-	static constexpr int value = sizeof(T) / 4;
+	static constexpr int value = (sizeof(T) + 3) / 4; // the last word of a state whose size is no multiple of 4 is padded
 };
 
 template <class T>
@@ -59,7 +58,7 @@ __device__ __forceinline__ T load_soa(std::uint32_t const* base, std::int64_t st
 template <class T>
 __device__ __forceinline__ void store_soa(std::uint32_t* base, std::int64_t stride, std::int64_t i, T const& v) {
 	constexpr int W = words_of<T>::value;
-	std::uint32_t w[W];
+	std::uint32_t w[W] = {};
 	memcpy(w, &v, sizeof(T));
 #pragma unroll
 	for (int k = 0; k < W; k++)
@@ -119,10 +118,10 @@ __device__ apply_fn apply_ptr = apply_impl<Syn, DstNeur>;
 
 // ---- stateful / plastic synapses -------------------------------------------------------------------
 // apply_events: the events one stateful connection addressed to one neuron in the step that just ran
-template <class Syn, class DstNeur>
+template <class Syn, class SrcNeur, class DstNeur>
 __device__ void apply_events_impl(void const* functor, void* neuron, std::uint32_t const* syn, std::int64_t syn_stride,
-                                  std::int32_t* list, unsigned n) {
-	if constexpr (StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+                                  std::int32_t* list, unsigned n, from_ctx const* from) {
+	if constexpr (StatefulSynapse<Syn>) {
 		using N = typename DstNeur::neuron;
 		using S = typename Syn::synapse;
 		for (unsigned i = 1; i < n; i++) { // insertion sort: ascending edge index = (source, row) order
@@ -136,13 +135,28 @@ __device__ void apply_events_impl(void const* functor, void* neuron, std::uint32
 		N nn        = *static_cast<N*>(neuron);
 		for (unsigned i = 0; i < n; i++) {
 			S const sy = load_soa<S>(syn, syn_stride, list[i]);
-			f.deliver(sy, nn);
+			if constexpr (DeliverTo<Syn, DstNeur>)
+				f.deliver(sy, nn);
+			else if constexpr (detail::deliver_from_to_v<Syn, SrcNeur, DstNeur>) {
+				// the row that holds edge list[i]: last src with offsets[src] <= e
+				std::int64_t lo = 0, hi = from->n_src;
+				while (hi - lo > 1) {
+					std::int64_t const mid = (lo + hi) >> 1;
+					if (from->offsets[mid] <= list[i])
+						lo = mid;
+					else
+						hi = mid;
+				}
+				auto const sn = load_soa<typename SrcNeur::neuron>(from->state, from->stride, lo);
+				f.deliver(sy, sn, nn);
+			}
 		}
 		*static_cast<N*>(neuron) = nn;
 	}
+	(void)functor, (void)neuron, (void)syn, (void)syn_stride, (void)list, (void)n, (void)from;
 }
-template <class Syn, class DstNeur>
-__device__ apply_events_fn apply_events_ptr = apply_events_impl<Syn, DstNeur>;
+template <class Syn, class SrcNeur, class DstNeur>
+__device__ apply_events_fn apply_events_ptr = apply_events_impl<Syn, SrcNeur, DstNeur>;
 
 // Lazy plasticity: bring one synapse from step `age` up to and including step `time`
 // (synapse_population.h:95-116 with Outdated == true).  hist bit j = the target fired at step time - j.
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 					unsigned const ne  = in.evt_cnt[ii];
 					if (ne) {
 						in.evt_cnt[ii] = 0;
-						in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[ii], ne);
+						in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[ii], ne, &in.from);
 					}
 				}
 			}
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(256) export_kernel(export_args a) {
 		if (in.evt_cnt) {
 			unsigned const ne = in.evt_cnt[i];
 			if (ne)
-				in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[i], ne);
+				in.apply_events(in.functor, &n, in.syn, in.syn_stride, in.evt_list + in.evt_off[i], ne, &in.from);
 			continue;
 		}
 		unsigned const k = in.counts[(a.t_next % in.ring) * in.cstride + i];
@@ -588,7 +602,7 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_ptr<Syn, DstNeur>, sizeof(apply_fn)));
 		}
 		static int get_apply_events(apply_events_fn* out) {
-			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_events_ptr<Syn, DstNeur>, sizeof(apply_events_fn)));
+			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_events_ptr<Syn, SrcNeur, DstNeur>, sizeof(apply_events_fn)));
 		}
 		static void init_host(void const* functor, void* out, std::int64_t const* offsets, std::int32_t const* neighbors,
 		                      std::int64_t n_src, std::uint64_t seed_lo, std::uint64_t seed_hi) {
@@ -608,7 +622,7 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 			(void)functor, (void)out, (void)offsets, (void)neighbors, (void)n_src, (void)seed_lo, (void)seed_hi;
 		}
 		static int launch_stateful(stateful_args const* a) {
-			if constexpr (StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) {
+			if constexpr (StatefulSynapse<Syn>) {
 				auto stream = static_cast<cudaStream_t>(a->stream);
 				switch (a->phase) {
 				case 0: stateful_visit_kernel<Syn, true><<<148 * 4, 256, 0, stream>>>(*a); break;

@@ -28,6 +28,7 @@
 #include "spice/concepts.h"
 #include "spice/detail/model_ops.cuh"
 #include "spice/topology.h"
+#include "spice/util/range.h"
 #include "spice/util/numeric.h"
 #include "spice/util/random.h"
 #include "spice_b200.h"

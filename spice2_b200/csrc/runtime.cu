@@ -394,6 +394,8 @@ struct connection {
 	unsigned* run_ptr         = nullptr; // arranged: [src * tiles + 1]
 	// stateful / plastic synapses (window = 1 step; spice/detail/model_ops.cuh)
 	bool stateful = false, plastic = false;
+	bool from_to              = false;   // deliver() also reads the source neuron (concepts.h DeliverFromTo)
+	std::uint32_t* src_snapshot = nullptr; // from_to: the source population's state at the end of the last step
 	std::uint32_t* syn        = nullptr; // word-SoA synapse state, parallel to neighbors
 	long long syn_stride      = 0;
 	std::uint64_t* ages       = nullptr; // [src] (synapse_population.h:89-94)
@@ -589,6 +591,11 @@ int finalize(spice_ctx* ctx) {
 			CHECK_CUDA(ctx, cudaMalloc(&c.evt_list, sizeof(std::int32_t) * static_cast<size_t>(c.evt_cap)));
 			CHECK_CUDA(ctx, cudaMemset(c.evt_cnt, 0, sizeof(std::uint32_t) * static_cast<size_t>(n)));
 			CHECK_CUDA(ctx, cudaMemset(c.evt_cursor, 0, sizeof(unsigned long long)));
+			if (c.from_to) {
+				size_t const bytes = sizeof(std::uint32_t) * ((src.ops->neuron_bytes + 3) / 4) * static_cast<size_t>(src.stride);
+				CHECK_CUDA(ctx, cudaMalloc(&c.src_snapshot, std::max<size_t>(bytes, 16)));
+				CHECK_CUDA(ctx, cudaMemcpy(c.src_snapshot, src.state, bytes, cudaMemcpyDeviceToDevice));
+			}
 			if (c.plastic) {
 				CHECK_CUDA(ctx, cudaMalloc(&c.ages, sizeof(std::uint64_t) * static_cast<size_t>(std::max<long long>(src.size, 1))));
 				CHECK_CUDA(ctx, cudaMemset(c.ages, 0, sizeof(std::uint64_t) * static_cast<size_t>(std::max<long long>(src.size, 1))));
@@ -762,7 +769,9 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	for (int k = 0; k < *n_in; k++) {
 		connection const& c = ctx->conns[p.incoming[k]];
 		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1,
-		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events};
+		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events,
+		                               from_ctx{c.src_snapshot, ctx->pops[c.src].stride, reinterpret_cast<std::int64_t const*>(c.offsets),
+		                                        ctx->pops[c.src].size}};
 	}
 }
 
@@ -951,6 +960,15 @@ int run_window(spice_ctx* ctx, int nsteps) {
 						break;
 				}
 			}
+		// deliver() of a DeliverFromTo synapse sees its source as it is now, at the end of the step
+		// (synapse_population.h:125-131 runs after every population's update, snn.cpp:21-25); the events
+		// counted above are applied at the start of the next step, so keep that state
+		for (auto& c : ctx->conns)
+			if (c.from_to) {
+				population const& src = ctx->pops[c.src];
+				size_t const bytes    = sizeof(std::uint32_t) * ((src.ops->neuron_bytes + 3) / 4) * static_cast<size_t>(src.stride);
+				CHECK_CUDA(ctx, cudaMemcpyAsync(c.src_snapshot, src.state, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+			}
 	}
 	if (ctx->tiled) {
 		if (ctx->n_desc > 0) {
@@ -1079,10 +1097,12 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	long long const d = static_cast<long long>(std::round(delay / ctx->dt)); // snn.h:33
 	PRE(ctx, d >= 1 && "The delay must be at least 1dt.");                 // snn.h:35
 	PRE(ctx, d <= ctx->max_delay && "The delay of a synapse population may not exceed the maximum delay of the network."); // snn.h:36-38
-	if (ops->deliver_from_to)
-		return fail(ctx, SPICE_ERR_UNSUPPORTED, "synapses whose deliver() reads the source neuron are not on the GPU path yet");
+	if (ops->deliver_from_to && (ops->synapse_bytes == 0 || ctx->world > 1))
+		return fail(ctx, SPICE_ERR_UNSUPPORTED,
+		            "synapses whose deliver() reads the source neuron: only stateful synapses on a single rank are on the GPU path yet");
 	PRE(ctx, ops->synapse_bytes % 4 == 0);
 	c->stateful = ops->synapse_bytes != 0;
+	c->from_to  = ops->deliver_from_to != 0;
 	c->plastic  = ops->plastic != 0;
 	c->ops   = ops;
 	c->src   = src_pop;
@@ -1227,6 +1247,7 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 		cudaFree(c.neighbors);
 		cudaFree(c.counts);
 		cudaFree(c.tile_ptr);
+		cudaFree(c.src_snapshot);
 		cudaFree(c.packed);
 		cudaFree(c.run_ptr);
 		cudaFree(c.syn);
@@ -1305,11 +1326,12 @@ int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t si
 		UInt128 const sd = (ctx->seed++).seed();
 		std::vector<unsigned char> aos(static_cast<size_t>(std::max<long long>(size, 1)) * ops->neuron_bytes);
 		ops->init_host(f, aos.data(), size, sd.lo, sd.hi);
-		int const words = ops->neuron_bytes / 4;
+		int const words = (ops->neuron_bytes + 3) / 4; // word-SoA; a size that is no multiple of 4 pads its last word
 		std::vector<std::uint32_t> soa(static_cast<size_t>(words) * static_cast<size_t>(p.stride), 0);
 		for (long long i = p.lo; i < p.hi; i++)
 			for (int w = 0; w < words; w++)
-				std::memcpy(&soa[static_cast<size_t>(w) * p.stride + (i - p.lo)], aos.data() + i * ops->neuron_bytes + 4 * w, 4);
+				std::memcpy(&soa[static_cast<size_t>(w) * p.stride + (i - p.lo)], aos.data() + i * ops->neuron_bytes + 4 * w,
+				            std::min<size_t>(4, ops->neuron_bytes - 4 * w));
 		CHECK_CUDA(ctx, cudaMalloc(&p.state, sizeof(std::uint32_t) * soa.size()));
 		CHECK_CUDA(ctx, cudaMemcpy(p.state, soa.data(), sizeof(std::uint32_t) * soa.size(), cudaMemcpyHostToDevice));
 	}

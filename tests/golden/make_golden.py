@@ -73,9 +73,14 @@ for k, v in S.items():
     print(k, v["totals"], flush=True)
 G["samples"] = S
 # md5 of the reference sample programs' stdout (oracle/_ref/{brunel,brunel+,vogels})
+import ctypes as C
 import hashlib, subprocess
 G["sample_stdout_md5"] = {n: hashlib.md5(subprocess.run([str(HERE.parent.parent / "oracle" / "_ref" / n)], capture_output=True,
-                                                         check=True).stdout).hexdigest() for n in ("brunel", "brunel+", "vogels")}
+                                                         check=True).stdout).hexdigest() for n in ("brunel", "brunel+", "vogels", "ping_pong")}
+# samples/sssp.cpp run by the compiled reference (DeliverFromTo synapses): distances of the 7 vertices
+_d = np.zeros(7, np.int64)
+C.CDLL(str(HERE.parent.parent / "oracle" / "_ref" / "libspice_ref_strict.so")).ref_sssp_distances(_d.ctypes.data_as(C.c_void_p))
+G["sssp_distances"] = [int(x) for x in _d]
 (HERE / "golden.json").write_text(json.dumps(G, indent=1))
 
 # ---- libm pins (glibc 2.39 log / expf / pow at the reference's call sites) ---------------------

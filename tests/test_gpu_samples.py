@@ -10,10 +10,20 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("name", ["brunel", "brunel+", "vogels"])
+@pytest.mark.parametrize("name", ["brunel", "brunel+", "vogels", "ping_pong"])
 def test_sample_stdout_md5(golden, name):
     exe = ROOT / "samples" / "build" / name
     if not exe.exists():
         subprocess.run(["make", "-s", "-C", str(ROOT / "samples")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, check=True, timeout=600).stdout
     assert hashlib.md5(out).hexdigest() == golden["sample_stdout_md5"][name]
+
+
+def test_sssp_distances(golden):
+    """samples/sssp over the facade: DeliverFromTo synapses (deliver() reads the source neuron), per-synapse and
+    per-population init hooks; the distances the compiled reference computes, and the sample's own asserts."""
+    exe = ROOT / "samples" / "build" / "sssp"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "samples")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, check=True, timeout=600).stdout.split()
+    assert [int(x) for x in out] == golden["sssp_distances"]
