@@ -86,6 +86,17 @@ SPICE_API int spice_ctx_set_stream(spice_ctx* ctx, void* cuda_stream);
  * `functor` points at a Neur object (ops->functor_bytes bytes), copied into the population. */
 SPICE_API int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t size, void const* functor,
                          int* pop_out);
+/* snn::add_population for a neuron with a per-population update()          (concepts.h:46-57,
+ * neuron_population.h:86-101; samples/external_input.cpp): the population's spikes come from the
+ * host.  When a step is enqueued the runtime calls update(user, dt, seed_lo, seed_hi, rng_offset,
+ * ids_out, capacity, &draws): it writes the population-relative ids (0 <= id < size) of the neurons
+ * that fire in this step and returns how many (<= capacity = size; < 0: failure).  (seed, rng_offset)
+ * address the step's random stream — the engine of snn.cpp:12 advanced by the draws of the
+ * populations added before this one; a functor that DRAWS from it (draws != 0) is not supported
+ * yet, nor is more than one rank. */
+typedef int64_t (*spice_host_update_fn)(void* user, float dt, uint64_t seed_lo, uint64_t seed_hi, uint64_t rng_offset,
+                                        int32_t* ids_out, int64_t capacity, int64_t* draws_out);
+SPICE_API int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn update, void* user, int* pop_out);
 /* NeuronPopulation::size()                                           (neuron_population.h:114) */
 SPICE_API int64_t spice_population_size(spice_ctx const* ctx, int pop);
 /* the contiguous range of the population this rank owns */

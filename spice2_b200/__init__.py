@@ -52,6 +52,7 @@ def lib() -> C.CDLL:
             "spice_last_error": (C.c_char_p, [vp]),
             "spice_ctx_set_stream": (i32, [vp, vp]),
             "spice_add_population": (i32, [vp, vp, i64, vp, C.POINTER(i32)]),
+            "spice_add_host_population": (i32, [vp, i64, vp, vp, C.POINTER(i32)]),
             "spice_population_size": (i64, [vp, i32]),
             "spice_population_range": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
             "spice_connect_fixed_probability": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
@@ -150,12 +151,16 @@ def seed_seq(words, increments=0):
     return int(out[0]), int(out[1])
 
 
+HOST_UPDATE_FN = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_float, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64,
+                             C.POINTER(C.c_int64))
+
+
 class Population:
     """Handle returned by snn.add_population (reference: detail::neuron_population<Neur>*)."""
 
     def __init__(self, net: "snn", index: int, model: str, size: int):
         self.net, self.index, self.model, self._size = net, index, model, size
-        self.dtype = NEURON_MODELS[model][1]
+        self.dtype = NEURON_MODELS[model][1] if model in NEURON_MODELS else None
 
     def size(self) -> int:
         return self._size
@@ -201,6 +206,7 @@ class snn:
         self._h = h
         self.populations: list[Population] = []
         self.connections = []
+        self._keepalive = []  # ctypes callbacks of host-fed populations
         self.rank, self.world = rank, world
 
     def close(self):
@@ -229,6 +235,29 @@ class snn:
         idx = C.c_int()
         self._check(lib().spice_add_population(self._h, ops, size, functor, C.byref(idx)))
         pop = Population(self, idx.value, model, size)
+        self.populations.append(pop)
+        return pop
+
+    def add_host_population(self, size: int, update) -> Population:
+        """A population whose spikes come from the host (a neuron with a per-population update(),
+        concepts.h:46-57): `update(dt)` is called once per step, in step order, when the step is enqueued,
+        and returns the ids of the neurons that fire."""
+        def trampoline(_user, dt, _lo, _hi, _off, ids_out, capacity, draws_out):
+            try:
+                ids = np.asarray(update(dt), np.int32).ravel()
+                if len(ids) > capacity:
+                    return -1
+                C.memmove(ids_out, ids.ctypes.data, ids.nbytes)
+                draws_out[0] = 0
+                return len(ids)
+            except Exception:  # noqa: BLE001 - reported as a failed step by the runtime
+                return -1
+
+        cb = HOST_UPDATE_FN(trampoline)
+        self._keepalive.append(cb)
+        idx = C.c_int()
+        self._check(lib().spice_add_host_population(self._h, size, C.cast(cb, C.c_void_p), None, C.byref(idx)))
+        pop = Population(self, idx.value, "host", size)
         self.populations.append(pop)
         return pop
 

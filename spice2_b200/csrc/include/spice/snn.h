@@ -58,9 +58,14 @@ struct state_cache<void> {};
 template <Neuron Neur>
 class neuron_population : public NeuronPopulation {
 public:
-	neuron_population(spice_ctx* ctx, Neur neuron, Int const size) : _ctx(ctx), _size(size) {
-		check(ctx, spice_add_population(ctx, neuron_ops<Neur>(), size, &neuron, &_index));
+	neuron_population(spice_ctx* ctx, Neur neuron, Int const size) : _ctx(ctx), _size(size), _host(std::move(neuron)) {
+		if constexpr (PerPopulationUpdate<Neur>) // spikes come from the host functor, step by step (neuron_population.h:86-101)
+			check(ctx, spice_add_host_population(ctx, size, &neuron_population::host_update, this, &_index));
+		else
+			check(ctx, spice_add_population(ctx, neuron_ops<Neur>(), size, &_host, &_index));
 	}
+	neuron_population(neuron_population const&)            = delete; // the runtime holds `this`
+	neuron_population& operator=(neuron_population const&) = delete;
 
 	Int size() const override { return _size; }
 	int index() const override { return _index; }
@@ -85,9 +90,42 @@ public:
 	}
 
 private:
+	// engine over the step's stream that counts its draws
+	struct counting_engine {
+		using result_type = UInt;
+		util::xoroshiro64_128p g;
+		int64_t* draws;
+		static constexpr result_type min() { return util::xoroshiro64_128p::min(); }
+		static constexpr result_type max() { return util::xoroshiro64_128p::max(); }
+		result_type operator()() {
+			++*draws;
+			return g();
+		}
+	};
+	static int64_t host_update(void* user, float dt, uint64_t seed_lo, uint64_t seed_hi, uint64_t rng_offset, int32_t* ids_out,
+	                           int64_t capacity, int64_t* draws_out) {
+		if constexpr (PerPopulationUpdate<Neur>) {
+			auto* self = static_cast<neuron_population*>(user);
+			counting_engine rng{util::xoroshiro64_128p(seed_lo, seed_hi), draws_out};
+			for (uint64_t i = 0; i < rng_offset; i++) // populations before this one drew first (snn.cpp:12-15)
+				rng.g();
+			self->_out.clear();
+			self->_host.update(dt, rng, self->_out);
+			if (static_cast<int64_t>(self->_out.size()) > capacity)
+				return -1;
+			std::copy(self->_out.begin(), self->_out.end(), ids_out);
+			return static_cast<int64_t>(self->_out.size());
+		} else {
+			(void)user, (void)dt, (void)seed_lo, (void)seed_hi, (void)rng_offset, (void)ids_out, (void)capacity, (void)draws_out;
+			return -1;
+		}
+	}
+
 	spice_ctx* _ctx;
 	Int _size;
 	int _index = -1;
+	Neur _host;               // the functor; host-fed populations keep calling it
+	std::vector<Int32> _out;  // its output buffer
 	[[no_unique_address]] state_cache<neuron_traits_t<Neur>> _cache;
 };
 }

@@ -366,6 +366,12 @@ struct population {
 	std::uint32_t* state    = nullptr;
 	std::uint64_t* history  = nullptr;
 	long long rng_offset    = 0; // draws consumed per step by the populations added before this one
+	// host-fed population (spice_add_host_population): spikes staged in page-locked memory, one slot per ring slot
+	spice_host_update_fn host_update = nullptr;
+	void* host_user                  = nullptr;
+	std::int32_t* h_stage            = nullptr; // [ring][max(size, 1)]
+	std::uint32_t* h_stage_cnt       = nullptr; // [ring]
+	std::vector<cudaEvent_t> stage_done;        // [ring] the slot's copies have run
 	u128* jump_poly         = nullptr;
 	// exchange region views
 	long long ring_ids_off = 0, ring_cnt_off = 0; // byte offsets in the exchange region
@@ -547,6 +553,13 @@ int finalize(spice_ctx* ctx) {
 		}
 	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay, 2ll * ctx->window));
 	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
+	for (auto& p : ctx->pops)
+		if (p.host_update) {
+			size_t const cap = static_cast<size_t>(std::max<long long>(p.size, 1));
+			CHECK_CUDA(ctx, cudaHostAlloc(&p.h_stage, sizeof(std::int32_t) * cap * ctx->ring, cudaHostAllocDefault));
+			CHECK_CUDA(ctx, cudaHostAlloc(&p.h_stage_cnt, sizeof(std::uint32_t) * ctx->ring, cudaHostAllocDefault));
+			p.stage_done.assign(static_cast<size_t>(ctx->ring), nullptr);
+		}
 
 	int const np = static_cast<int>(ctx->pops.size());
 	// exchange region layout (identical on every rank)
@@ -836,8 +849,41 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	window_prologue<<<nsteps, 512, 0, ctx->stream>>>(pa);
 	ctx->launches++;
 
+	// host-fed populations: ask the host for every step's spikes, in step order, and copy them into the ring
+	for (int s = 0; s < nsteps; s++)
+		for (auto& p : ctx->pops) {
+			if (!p.host_update)
+				continue;
+			long long const slot = (ctx->time + s) % ctx->ring;
+			long long const cap  = std::max<long long>(p.size, 1);
+			cudaEvent_t& done    = p.stage_done[static_cast<size_t>(slot)];
+			if (done)
+				CHECK_CUDA(ctx, cudaEventSynchronize(done)); // the slot's previous copies have run
+			else
+				CHECK_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+			int64_t draws   = 0;
+			int64_t const n = p.host_update(p.host_user, dts[s], pa.seed[s].lo, pa.seed[s].hi, static_cast<uint64_t>(p.rng_offset),
+			                                p.h_stage + slot * cap, p.size, &draws);
+			if (n < 0 || n > p.size)
+				return fail(ctx, SPICE_ERR_PRECONDITION, "per-population update(): spike count out of range");
+			if (draws != 0)
+				return fail(ctx, SPICE_ERR_UNSUPPORTED, "a per-population update() that draws from the step's random stream is not supported yet");
+			for (int64_t i = 0; i < n; i++)
+				if (p.h_stage[slot * cap + i] < 0 || p.h_stage[slot * cap + i] >= p.size)
+					return fail(ctx, SPICE_ERR_PRECONDITION, "per-population update(): spike id out of range");
+			p.h_stage_cnt[slot] = static_cast<std::uint32_t>(n);
+			if (n)
+				CHECK_CUDA(ctx, cudaMemcpyAsync(xptr<std::int32_t>(ctx->xbase, p.ring_ids_off) + slot * cap, p.h_stage + slot * cap,
+				                                sizeof(std::int32_t) * static_cast<size_t>(n), cudaMemcpyHostToDevice, ctx->stream));
+			CHECK_CUDA(ctx, cudaMemcpyAsync(xptr<std::uint32_t>(ctx->xbase, p.ring_cnt_off) + slot * ctx->world, p.h_stage_cnt + slot,
+			                                sizeof(std::uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			CHECK_CUDA(ctx, cudaEventRecord(done, ctx->stream));
+		}
+
 	for (int pi = 0; pi < np; pi++) {
 		population& p = ctx->pops[pi];
+		if (p.host_update)
+			continue;
 		update_args ua{};
 		ua.stream  = ctx->stream;
 		ua.functor = p.functor_dev;
@@ -1266,6 +1312,13 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->xbase);
 	cudaFree(ctx->d_ring_cnt);
 	cudaFree(ctx->d_ring_ids);
+	for (auto& p : ctx->pops) {
+		cudaFreeHost(p.h_stage);
+		cudaFreeHost(p.h_stage_cnt);
+		for (auto e : p.stage_done)
+			if (e)
+				cudaEventDestroy(e);
+	}
 	cudaFree(ctx->d_ring_cap);
 	cudaFree(ctx->d_seg_lo);
 	cudaFree(ctx->d_peer_cnt);
@@ -1301,6 +1354,36 @@ int spice_ctx_set_stream(spice_ctx* ctx, void* cuda_stream) {
 		ctx->own_stream = false;
 	}
 	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return SPICE_OK;
+}
+
+namespace {
+// ops table of a host-fed population: stateless, no draws, nothing to launch
+int host_pop_noop_update(update_args const*) { return 0; }
+int host_pop_noop_export(export_args const*) { return 0; }
+int host_pop_noop_import(import_args const*) { return 0; }
+void host_pop_noop_init(void const*, void*, std::int64_t, std::uint64_t, std::uint64_t) {}
+spice_neuron_ops const host_pop_ops{1, "host", 0, 0, 0, 0, &host_pop_noop_init, &host_pop_noop_update, &host_pop_noop_export, &host_pop_noop_import};
+}
+
+int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn update, void* user, int* pop_out) {
+	PRE(ctx, update != nullptr);
+	PRE(ctx, size >= 0 && size < 2147483647);
+	PRE(ctx, !ctx->finalized && "add_population() after the first step is not supported");
+	if (ctx->world > 1)
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, "host-fed populations (per-population update()) are single-rank for now");
+	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	population p;
+	p.ops         = &host_pop_ops;
+	p.size        = size;
+	p.lo          = 0;
+	p.hi          = size;
+	p.stride      = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(size, 1)), 32));
+	p.host_update = update;
+	p.host_user   = user;
+	ctx->pops.push_back(std::move(p));
+	if (pop_out)
+		*pop_out = static_cast<int>(ctx->pops.size()) - 1;
 	return SPICE_OK;
 }
 

@@ -76,7 +76,7 @@ G["samples"] = S
 import ctypes as C
 import hashlib, subprocess
 G["sample_stdout_md5"] = {n: hashlib.md5(subprocess.run([str(HERE.parent.parent / "oracle" / "_ref" / n)], capture_output=True,
-                                                         check=True).stdout).hexdigest() for n in ("brunel", "brunel+", "vogels", "ping_pong")}
+                                                         check=True).stdout).hexdigest() for n in ("brunel", "brunel+", "vogels", "ping_pong", "external_input")}
 # samples/sssp.cpp run by the compiled reference (DeliverFromTo synapses): distances of the 7 vertices
 _d = np.zeros(7, np.int64)
 C.CDLL(str(HERE.parent.parent / "oracle" / "_ref" / "libspice_ref_strict.so")).ref_sssp_distances(_d.ctypes.data_as(C.c_void_p))

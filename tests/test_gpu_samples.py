@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("name", ["brunel", "brunel+", "vogels", "ping_pong"])
+@pytest.mark.parametrize("name", ["brunel", "brunel+", "vogels", "ping_pong", "external_input"])
 def test_sample_stdout_md5(golden, name):
     exe = ROOT / "samples" / "build" / name
     if not exe.exists():

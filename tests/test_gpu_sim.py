@@ -285,3 +285,37 @@ def test_sink_large_population_sorted(sp):
     assert np.array_equal(ids, np.concatenate(per_step))
     for x in per_step:
         assert len(x) > 3000 and np.all(np.diff(x) > 0)
+
+
+def test_host_fed_population_replays_poisson_input(sp):
+    """A host-fed population (per-population update(), concepts.h:46-57) that replays the spike train the
+    Poisson population of a Brunel network emitted drives E and I to exactly the same rasters and state."""
+    from spice2_b200 import fixed_probability
+
+    N, p, dt, delay = 4000, 0.1, 1e-4, 15e-4
+    w_exc, w_inh = np.float32(2.0 / 400), np.float32(-10.0 / 400)
+
+    def build(host_feed=None):
+        net = sp.snn(dt, delay, (1337,))
+        P = net.add_host_population(N // 2, host_feed) if host_feed else net.add_population("brunel.poisson", N // 2)
+        E = net.add_population("brunel.lif", N * 4 // 10)
+        I = net.add_population("brunel.lif", N // 10)
+        for (s, d, w) in ((P, E, w_exc), (P, I, w_exc), (E, E, w_exc), (E, I, w_exc), (I, E, w_inh), (I, I, w_inh)):
+            net.connect("brunel.fixed_weight", s, d, fixed_probability(p), delay, weight=w)
+        return net, (P, E, I)
+
+    steps = 200
+    net, pops = build()
+    counts, ids = gpu_raster(net, steps, 37)
+    state_e = pops[1].get_neurons()
+    # P's spike train, step by step
+    train, at = [], 0
+    for s in range(steps):
+        train.append(ids[at: at + counts[s, 0]].copy())
+        at += int(counts[s].sum())
+    feed = iter(train)
+    net2, pops2 = build(lambda _dt: next(feed))
+    counts2, ids2 = gpu_raster(net2, steps, 23)
+    assert np.array_equal(counts, counts2) and np.array_equal(ids, ids2)
+    assert np.array_equal(state_e, pops2[1].get_neurons())
+    assert counts[:, 1].sum() > 50  # E does fire in this window
