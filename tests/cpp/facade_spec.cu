@@ -1,0 +1,124 @@
+// The reference's unit tests of the hot path (test/detail/synapse_population.cpp:28-81,
+// test/detail/neuron_population.cpp:146-170) exercise internal classes; here the same small graphs
+// and fake models run through the PUBLIC API on the GPU: a host-fed source population
+// (per-population update()) emits the test's spike list, an adj_list carries the 3 x 5 graph, and the
+// counters the synapses leave in the target neurons are read back with get_neurons().
+// Exit status 0 = every expectation of the reference tests holds.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "spice/snn.h"
+
+using namespace spice;
+using namespace spice::util;
+
+#define EXPECT_EQ(a, b)                                                                                          \
+	do {                                                                                                         \
+		if (!((a) == (b))) {                                                                                     \
+			std::printf("%s:%d: expected %s == %s (%lld vs %lld)\n", __FILE__, __LINE__, #a, #b, (long long)(a), \
+			            (long long)(b));                                                                         \
+			std::exit(1);                                                                                        \
+		}                                                                                                        \
+	} while (0)
+
+// emits {0, 1} in the first step, nothing afterwards (synapse_population.cpp:47 `spikes[] = {0, 1}`)
+struct source {
+	Int step = 0;
+	void update(float, auto&, std::vector<Int32>& out) {
+		if (step++ == 0)
+			out.insert(out.end(), {0, 1});
+	}
+};
+static_assert(PerPopulationUpdate<source>);
+
+struct stateful_neuron { // synapse_population.cpp:13-19
+	struct neuron {
+		int received_count = 0;
+	};
+	SPICE_HD bool update(neuron&, float, auto&) const { return false; }
+};
+static_assert(StatefulNeuron<stateful_neuron>);
+
+struct stateless_synapse { // synapse_population.cpp:22-24
+	SPICE_HD void deliver(stateful_neuron::neuron& n) const { n.received_count++; }
+};
+struct stateful_synapse { // synapse_population.cpp:59-66
+	struct synapse {
+		int w = 2;
+	};
+	SPICE_HD void deliver(synapse const& syn, stateful_neuron::neuron& n) const { n.received_count += syn.w; }
+};
+
+adj_list graph() { // synapse_population.cpp:33-40
+	adj_list adj;
+	adj.connect(0, 0);
+	adj.connect(0, 1);
+	adj.connect(0, 3);
+	adj.connect(1, 3);
+	adj.connect(2, 4);
+	return adj;
+}
+
+template <class Syn>
+std::vector<int> deliver_once() {
+	snn net(1, 1, {1337});
+	auto src = net.add_population<source>(3);
+	auto dst = net.add_population<stateful_neuron>(5);
+	auto adj = graph();
+	net.connect<Syn>(src, dst, adj, 1);
+	net.step();
+	std::vector<int> got;
+	for (auto const& n : dst->get_neurons())
+		got.push_back(n.received_count);
+	return got;
+}
+
+// neuron_population.cpp:141-170
+struct per_population_update {
+	void update(float, auto&, std::vector<Int32>& spikes) { spikes.insert(spikes.end(), {1, 3, 8}); }
+};
+
+int main() {
+	{ // SynapsePopulation.DeliverStateless
+		auto const n = deliver_once<stateless_synapse>();
+		EXPECT_EQ(n[0], 1);
+		EXPECT_EQ(n[1], 1);
+		EXPECT_EQ(n[2], 0);
+		EXPECT_EQ(n[3], 2);
+		EXPECT_EQ(n[4], 0);
+	}
+	{ // SynapsePopulation.DeliverStateful
+		auto const n = deliver_once<stateful_synapse>();
+		EXPECT_EQ(n[0], 2);
+		EXPECT_EQ(n[1], 2);
+		EXPECT_EQ(n[2], 0);
+		EXPECT_EQ(n[3], 4);
+		EXPECT_EQ(n[4], 0);
+	}
+	{ // NeuronPopulation.PerPopulationUpdate
+		snn net(1, 1, {1337});
+		auto pop = net.add_population<per_population_update>(10);
+		EXPECT_EQ(pop->size(), 10);
+		net.step();
+		EXPECT_EQ(pop->spikes(0).size(), 3u);
+		EXPECT_EQ(pop->spikes(0)[0], 1);
+		EXPECT_EQ(pop->spikes(0)[1], 3);
+		EXPECT_EQ(pop->spikes(0)[2], 8);
+	}
+	{ // preconditions throw std::logic_error (util/assert.h:3-17): a delay beyond max_delay (snn.h:36-38)
+		snn net(1, 1, {1337});
+		auto src = net.add_population<source>(3);
+		auto dst = net.add_population<stateful_neuron>(5);
+		auto adj = graph();
+		bool threw = false;
+		try {
+			net.connect<stateless_synapse>(src, dst, adj, 2);
+		} catch (std::logic_error const&) {
+			threw = true;
+		}
+		EXPECT_EQ(threw, true);
+	}
+	std::printf("facade_spec: ok\n");
+	return 0;
+}

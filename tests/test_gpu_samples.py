@@ -27,3 +27,13 @@ def test_sssp_distances(golden):
         subprocess.run(["make", "-s", "-C", str(ROOT / "samples")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, check=True, timeout=600).stdout.split()
     assert [int(x) for x in out] == golden["sssp_distances"]
+
+
+def test_facade_spec_program():
+    """tests/cpp/facade_spec.cu: the reference's own unit tests of delivery and per-population update
+    (test/detail/synapse_population.cpp:28-81, test/detail/neuron_population.cpp:146-170) through the public API."""
+    exe = ROOT / "tests" / "cpp" / "build" / "facade_spec"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
