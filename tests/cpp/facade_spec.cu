@@ -32,6 +32,16 @@ struct source {
 };
 static_assert(PerPopulationUpdate<source>);
 
+// emits {1, 2} in step `at` (synapse_population.cpp:100 `spikes[] = {1, 2}`)
+struct late_source {
+	Int at   = 0;
+	Int step = 0;
+	void update(float, auto&, std::vector<Int32>& out) {
+		if (step++ == at)
+			out.insert(out.end(), {1, 2});
+	}
+};
+
 struct stateful_neuron { // synapse_population.cpp:13-19
 	struct neuron {
 		int received_count = 0;
@@ -49,6 +59,16 @@ struct stateful_synapse { // synapse_population.cpp:59-66
 	};
 	SPICE_HD void deliver(synapse const& syn, stateful_neuron::neuron& n) const { n.received_count += syn.w; }
 };
+
+struct plastic_synapse { // synapse_population.cpp:83-93: counts how many steps it was brought forward
+	struct synapse {
+		int update_count = 0;
+	};
+	SPICE_HD void deliver(synapse const& syn, stateful_neuron::neuron& n) const { n.received_count = syn.update_count; }
+	SPICE_HD void update(synapse& syn, float, bool, bool) const { syn.update_count++; }
+	SPICE_HD void skip(synapse& syn, float, Int steps) const { syn.update_count += steps; }
+};
+static_assert(PlasticSynapse<plastic_synapse>);
 
 adj_list graph() { // synapse_population.cpp:33-40
 	adj_list adj;
@@ -95,6 +115,22 @@ int main() {
 		EXPECT_EQ(n[2], 0);
 		EXPECT_EQ(n[3], 4);
 		EXPECT_EQ(n[4], 0);
+	}
+	// SynapsePopulation.DeliverPlastic (synapse_population.cpp:96-168): the lazy bookkeeping (`_ages`, the flush of
+	// snn.cpp:17-19 at step 0).  A synapse delivered at step T has been brought forward over steps 0..T exactly
+	// once each, however often it was visited: T + 1 updates (the reference's cases T = 0, 1 and 9).
+	for (Int T : {0, 1, 9, 70}) {
+		snn net(1, 1, {1337});
+		auto src = net.add_population<late_source>(3, {T});
+		auto dst = net.add_population<stateful_neuron>(5);
+		auto adj = graph();
+		net.connect<plastic_synapse>(src, dst, adj, 1);
+		for (Int i = 0; i <= T; i++)
+			net.step();
+		auto const n = dst->get_neurons();
+		EXPECT_EQ(n[3].received_count, T + 1);
+		EXPECT_EQ(n[4].received_count, T + 1);
+		EXPECT_EQ(n[0].received_count, 0);
 	}
 	{ // NeuronPopulation.PerPopulationUpdate
 		snn net(1, 1, {1337});
