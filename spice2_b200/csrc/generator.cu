@@ -243,6 +243,7 @@ struct orbit_args {
 	long long const* seg_base;
 	long long base;   // global position of y[0]
 	long long limit;  // rows starting at or after this global position belong to the next chunk
+	long long len;    // draws held in y (chunk + overlap)
 	long long* row_start; // [src + 1], global positions
 	orbit_state* st;
 };
@@ -285,6 +286,31 @@ __global__ void __launch_bounds__(32) fp_orbit(orbit_args a) {
 		long long e       = -1; // local position of the terminating draw
 		long long Pnext   = 0;
 		bool need_exact   = false;
+		{
+			// Coarse step: index + round(noise) never decreases along a row, so the row cannot have ended
+			// before a draw at which it provably has not.  Test the first draw of the next 32 blocks at
+			// once (one round trip instead of one per block) and start the fine scan in the block before
+			// the first one that may be past the end.
+			long long const B = blk + lane;
+			long long const t = B * kBlk;
+			bool may_be_past  = true;
+			if (t < a.len) {
+				may_be_past        = false;
+				long long const n  = t - sl;
+				if (n >= 0) {
+					long long const Pt = a.seg_base[t / kSeg] + a.blk_local[B] + quantize(a.y[t], P.fix); // P(t + 1)
+					double const v     = __dmul_rn(__dmul_rn(__ll2double_rn(Pt - Ps), P.inv_fix), P.c);
+					long long const rh = __double2ll_rd(v + P.delta + 0.5);
+					may_be_past        = (n >= P.max_degree) | (n + rh >= P.dst);
+				}
+			}
+			unsigned const m = __ballot_sync(0xffffffffu, may_be_past);
+			int const j      = m ? __ffs(m) - 1 : 32;
+			if (j >= 2) {
+				blk += j - 1;
+				first_block = false; // its first draw provably precedes the end
+			}
+		}
 		for (;;) {
 			long long const t  = blk * kBlk + lane;
 			long long const in = quantize(a.y[t], P.fix);
@@ -381,21 +407,42 @@ __global__ void __launch_bounds__(128) fp_rows(rows_args a) {
 	int index = 0, dst = 0;
 	long long t        = s;
 	double const* y    = a.y;
-	for (;;) {
-		if (row_step(y[t], P, noise, index, dst))
-			break;
-		if (dst >= P.col_lo && dst < P.col_hi) {
-			if (a.write) {
-				if (out < a.capacity)
-					a.neighbors[out] = dst - static_cast<int>(P.col_lo);
-				out++;
+	// The recurrence is sequential, its inputs are not: the draws are fetched 8 at a time, one batch
+	// ahead (a chunk holds only ~1,700 rows, so a dependent load per step would leave the kernel
+	// waiting on memory latency).  Reads past the row's end stay inside the chunk's overlap margin.
+	constexpr int kAhead = 16;
+	double cur[kAhead], nxt[kAhead];
+#pragma unroll
+	for (int i = 0; i < kAhead; i++)
+		cur[i] = y[t + i];
+	for (bool done = false; !done;) {
+#pragma unroll
+		for (int i = 0; i < kAhead; i++)
+			nxt[i] = y[t + kAhead + i];
+#pragma unroll
+		for (int i = 0; i < kAhead; i++) {
+			if (done)
+				continue;
+			if (row_step(cur[i], P, noise, index, dst)) {
+				done = true;
+				continue;
 			}
-			kept++;
+			if (dst >= P.col_lo && dst < P.col_hi) {
+				if (a.write) {
+					if (out < a.capacity)
+						a.neighbors[out] = dst - static_cast<int>(P.col_lo);
+					out++;
+				}
+				kept++;
+			}
+			index++;
+			t++;
+			if (t > en) // would run past the orbit's row end: the check below reports it
+				done = true;
 		}
-		index++;
-		t++;
-		if (t > en) // would run past the orbit's row end: the check below reports it
-			break;
+#pragma unroll
+		for (int i = 0; i < kAhead; i++)
+			cur[i] = nxt[i];
 	}
 	if (t != en)
 		atomicOr(a.error, 1);
@@ -500,7 +547,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	// expected stream length and output size
 	double const mean_deg = std::min(static_cast<double>(dst) * p + 1.0, static_cast<double>(P.max_degree));
 	long long const ov    = round_up(P.max_degree + 2 + 2 * kBlk, kSeg);
-	long long ch          = chunk_draws > 0 ? chunk_draws : (1ll << 24);
+	long long ch          = chunk_draws > 0 ? chunk_draws : (1ll << 26);
 	{
 		double const est = static_cast<double>(src) * (mean_deg + 1.0) * 1.02 + 65536.0;
 		if (est < static_cast<double>(ch))
@@ -593,7 +640,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	while (row < src) {
 		GEN_CUDA(static_cast<cudaError_t>(run_values(base)));
 		fp_segscan<<<1, 1024, 0, stream>>>(seg_sum, seg_base, segs);
-		orbit_args oa{P, y, blk_local, seg_base, base, base + ch, row_start, st};
+		orbit_args oa{P, y, blk_local, seg_base, base, base + ch, len, row_start, st};
 		fp_orbit<<<1, 32, 0, stream>>>(oa);
 		launches += 2;
 		GEN_CUDA(cudaGetLastError());
