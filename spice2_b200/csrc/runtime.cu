@@ -422,6 +422,10 @@ struct spice_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream     = false;
+	// the populations of a window update concurrently: side streams forked from / joined into `stream`
+	static constexpr int kAux = 3;
+	cudaStream_t aux[kAux]   = {};
+	cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
 	float dt            = 0;
 	long long max_delay = 1;
 	util::seed_seq seed{UInt128{0, 0}};
@@ -880,12 +884,39 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			CHECK_CUDA(ctx, cudaEventRecord(done, ctx->stream));
 		}
 
+	// The populations' update kernels are independent of each other (each reads counters written in
+	// earlier windows and writes its own state and spike lists), and the smaller ones do not fill the
+	// device: all but the first run on side streams, forked here and joined before the exchange.
+	int device_pops = 0;
+	for (auto const& p : ctx->pops)
+		device_pops += (!p.host_update && p.hi > p.lo) ? 1 : 0;
+	bool const fan = device_pops > 1 && !std::getenv("SPICE_SERIAL_UPDATES");
+	if (fan) {
+		if (!ctx->ev_fork) {
+			CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+			for (int k = 0; k < spice_ctx::kAux; k++) {
+				CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+				CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
+			}
+		}
+		CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+	}
+	int launched = 0;
+	unsigned aux_used = 0;
 	for (int pi = 0; pi < np; pi++) {
 		population& p = ctx->pops[pi];
 		if (p.host_update)
 			continue;
 		update_args ua{};
 		ua.stream  = ctx->stream;
+		if (fan && p.hi > p.lo && launched++ > 0) {
+			int const k = (launched - 2) % spice_ctx::kAux;
+			if (!((aux_used >> k) & 1u)) {
+				CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->ev_fork, 0));
+				aux_used |= 1u << k;
+			}
+			ua.stream = ctx->aux[k];
+		}
 		ua.functor = p.functor_dev;
 		ua.state   = p.state;
 		ua.n_local = p.hi - p.lo;
@@ -929,6 +960,11 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ctx->launches++;
 		}
 	}
+	for (int k = 0; k < spice_ctx::kAux; k++)
+		if ((aux_used >> k) & 1u) {
+			CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->aux[k]));
+			CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+		}
 
 	if (ctx->profile)
 		prof_mark(ctx);
@@ -1341,6 +1377,14 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	for (auto e : ctx->prof_events)
 		cudaEventDestroy(e);
 	cudaGetLastError();
+	for (int k = 0; k < spice_ctx::kAux; k++) {
+		if (ctx->aux[k])
+			cudaStreamDestroy(ctx->aux[k]);
+		if (ctx->ev_join[k])
+			cudaEventDestroy(ctx->ev_join[k]);
+	}
+	if (ctx->ev_fork)
+		cudaEventDestroy(ctx->ev_fork);
 	if (ctx->own_stream)
 		cudaStreamDestroy(ctx->stream);
 	delete ctx;
