@@ -117,7 +117,6 @@ struct unit_info {
 	int stride;               // tiles (packed) / tiles + 1 (plain)
 	unsigned total;           // spikes of the step (all ranks)
 	long long ring_slot;
-	unsigned seg_n[spice::detail::kMaxWorld], seg_first[spice::detail::kMaxWorld]; // per rank: spikes, start in the flat order
 };
 
 // One warp's pipeline over its share of a unit: the batches b = first, first + step, ... of the
@@ -136,23 +135,10 @@ struct unit_walker {
 	int lane;
 	unsigned char* cnt;
 	int4 const* stream;  // the connection's packed stream
-	unsigned my_n, my_first;
 	unsigned p_g0, p_ng; // this lane's run of the batch whose descriptors are written next
 	std::int32_t id_next; // this lane's spike of the batch after that
 
-	__device__ __forceinline__ std::int32_t spike_id(unsigned q) const { // flat index -> source neuron (0 when q >= total)
-		int r       = 0;
-		unsigned f0 = 0;
-		for (int i = 1; i < a.world; i++) {
-			unsigned const f = __shfl_sync(kFull, my_first, i);
-			unsigned const n = __shfl_sync(kFull, my_n, i);
-			if (q >= f && n > 0) {
-				r  = i;
-				f0 = f;
-			}
-		}
-		return q < U.total ? U.ids0[U.C->seg_lo[r] + (q - f0)] : 0;
-	}
+	__device__ __forceinline__ std::int32_t spike_id(unsigned q) const { return q < U.total ? U.ids0[q] : 0; } // source neuron (0 past the end)
 	__device__ __forceinline__ void load_ptrs(unsigned q, std::int32_t id) {
 		p_g0 = 0, p_ng = 0;
 		if (q < U.total) {
@@ -187,13 +173,6 @@ struct unit_walker {
 	__device__ __forceinline__ void run(unsigned first, unsigned step, unsigned nbatch) {
 		cnt    = smem + kDescBytes;
 		stream = reinterpret_cast<int4 const*>(U.C->packed);
-		// the step's spike list: one segment per rank; lane r keeps segment r's size and its start in
-		// the flat order (read once per unit by the claiming thread: one global round trip less per warp)
-		my_n = 0, my_first = 0;
-		if (lane < a.world) {
-			my_n     = U.seg_n[lane];
-			my_first = U.seg_first[lane];
-		}
 
 		zero_tile(cnt, a.tile_cap, (U.width + 127) & ~127, lane);
 		unsigned const mine = first < nbatch ? (nbatch - first + step - 1) / step : 0; // batches of this warp
@@ -229,20 +208,14 @@ struct unit_walker {
 // Rare path, out of line: connections whose entries are plain columns (rows that may repeat a
 // target: adj_list multapses).  One global atomic per event into the tile's (zeroed) range.
 __device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U, int lane, int warp) {
-	unsigned const world = static_cast<unsigned>(a.world);
-	long long ev         = 0;
-	unsigned q0          = 0;
-	for (unsigned r = 0; r < world; r++) {
-		unsigned const n = U.C->ring_cnt[U.ring_slot * a.world + r];
-		for (unsigned j = warp; j < n; j += kWarps) {
-			long long const id  = U.ids0[U.C->seg_lo[r] + j];
-			long long const* tp = U.tile_ptr + id * U.stride;
-			long long const beg = tp[0], end = tp[1];
-			for (long long e = beg + lane; e < end; e += 32)
-				atomicAdd(U.out + (U.C->neighbors[e] - U.lo), 1u);
-			ev += end - beg;
-		}
-		q0 += n;
+	long long ev = 0;
+	for (unsigned j = warp; j < U.total; j += kWarps) {
+		long long const id  = U.ids0[j];
+		long long const* tp = U.tile_ptr + id * U.stride;
+		long long const beg = tp[0], end = tp[1];
+		for (long long e = beg + lane; e < end; e += 32)
+			atomicAdd(U.out + (U.C->neighbors[e] - U.lo), 1u);
+		ev += end - beg;
 	}
 	if (lane == 0 && ev)
 		atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
@@ -277,14 +250,8 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				U.gp        = C.run_ptr + k;
 				U.tile_ptr  = C.tile_ptr + k;
 				U.stride    = C.arranged ? C.tiles : C.tiles + 1;
-				unsigned total = 0;
-				for (int r = 0; r < a.world; r++) {
-					unsigned const n = C.ring_cnt[U.ring_slot * a.world + r];
-					U.seg_n[r]       = n;
-					U.seg_first[r]   = total;
-					total += n;
-				}
-				U.total = total;
+				unsigned const total = C.ring_cnt[U.ring_slot * C.cnt_stride];
+				U.total              = total;
 				if (k == 0 && total)
 					atomicAdd(a.stats + 1, static_cast<unsigned long long>(total));
 			}

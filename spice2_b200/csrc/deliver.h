@@ -12,10 +12,13 @@ constexpr int kTileMax = 5120; // targets per tile: one warp keeps two u8 counte
 // One connection as the delivery kernel sees it (lives in device memory, one array per context,
 // in schedule order: heaviest connections first).
 struct conn_desc {
-	std::int32_t const* ring_ids;  // spike ring of the SOURCE population (this rank's copy)
-	std::uint32_t const* ring_cnt; // [ring][world]
+	// spike lists of the SOURCE population, one per ring slot, flat: ids[slot * ring_cap .. + cnt[slot * cnt_stride]).
+	// One rank: the spike ring itself; several ranks: the ring's per-rank segments concatenated once per window
+	// (flatten_window in runtime.cu), so the kernel never deals with segments.
+	std::int32_t const* ring_ids;
+	std::uint32_t const* ring_cnt;
 	long long ring_cap;
-	long long seg_lo[spice::detail::kMaxWorld]; // first source neuron of every rank's segment of a ring slot
+	long long cnt_stride;
 	std::int32_t const* packed;    // arranged connections: the delivery stream (see pack_runs)
 	unsigned const* run_ptr;       // arranged connections: [src * tiles + 1] first 16-byte group of every run
 	std::int32_t const* neighbors; // plain connections: CSR entries (local columns)

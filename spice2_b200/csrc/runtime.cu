@@ -349,6 +349,35 @@ __global__ void __launch_bounds__(kSinkThreads) sink_pack(sink_args a) {
 		a.h_ids[(base + k) % a.cap] = a.stage[(base + k) % a.cap];
 }
 
+// Several ranks: a ring slot holds one segment of spike ids per rank.  Once per window, after the
+// exchange, every (step, population) list is copied into one flat list (rank order = ascending ids), so
+// the delivery kernel reads spike lists the same way whatever the number of ranks.
+struct flatten_args {
+	std::int32_t const* const* ring_ids; // [npops]
+	std::uint32_t const* const* ring_cnt;
+	long long const* ring_cap;           // [npops]
+	long long const* seg_lo;             // [npops][world]
+	std::int32_t* const* flat_ids;       // [npops] [ring][cap]
+	std::uint32_t* const* flat_cnt;      // [npops] [ring]
+	int npops, ring, world;
+	long long t0;
+};
+__global__ void __launch_bounds__(256) flatten_window(flatten_args a) {
+	int const s = blockIdx.x / a.npops, p = blockIdx.x % a.npops;
+	long long const slot = (a.t0 + s) % a.ring;
+	std::int32_t* out    = a.flat_ids[p] + slot * a.ring_cap[p];
+	unsigned done        = 0;
+	for (int r = 0; r < a.world; r++) {
+		unsigned const c         = a.ring_cnt[p][slot * a.world + r];
+		std::int32_t const* from = a.ring_ids[p] + slot * a.ring_cap[p] + a.seg_lo[p * a.world + r];
+		for (unsigned j = threadIdx.x; j < c; j += blockDim.x)
+			out[done + j] = from[j];
+		done += c;
+	}
+	if (threadIdx.x == 0)
+		a.flat_cnt[p][slot] = done;
+}
+
 __global__ void fill_u32(std::uint32_t* dst, long long n, std::uint32_t value) {
 	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (i < n)
@@ -366,6 +395,8 @@ struct population {
 	std::uint32_t* state    = nullptr;
 	std::uint64_t* history  = nullptr;
 	long long rng_offset    = 0; // draws consumed per step by the populations added before this one
+	std::int32_t* flat_ids  = nullptr; // world > 1: [ring][max(size, 1)] the ring's segments concatenated (flatten_window)
+	std::uint32_t* flat_cnt = nullptr; // world > 1: [ring]
 	// host-fed population (spice_add_host_population): spikes staged in page-locked memory, one slot per ring slot
 	spice_host_update_fn host_update = nullptr;
 	void* host_user                  = nullptr;
@@ -461,6 +492,8 @@ struct spice_ctx {
 	std::int32_t** d_ring_ids         = nullptr; // [npops]
 	long long* d_ring_cap             = nullptr;
 	long long* d_seg_lo               = nullptr; // [npops][world]
+	std::int32_t** d_flat_ids         = nullptr; // [npops] (world > 1)
+	std::uint32_t** d_flat_cnt        = nullptr;
 	u128* d_nib                       = nullptr;
 	unsigned long long* d_stats       = nullptr; // events, spikes
 	int* d_error                      = nullptr;
@@ -566,6 +599,20 @@ int finalize(spice_ctx* ctx) {
 		}
 
 	int const np = static_cast<int>(ctx->pops.size());
+	if (ctx->world > 1) {
+		// Load the kernels that are first launched BEHIND wait_window now: loading a kernel lazily can
+		// synchronise the context, which never happens while wait_window spins for a peer whose work this
+		// thread has not enqueued yet (two rank contexts in one process, tests/test_gpu_sim.py).
+		cudaFuncAttributes fa{};
+		CHECK_CUDA(ctx, cudaFuncGetAttributes(&fa, flatten_window));
+	}
+	if (ctx->world > 1) // flat copies of the spike lists for the delivery kernel (flatten_window)
+		for (auto& p : ctx->pops) {
+			size_t const cap = static_cast<size_t>(std::max<long long>(p.size, 1));
+			CHECK_CUDA(ctx, cudaMalloc(&p.flat_ids, sizeof(std::int32_t) * cap * ctx->ring));
+			CHECK_CUDA(ctx, cudaMalloc(&p.flat_cnt, sizeof(std::uint32_t) * ctx->ring));
+			CHECK_CUDA(ctx, cudaMemset(p.flat_cnt, 0, sizeof(std::uint32_t) * ctx->ring));
+		}
 	// exchange region layout (identical on every rank)
 	size_t off = 0;
 	for (auto& p : ctx->pops) {
@@ -677,11 +724,10 @@ int finalize(spice_ctx* ctx) {
 			population const& src = ctx->pops[c.src];
 			population const& dst = ctx->pops[c.dst];
 			deliver::conn_desc d{};
-			d.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
-			d.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
-			d.ring_cap = std::max<long long>(src.size, 1);
-			for (int r = 0; r < ctx->world; r++)
-				d.seg_lo[r] = src.size * r / ctx->world;
+			d.ring_ids   = ctx->world > 1 ? src.flat_ids : xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
+			d.ring_cnt   = ctx->world > 1 ? src.flat_cnt : xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
+			d.ring_cap   = std::max<long long>(src.size, 1);
+			d.cnt_stride = 1;
 			d.packed      = c.packed;
 			d.run_ptr     = c.run_ptr;
 			d.neighbors   = c.neighbors;
@@ -748,6 +794,18 @@ int finalize(spice_ctx* ctx) {
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_cap, sizeof(long long) * std::max(np, 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_seg_lo, sizeof(long long) * std::max<size_t>(h_seg.size(), 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_peer_cnt, sizeof(void*) * std::max(np, 1) * ctx->world));
+	if (ctx->world > 1 && np) {
+		std::vector<std::int32_t*> h_flat_ids;
+		std::vector<std::uint32_t*> h_flat_cnt;
+		for (auto const& p : ctx->pops) {
+			h_flat_ids.push_back(p.flat_ids);
+			h_flat_cnt.push_back(p.flat_cnt);
+		}
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_flat_ids, sizeof(void*) * np));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_flat_cnt, sizeof(void*) * np));
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_flat_ids, h_flat_ids.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
+		CHECK_CUDA(ctx, cudaMemcpy(ctx->d_flat_cnt, h_flat_cnt.data(), sizeof(void*) * np, cudaMemcpyHostToDevice));
+	}
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pop_size, sizeof(long long) * std::max(np, 1)));
 	if (np) {
 		std::vector<long long> h_size;
@@ -986,6 +1044,12 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		wait_args wa{xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off)), ctx->world, ctx->seq, ctx->d_error};
 		wait_window<<<1, 32, 0, ctx->stream>>>(wa);
 		ctx->launches += 2;
+		if (ctx->tiled && np > 0) { // one flat spike list per (step, population) for the delivery kernel
+			flatten_args fa{ctx->d_ring_ids, ctx->d_ring_cnt, ctx->d_ring_cap, ctx->d_seg_lo, ctx->d_flat_ids, ctx->d_flat_cnt,
+			                np,              ctx->ring,       ctx->world,      ctx->time};
+			flatten_window<<<nsteps * np, 256, 0, ctx->stream>>>(fa);
+			ctx->launches++;
+		}
 	}
 
 	if (ctx->profile)
@@ -1349,12 +1413,16 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_ring_cnt);
 	cudaFree(ctx->d_ring_ids);
 	for (auto& p : ctx->pops) {
+		cudaFree(p.flat_ids);
+		cudaFree(p.flat_cnt);
 		cudaFreeHost(p.h_stage);
 		cudaFreeHost(p.h_stage_cnt);
 		for (auto e : p.stage_done)
 			if (e)
 				cudaEventDestroy(e);
 	}
+	cudaFree(ctx->d_flat_ids);
+	cudaFree(ctx->d_flat_cnt);
 	cudaFree(ctx->d_ring_cap);
 	cudaFree(ctx->d_seg_lo);
 	cudaFree(ctx->d_peer_cnt);
