@@ -47,7 +47,7 @@ namespace spice::deliver {
 namespace {
 
 constexpr int kWarps       = 4;  // warps per CTA: they share a unit, each with its own copy of the tile
-constexpr int kCtasPerSm   = 4;  // register budget: 16 warps per SM
+constexpr int kCtasPerSm   = 5;  // register budget: 20 warps per SM
 constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane and run, in registers)
 constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
 constexpr unsigned kFull   = 0xffffffffu;
