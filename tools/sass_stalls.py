@@ -23,4 +23,5 @@ for i, r in enumerate(data):
     op = re.sub(r'@!?U?P\d\s+', '', r[1]).split()[0].split('.')[0]
     if op in ('VOTE', 'ATOMG', 'LDG', 'BAR', 'ATOMS', 'NANOSLEEP', 'B2R', 'LDL', 'STL'): d[3].add(op)
 for b, d in blk.items():
-    if d[1] > tot / 150: print(d[0], 'samples', d[1], 'maxexec', d[2], sorted(d[3]))
+    if d[1] > tot / 150:
+        print(d[0], 'samples', d[1], 'maxexec', d[2], sorted(d[3]))
