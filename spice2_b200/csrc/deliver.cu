@@ -38,7 +38,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "deliver.h"
@@ -117,6 +119,10 @@ struct unit_info {
 	int stride;               // tiles (packed) / tiles + 1 (plain)
 	unsigned total;           // spikes of the step (all ranks)
 	long long ring_slot;
+	// split launches (an item = one round of a unit):
+	unsigned b0, b1;          // the item's batches [b0, b1) of the step's spike list
+	unsigned round, rounds;   // which of the unit's rounds this is
+	unsigned* flag;           // set to the window's epoch once round 0 has stored the unit's counters
 };
 
 // One warp's pipeline over its share of a unit: the batches b = first, first + step, ... of the
@@ -194,11 +200,15 @@ struct unit_walker {
 					write_desc(i, first + (i + 1) * step, step);
 				}
 				run_desc const* const id = desc + (((h + 1) >> 1) & 1) * 32 + ((h + 1) & 1) * 16;
+				bool const more          = h + 1 < 2 * mine;
 #pragma unroll
 				for (int j = 0; j < kRing; j++) {
 					tally(cnt, v[j]);
 					__syncwarp();
-					v[j] = issue(id + j);
+					// nothing is fetched behind the call's last half batch: the descriptors there belong to the
+					// unit's next round (issue() would count the tails of its long runs into this one)
+					if (more)
+						v[j] = issue(id + j);
 				}
 			}
 		}
@@ -221,6 +231,61 @@ __device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U,
 		atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
 }
 
+constexpr unsigned kPerRound = kWarps * kRoundBatches; // batches a CTA counts between two merges
+
+// rounds a unit of connection C takes when its step holds `total` spikes
+__device__ __forceinline__ unsigned rounds_of(conn_desc const& C, unsigned total) {
+	unsigned const nbatch = (total + 31) / 32;
+	return C.arranged ? max(1u, (nbatch + kPerRound - 1) / kPerRound) : 1u;
+}
+
+__device__ __forceinline__ unsigned ld_acquire(unsigned const* p) {
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Split launches: plan[c * nsteps + s] = first item of (connection c, step s), plan[nconns * nsteps] = items.
+// (connection, step) holds tiles x rounds items, a unit's rounds next to each other, round 0 first.
+__global__ void __launch_bounds__(256) plan_items(tiles_args a) {
+	using scan_t = cub::BlockScan<unsigned, 256>;
+	__shared__ typename scan_t::TempStorage tmp;
+	__shared__ unsigned running;
+	int const ncs = a.nconns * a.nsteps;
+	if (threadIdx.x == 0)
+		running = 0;
+	__syncthreads();
+	for (int base = 0; base < ncs; base += 256) {
+		int const j = base + threadIdx.x;
+		unsigned v  = 0;
+		if (j < ncs) {
+			conn_desc const& C = a.conns[j / a.nsteps];
+			long long const t  = a.t0 + j % a.nsteps;
+			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C, C.ring_cnt[(t % a.ring) * C.cnt_stride]);
+		}
+		unsigned ex, agg;
+		scan_t(tmp).ExclusiveSum(v, ex, agg);
+		unsigned const r0 = running;
+		if (j < ncs)
+			a.plan[j] = r0 + ex;
+		__syncthreads();
+		if (threadIdx.x == 0)
+			running = r0 + agg;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		a.plan[ncs] = running;
+}
+
+// kSplit = false: a CTA claims whole units and loops over their rounds.
+// kSplit = true:  a CTA claims single rounds (plan_items); round 0 of a unit stores the counters and
+//                 publishes the unit's flag, later rounds wait for the flag and add with atomics.  The
+//                 wait cannot deadlock: round 0 has a lower ticket, so a running CTA holds it, and
+//                 round 0 never waits.  For windows with few, long units (a rank of a multi-GPU run).
+template <bool kSplit>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_args a) {
 	extern __shared__ uint4 smem4[];
 	__shared__ unit_info U;
@@ -228,18 +293,43 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	size_t const wbytes  = warp_smem(a.tile_cap);
 	unsigned char* smem  = reinterpret_cast<unsigned char*>(smem4) + warp * wbytes;
-	unsigned const units = static_cast<unsigned>(a.total_tiles) * a.nsteps;
+	unsigned const units = kSplit ? a.plan[a.nconns * a.nsteps] : static_cast<unsigned>(a.total_tiles) * a.nsteps;
+	int cs = 0; // thread 0, split launches: the (connection, step) of the last ticket; tickets only grow
 	for (;;) {
 		if (threadIdx.x == 0) {
 			unsigned const u = atomicAdd(a.work, 1u);
 			claimed          = u;
 			if (u < units) {
-				int c = 0;
-				while (c + 1 < a.nconns && static_cast<unsigned>(a.conns[c + 1].tile_prefix) * a.nsteps <= u)
-					c++;
-				conn_desc const& C   = a.conns[c];
-				unsigned const local = u - static_cast<unsigned>(C.tile_prefix) * a.nsteps;
-				int const s = static_cast<int>(local / C.tiles), k = static_cast<int>(local % C.tiles);
+				int c = 0, s, k;
+				unsigned r = 0;
+				if constexpr (kSplit) {
+					while (a.plan[cs + 1] <= u)
+						cs++;
+					c = cs / a.nsteps;
+					s = cs % a.nsteps;
+				} else {
+					while (c + 1 < a.nconns && static_cast<unsigned>(a.conns[c + 1].tile_prefix) * a.nsteps <= u)
+						c++;
+				}
+				conn_desc const& C = a.conns[c];
+				if constexpr (kSplit) {
+					unsigned const local  = u - a.plan[cs];
+					unsigned const total  = C.ring_cnt[((a.t0 + s) % a.ring) * C.cnt_stride];
+					unsigned const nbatch = (total + 31) / 32;
+					unsigned const rounds = rounds_of(C, total);
+					unsigned const per    = (nbatch + rounds - 1) / rounds; // batches per round (<= kPerRound), evened out
+					k                     = static_cast<int>(local / rounds);
+					r                     = local % rounds;
+					U.round               = r;
+					U.rounds              = rounds;
+					U.b0                  = r * per;
+					U.b1                  = min(nbatch, U.b0 + per);
+					U.flag                = a.unit_flag + (static_cast<unsigned>(C.tile_prefix) * a.nsteps + static_cast<unsigned>(s) * C.tiles + k);
+				} else {
+					unsigned const local = u - static_cast<unsigned>(C.tile_prefix) * a.nsteps;
+					s                    = static_cast<int>(local / C.tiles);
+					k                    = static_cast<int>(local % C.tiles);
+				}
 				long long const t = a.t0 + s;
 				U.C         = &C;
 				U.lo        = k * C.tile;
@@ -252,7 +342,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				U.stride    = C.arranged ? C.tiles : C.tiles + 1;
 				unsigned const total = C.ring_cnt[U.ring_slot * C.cnt_stride];
 				U.total              = total;
-				if (k == 0 && total)
+				if (k == 0 && r == 0 && total)
 					atomicAdd(a.stats + 1, static_cast<unsigned long long>(total));
 			}
 		}
@@ -270,12 +360,16 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 			__syncthreads();
 			continue;
 		}
-		constexpr unsigned per_round = kWarps * kRoundBatches;
-		unsigned const rounds        = max(1u, (nbatch + per_round - 1) / per_round);
+		constexpr unsigned per_round = kPerRound;
+		unsigned const rounds        = kSplit ? 1u : max(1u, (nbatch + per_round - 1) / per_round);
 		for (unsigned round = 0; round < rounds; round++) {
-			unsigned const b0 = round * per_round;
+			unsigned const b0 = kSplit ? U.b0 : round * per_round;
 			unit_walker w{a, U, smem, lane};
-			w.run(b0 + warp, kWarps, min(nbatch, b0 + per_round));
+			w.run(b0 + warp, kWarps, kSplit ? U.b1 : min(nbatch, b0 + per_round));
+			if constexpr (kSplit)
+				if (U.round > 0 && threadIdx.x == 0) // round 0 has stored the unit's counters?
+					while (ld_acquire(U.flag) != a.epoch)
+						__nanosleep(64);
 			__syncthreads();
 			// add the warps' arrays and store / accumulate: this CTA is the only writer of the range.
 			// Word wd of array A holds targets 4 wd .. 4 wd + 3; their B counters sit in the same
@@ -297,17 +391,34 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				}
 				uint4 c = make_uint4(even & 0xffffu, odd & 0xffffu, even >> 16, odd >> 16);
 				ev += c.x + c.y + c.z + c.w;
-				if (round) {
-					uint4 const prev = o[wd];
-					c.x += prev.x, c.y += prev.y, c.z += prev.z, c.w += prev.w;
+				if constexpr (kSplit) {
+					if (U.round == 0)
+						o[wd] = c;
+					else {
+						if (c.x) atomicAdd(U.out + 4 * wd + 0, c.x);
+						if (c.y) atomicAdd(U.out + 4 * wd + 1, c.y);
+						if (c.z) atomicAdd(U.out + 4 * wd + 2, c.z);
+						if (c.w) atomicAdd(U.out + 4 * wd + 3, c.w);
+					}
+				} else {
+					if (round) {
+						uint4 const prev = o[wd];
+						c.x += prev.x, c.y += prev.y, c.z += prev.z, c.w += prev.w;
+					}
+					o[wd] = c;
 				}
-				o[wd] = c;
 			}
 			for (int off = 16; off; off >>= 1)
 				ev += __shfl_xor_sync(kFull, ev, off);
 			if (lane == 0 && ev)
 				atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
+			if constexpr (kSplit)
+				if (U.round == 0 && U.rounds > 1)
+					__threadfence(); // the counters before the flag
 			__syncthreads();
+			if constexpr (kSplit)
+				if (U.round == 0 && U.rounds > 1 && threadIdx.x == 0)
+					st_release(U.flag, a.epoch);
 		}
 	}
 }
@@ -549,7 +660,17 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
 	return static_cast<int>(cudaGetLastError());
 }
 
-int launch_tiles(void* stream, tiles_args const& a, int device) {
+// experiments (read once): SPICE_DELIVER_CTAS_PER_SM / SPICE_DELIVER_GRID shrink the persistent grid,
+// SPICE_DELIVER_SPLIT = 0 / 1 forces whole-unit / single-round work items
+static int env_int(char const* name, int dflt) {
+	char const* e = std::getenv(name);
+	return e && *e ? std::atoi(e) : dflt;
+}
+constexpr long long kSplitBelow = 4; // split when a window has fewer than this many units per resident CTA
+
+int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
+	static int const ctas_env = env_int("SPICE_DELIVER_CTAS_PER_SM", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
+	                 split_env = env_int("SPICE_DELIVER_SPLIT", -1);
 	static int blocks_per_sm[64] = {};
 	static int sms[64]           = {};
 	static int smem_set[64]      = {};
@@ -557,25 +678,55 @@ int launch_tiles(void* stream, tiles_args const& a, int device) {
 	if (device < 0 || device >= 64)
 		return static_cast<int>(cudaErrorInvalidDevice);
 	if (smem_set[device] < static_cast<int>(smem)) {
-		cudaError_t e = cudaFuncSetAttribute(deliver_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-		if (e != cudaSuccess)
-			return static_cast<int>(e);
-		e = cudaFuncSetAttribute(deliver_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		if (e != cudaSuccess)
-			return static_cast<int>(e);
-		int nb = 0;
-		e      = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, deliver_tiles, kWarps * 32, smem);
-		if (e != cudaSuccess)
-			return static_cast<int>(e);
+		int nb = 1 << 30;
+		for (auto kernel : {deliver_tiles<false>, deliver_tiles<true>}) {
+			cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+			if (e != cudaSuccess)
+				return static_cast<int>(e);
+			e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			if (e != cudaSuccess)
+				return static_cast<int>(e);
+			int n = 0;
+			e     = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kWarps * 32, smem);
+			if (e != cudaSuccess)
+				return static_cast<int>(e);
+			nb = std::min(nb, n);
+		}
 		cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);
 		blocks_per_sm[device] = std::max(nb, 1);
-		smem_set[device]      = static_cast<int>(smem);
+		if (ctas_env > 0)
+			blocks_per_sm[device] = std::clamp(ctas_env, 1, blocks_per_sm[device]);
+		smem_set[device] = static_cast<int>(smem);
 	}
 	long long const units = static_cast<long long>(a.total_tiles) * a.nsteps;
 	if (units <= 0)
 		return 0;
-	int const grid = static_cast<int>(std::min<long long>(units, static_cast<long long>(sms[device]) * blocks_per_sm[device]));
-	deliver_tiles<<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+	long long const full = static_cast<long long>(sms[device]) * blocks_per_sm[device];
+	int grid             = static_cast<int>(std::min<long long>(units, full));
+	if (grid_env > 0)
+		grid = std::clamp(grid_env, 1, grid);
+	// few units per CTA (a rank of a multi-GPU run: many sources, few tiles): hand out single rounds
+	bool split = a.plan && a.unit_flag && units < kSplitBelow * full;
+	if (split_env >= 0)
+		split = split_env != 0 && a.plan && a.unit_flag;
+	if (launches)
+		*launches = split ? 2 : 1;
+	if (split) {
+		grid = static_cast<int>(grid_env > 0 ? std::min<long long>(grid_env, full) : full); // items >= units; idle CTAs leave at once
+		plan_items<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+		deliver_tiles<true><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+	} else
+		deliver_tiles<false><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
 	return static_cast<int>(cudaGetLastError());
+}
+
+int preload() {
+	cudaFuncAttributes fa{};
+	cudaError_t e = cudaFuncGetAttributes(&fa, deliver_tiles<false>);
+	if (e == cudaSuccess)
+		e = cudaFuncGetAttributes(&fa, deliver_tiles<true>);
+	if (e == cudaSuccess)
+		e = cudaFuncGetAttributes(&fa, plan_items);
+	return static_cast<int>(e);
 }
 }

@@ -47,6 +47,10 @@ struct tiles_args {
 	unsigned long long* stats; // [0] events, [1] spikes
 	int* error;                // bit 16: internal error in the delivery kernel
 	int tile_cap;              // targets per warp-private counter array (max conns[].tile rounded up to 128)
+	// split launches (work items = single rounds of a unit; null: never split):
+	unsigned* plan;      // [nconns * window + 1] first item of every (connection, step), rewritten by every launch
+	unsigned* unit_flag; // [total_tiles * window] epoch of the launch whose round 0 has stored the unit's counters
+	unsigned epoch;      // this launch's, > 0 and different from the previous launches'
 };
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
@@ -69,6 +73,11 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
                 int tile, int tiles, int cap, std::int32_t* out);
 
 // One launch delivers every spike of the window on every connection.  `blocks` <= 0 picks a
-// persistent grid filling the device.  Returns a cudaError_t as int.
-int launch_tiles(void* stream, tiles_args const& a, int device);
+// persistent grid filling the device.  Windows with few units per CTA are launched split (plan_items +
+// deliver_tiles<true>, deliver.cu); `launches` receives the number of kernels launched.  Returns a
+// cudaError_t as int.
+int launch_tiles(void* stream, tiles_args const& a, int device, int* launches = nullptr);
+
+// Loads the delivery kernels (a lazily loaded kernel can synchronise the context at its first launch).
+int preload();
 }

@@ -319,3 +319,65 @@ def test_host_fed_population_replays_poisson_input(sp):
     assert np.array_equal(counts, counts2) and np.array_equal(ids, ids2)
     assert np.array_equal(state_e, pops2[1].get_neurons())
     assert counts[:, 1].sum() > 50  # E does fire in this window
+
+
+_SPLIT_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from spice2_b200.samples import brunel, vogels
+out = {{}}
+for name, make, steps in (("brunel", brunel, 300), ("vogels", vogels, 1500)):
+    net, pops = make()
+    net.raster_enable(True)
+    net.step(steps)
+    counts, ids = net.raster_read()
+    out[name + "_counts"], out[name + "_ids"] = counts, ids
+    out[name + "_state"] = np.frombuffer(pops[1].get_neurons().tobytes(), dtype=np.uint8)
+    out[name + "_events"] = np.array([net.stats()["synaptic_events"]])
+# dense vogels: every volley is 3200 + 800 spikes in one step (4 rounds per unit) and half of the runs
+# are longer than one warp-wide load (256-target tiles at p = 0.5: 128 entries on average)
+net, pops = vogels(p=0.5)
+net.raster_enable(True)
+net.step(200)
+counts, ids = net.raster_read()
+out["dense_counts"], out["dense_ids"] = counts, ids
+out["dense_E"] = np.frombuffer(pops[0].get_neurons().tobytes(), dtype=np.uint8)
+out["dense_I"] = np.frombuffer(pops[1].get_neurons().tobytes(), dtype=np.uint8)
+net.step(8)
+out["dense_events"] = np.array([net.stats()["synaptic_events"]])
+np.savez({dest!r}, **out)
+"""
+
+
+@pytest.mark.parametrize("split", [0, 1])
+def test_delivery_whole_units_and_single_rounds(sp, orc, golden, tmp_path, split):
+    """Both work distributions of the delivery kernel (deliver.cu: a CTA claims whole units / single
+    rounds of a unit, stored by round 0 and added by the later rounds) give the golden rasters.  The
+    vogels run starts with one volley of all 4000 neurons: 3200 spikes in one step = 4 rounds per unit."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = str(Path(__file__).resolve().parent.parent)
+    dest = str(tmp_path / f"split{split}.npz")
+    env = dict(os.environ, SPICE_DELIVER_SPLIT=str(split))
+    subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT.format(root=root, dest=dest)], check=True, env=env, timeout=600)
+    got = np.load(dest)
+    for name, key in (("brunel", "brunel_300_strict"), ("vogels", "vogels_1500_strict")):
+        g = golden["samples"][key]
+        assert [int(x) for x in got[name + "_counts"].sum(0)] == g["totals"]
+        assert hx(orc.fnv(got[name + "_counts"])) == g["fnv_counts"]
+        assert hx(orc.fnv(got[name + "_ids"])) == g["fnv_ids"]
+    assert int(got["vogels_events"][0]) > 0
+    onet, opops = vogels_oracle(orc, p=0.5)
+    rows, ocounts = run_raster(onet, opops, 200)
+    assert ocounts.max() == 3200  # whole-population volleys
+    assert np.array_equal(got["dense_counts"], ocounts)
+    assert np.array_equal(got["dense_ids"], flatten_raster(rows))
+    for key, pop in (("dense_E", opops[0]), ("dense_I", opops[1])):
+        assert got[key].tobytes() == onet.neurons(pop).tobytes()
+    for _ in range(8 + 7):  # see test_synaptic_event_count
+        onet.step()
+    assert int(got["dense_events"][0]) == onet.events()
