@@ -234,9 +234,9 @@ __device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U,
 constexpr unsigned kPerRound = kWarps * kRoundBatches; // batches a CTA counts between two merges
 
 // rounds a unit of connection C takes when its step holds `total` spikes
-__device__ __forceinline__ unsigned rounds_of(conn_desc const& C, unsigned total) {
+__device__ __forceinline__ unsigned rounds_of(conn_desc const& C, unsigned total, unsigned per_round) {
 	unsigned const nbatch = (total + 31) / 32;
-	return C.arranged ? max(1u, (nbatch + kPerRound - 1) / kPerRound) : 1u;
+	return C.arranged ? max(1u, (nbatch + per_round - 1) / per_round) : 1u;
 }
 
 __device__ __forceinline__ unsigned ld_acquire(unsigned const* p) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) plan_items(tiles_args a) {
 		if (j < ncs) {
 			conn_desc const& C = a.conns[j / a.nsteps];
 			long long const t  = a.t0 + j % a.nsteps;
-			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C, C.ring_cnt[(t % a.ring) * C.cnt_stride]);
+			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C, C.ring_cnt[(t % a.ring) * C.cnt_stride], a.round_batches);
 		}
 		unsigned ex, agg;
 		scan_t(tmp).ExclusiveSum(v, ex, agg);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 					unsigned const local  = u - a.plan[cs];
 					unsigned const total  = C.ring_cnt[((a.t0 + s) % a.ring) * C.cnt_stride];
 					unsigned const nbatch = (total + 31) / 32;
-					unsigned const rounds = rounds_of(C, total);
+					unsigned const rounds = rounds_of(C, total, a.round_batches);
 					unsigned const per    = (nbatch + rounds - 1) / rounds; // batches per round (<= kPerRound), evened out
 					k                     = static_cast<int>(local / rounds);
 					r                     = local % rounds;
@@ -661,16 +661,20 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
 }
 
 // experiments (read once): SPICE_DELIVER_CTAS_PER_SM / SPICE_DELIVER_GRID shrink the persistent grid,
-// SPICE_DELIVER_SPLIT = 0 / 1 forces whole-unit / single-round work items
+// SPICE_DELIVER_SPLIT = 0 / 1 forces whole-unit / single-round work items, SPICE_DELIVER_ROUND = batches of 32
+// spikes per single-round item (<= kPerRound)
 static int env_int(char const* name, int dflt) {
 	char const* e = std::getenv(name);
 	return e && *e ? std::atoi(e) : dflt;
 }
-constexpr long long kSplitBelow = 4; // split when a window has fewer than this many units per resident CTA
+// Split when a window has fewer than 2.5 units per resident CTA.  Measured on one B200 with the per-rank shapes of
+// the weak-scaled Brunel benchmark (tools/rank_shape_probe.py, rates oscillating by +-50 %; single rounds vs whole
+// units): 1 rank, 4.4 units per CTA: -6 %; 2 ranks, 3.0: -4 %; 4 ranks, 2.3: +7 %; 8 ranks, 1.5: +8 % (+22 % at +-80 %).
+constexpr long long kSplitBelowNum = 5, kSplitBelowDen = 2;
 
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	static int const ctas_env = env_int("SPICE_DELIVER_CTAS_PER_SM", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
-	                 split_env = env_int("SPICE_DELIVER_SPLIT", -1);
+	                 split_env = env_int("SPICE_DELIVER_SPLIT", -1), round_env = env_int("SPICE_DELIVER_ROUND", 0);
 	static int blocks_per_sm[64] = {};
 	static int sms[64]           = {};
 	static int smem_set[64]      = {};
@@ -706,15 +710,17 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	if (grid_env > 0)
 		grid = std::clamp(grid_env, 1, grid);
 	// few units per CTA (a rank of a multi-GPU run: many sources, few tiles): hand out single rounds
-	bool split = a.plan && a.unit_flag && units < kSplitBelow * full;
+	bool split = a.plan && a.unit_flag && kSplitBelowDen * units < kSplitBelowNum * full;
 	if (split_env >= 0)
 		split = split_env != 0 && a.plan && a.unit_flag;
 	if (launches)
 		*launches = split ? 2 : 1;
 	if (split) {
 		grid = static_cast<int>(grid_env > 0 ? std::min<long long>(grid_env, full) : full); // items >= units; idle CTAs leave at once
-		plan_items<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-		deliver_tiles<true><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+		tiles_args b    = a;
+		b.round_batches = round_env > 0 ? std::min<unsigned>(round_env, kPerRound) : kPerRound;
+		plan_items<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+		deliver_tiles<true><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(b);
 	} else
 		deliver_tiles<false><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
 	return static_cast<int>(cudaGetLastError());

@@ -51,6 +51,7 @@ struct tiles_args {
 	unsigned* plan;      // [nconns * window + 1] first item of every (connection, step), rewritten by every launch
 	unsigned* unit_flag; // [total_tiles * window] epoch of the launch whose round 0 has stored the unit's counters
 	unsigned epoch;      // this launch's, > 0 and different from the previous launches'
+	unsigned round_batches; // set by launch_tiles: batches of 32 spikes per item
 };
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
