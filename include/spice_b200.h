@@ -199,6 +199,9 @@ SPICE_API int spice_adjacency_timing(spice_adjacency const* a, float* total_ms, 
 SPICE_API int spice_adjacency_destroy(spice_adjacency* a);
 
 /* ---- seeds (host; random.h:143-175) ---------------------------------------------------------- */
+/* snn::_seed (snn.h:69): the seed the next `seed++` hands out -- the one the next connection's
+ * Topology::generate receives (synapse_population.h:31, csr.h:69-77). */
+SPICE_API int spice_ctx_seed(spice_ctx const* ctx, uint64_t out[2]);
 SPICE_API void spice_seed_seq(uint32_t const* words, int n, uint64_t out[2]);
 SPICE_API void spice_seed_next(uint64_t seed[2]);
 

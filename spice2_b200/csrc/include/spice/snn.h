@@ -18,6 +18,7 @@
 // Errors keep the reference's convention: std::logic_error("Assertion failed (file:line): cond").
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <memory>
 #include <span>
@@ -132,6 +133,18 @@ private:
 
 inline Int fixed_probability::size() const { return src_count * spice_fixed_probability_max_degree(dst_count, _p); }
 
+inline void fixed_probability::generate(std::span<Int> offsets, std::span<Int32> neighbors, util::seed_seq const& seed) {
+	SPICE_PRE(static_cast<Int>(offsets.size()) > src_count);
+	SPICE_PRE(static_cast<Int>(neighbors.size()) >= size());
+	spice_adjacency* a = nullptr;
+	if (spice_fixed_probability_generate(device, src_count, dst_count, _p, seed.seed().lo, seed.seed().hi, 0, dst_count, &a) != SPICE_OK)
+		throw std::logic_error(spice_last_error(nullptr));
+	int const rc = spice_adjacency_copy(a, offsets.data(), neighbors.data());
+	spice_adjacency_destroy(a);
+	if (rc != SPICE_OK)
+		throw std::logic_error(spice_last_error(nullptr));
+}
+
 class snn {
 public:
 	snn(float const dt, float const max_delay, util::seed_seq seed, int device = 0, int rank = 0, int world = 1,
@@ -162,8 +175,25 @@ public:
 		else if (auto* adj = dynamic_cast<adj_list*>(&c))
 			detail::check(_ctx.get(), spice_connect_adj_list(_ctx.get(), ops, source->index(), target->index(), adj->sources().data(),
 			                                                 adj->targets().data(), adj->size(), delay, &syn, nullptr));
-		else
-			throw std::logic_error("Assertion failed (snn.h): unsupported Topology subclass on the GPU backend");
+		else {
+			// a user-defined Topology: run its generate() on the host with the seed the connection is about to consume
+			// (synapse_population.h:31 `_graph(c, seed++)`, csr.h:69-77), then upload the rows like an adj_list's.  Rows
+			// arrive sorted by target; that is the order generate() emitted whenever it emitted ascending targets.
+			uint64_t sd[2];
+			detail::check(_ctx.get(), spice_ctx_seed(_ctx.get(), sd));
+			std::vector<Int> offsets(static_cast<std::size_t>(c.src_count > 0 ? c.src_count + 1 : 0));
+			std::vector<Int32> neighbors(static_cast<std::size_t>(c.size()));
+			c.generate(offsets, neighbors, util::seed_seq(UInt128{sd[0], sd[1]}));
+			SPICE_INV(std::is_sorted(offsets.begin(), offsets.end()));
+			Int const edges = offsets.empty() ? 0 : offsets.back();
+			SPICE_INV(edges <= static_cast<Int>(neighbors.size()));
+			std::vector<Int32> srcs(static_cast<std::size_t>(edges));
+			for (Int row = 0; row < c.src_count; row++)
+				std::fill(srcs.begin() + offsets[static_cast<std::size_t>(row)], srcs.begin() + offsets[static_cast<std::size_t>(row) + 1],
+				          static_cast<Int32>(row));
+			detail::check(_ctx.get(), spice_connect_adj_list(_ctx.get(), ops, source->index(), target->index(), srcs.data(),
+			                                                 neighbors.data(), edges, delay, &syn, nullptr));
+		}
 	}
 
 	template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>

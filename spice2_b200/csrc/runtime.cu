@@ -2092,6 +2092,14 @@ int spice_adjacency_destroy(spice_adjacency* a) {
 	return SPICE_OK;
 }
 
+int spice_ctx_seed(spice_ctx const* ctx, uint64_t out[2]) {
+	if (!ctx || !out)
+		return SPICE_ERR_PRECONDITION;
+	out[0] = ctx->seed.seed().lo;
+	out[1] = ctx->seed.seed().hi;
+	return SPICE_OK;
+}
+
 void spice_seed_seq(uint32_t const* words, int n, uint64_t out[2]) {
 	util::seed_seq s(words, static_cast<std::size_t>(n));
 	out[0] = s.seed().lo;

@@ -80,6 +80,19 @@ adj_list graph() { // synapse_population.cpp:33-40
 	return adj;
 }
 
+// The same 3 x 5 graph as a user-defined Topology writing an edge_stream (topology.h:11-35, topology.cpp:12-55):
+// the reference's extension point.  It also checks the seed it is handed: the connection's own (synapse_population.h:31).
+struct graph_topology : Topology {
+	UInt128 seen{};
+	Int size() const override { return 8; } // an upper bound, like fixed_probability::size()
+	using Topology::generate;
+	void generate(edge_stream& s, util::seed_seq const& seed) override {
+		seen = seed.seed();
+		s << std::pair{Int32(0), Int32(0)} << std::pair{Int32(0), Int32(1)} << std::pair{Int32(0), Int32(3)} << std::pair{Int32(1), Int32(3)}
+		  << std::pair{Int32(2), Int32(4)};
+	}
+};
+
 template <class Syn>
 std::vector<int> deliver_once() {
 	snn net(1, 1, {1337});
@@ -141,6 +154,28 @@ int main() {
 		EXPECT_EQ(pop->spikes(0)[0], 1);
 		EXPECT_EQ(pop->spikes(0)[1], 3);
 		EXPECT_EQ(pop->spikes(0)[2], 8);
+	}
+	{ // a user-defined Topology (edge_stream) delivers like the adj_list of the same edges, stateless and stateful
+		snn net(1, 1, {1337});
+		auto src  = net.add_population<source>(3);          // per-population update: no seed++
+		auto dst  = net.add_population<stateful_neuron>(5); // stateful adapter: one seed++ (neuron_population.h:60-67)
+		auto dst2 = net.add_population<stateful_neuron>(5);
+		graph_topology topo;
+		net.connect<stateless_synapse>(src, dst, topo, 1);
+		util::seed_seq want{1337};
+		want++;
+		want++;
+		EXPECT_EQ(topo.seen.lo, want.seed().lo);
+		EXPECT_EQ(topo.seen.hi, want.seed().hi);
+		net.connect<stateful_synapse>(src, dst2, graph_topology{}, 1);
+		net.step();
+		auto const a = dst->get_neurons();
+		auto const b = dst2->get_neurons();
+		int const expect[5] = {1, 1, 0, 2, 0};
+		for (int i = 0; i < 5; i++) {
+			EXPECT_EQ(a[i].received_count, expect[i]);
+			EXPECT_EQ(b[i].received_count, 2 * expect[i]);
+		}
 	}
 	{ // preconditions throw std::logic_error (util/assert.h:3-17): a delay beyond max_delay (snn.h:36-38)
 		snn net(1, 1, {1337});

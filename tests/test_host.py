@@ -144,3 +144,83 @@ def test_host_kahan_dt_matches_oracle(hosttool, orc):
     out = subprocess.run([str(hosttool), "kahan", "12000"], capture_output=True, text=True, check=True).stdout.split()
     got = np.array([int(v, 16) for v in out], np.uint32)
     assert np.array_equal(got, orc.kahan_dt(np.float32(1e-4), 12000).view(np.uint32))
+
+
+def test_topology_header_edge_stream(tmp_path):
+    """spice/topology.h on the host: the reference's CSR cases (test/detail/csr.cpp:17-61: Empty, Custom) through
+    Topology::generate(offsets, neighbors, seed), a user-defined Topology writing an edge_stream (topology.h:11-22,
+    topology.cpp:12-55), and the preconditions of edge_stream / the Topology base class."""
+    src = tmp_path / "topo.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <vector>
+#include "spice/topology.h"
+using namespace spice;
+#define CHECK(c) do { if (!(c)) { std::printf("line %d: %s\n", __LINE__, #c); return 1; } } while (0)
+struct ring : Topology {       // i -> i + 1 (mod n), and 0 -> every third neuron
+	Int size() const override { return src_count + dst_count; }
+	using Topology::generate;
+	void generate(edge_stream& s, util::seed_seq const& seed) override {
+		util::xoroshiro64_128p rng(seed);
+		draw = rng();
+		for (Int i = 0; i < src_count; i++) {
+			if (i == 0)
+				for (Int d = 0; d < dst_count; d += 3)
+					s << std::pair{Int32(0), Int32(d)};
+			if (i != 2)            // row 2 stays empty
+				s << std::pair{Int32(i), Int32((i + 1) % dst_count)};
+		}
+	}
+	UInt draw = 0;
+};
+struct nothing : Topology { Int size() const override { return 0; } };
+template <class F> bool throws(F f) { try { f(); } catch (std::logic_error const&) { return true; } return false; }
+int main() {
+	{ // CSR.Empty
+		adj_list adj; adj(1, 0);
+		std::vector<Int> off(2); std::vector<Int32> nb; // zero-filled, as csr's constructor sizes them (csr.h:70-71)
+		adj.generate(off, nb, util::seed_seq{1337});
+		CHECK(off[0] == 0 && off[1] == 0);
+	}
+	{ // CSR.Custom: unsorted input, empty middle row
+		adj_list adj;
+		CHECK(adj.size() == 0);
+		adj.connect(2, 2); adj.connect(0, 9); adj.connect(0, 0); adj.connect(2, 1); adj.connect(0, 7); adj.connect(0, 2);
+		adj(3, 10);
+		std::vector<Int> off(4, -1); std::vector<Int32> nb(adj.size(), -1);
+		adj.generate(off, nb, util::seed_seq{1337});
+		CHECK((off == std::vector<Int>{0, 4, 4, 6}));
+		CHECK((nb == std::vector<Int32>{0, 2, 7, 9, 1, 2}));
+	}
+	{ // user-defined topology; trailing empty rows are closed by flush()
+		ring r; r(6, 5);
+		std::vector<Int> off(7, -1); std::vector<Int32> nb(r.size(), -1);
+		r.generate(off, nb, util::seed_seq{1337});
+		CHECK((off == std::vector<Int>{0, 3, 4, 4, 5, 6, 7}));
+		CHECK((std::vector<Int32>(nb.begin(), nb.begin() + 7) == std::vector<Int32>{0, 3, 1, 2, 4, 0, 1}));
+		CHECK(r.draw == 0xa349d5b00b80b8e0ull); // first output of xoroshiro64_128p(seed_seq{1337}) (SURVEY 8c)
+	}
+	{ // preconditions
+		nothing n; n(1, 1);
+		std::vector<Int> off(2); std::vector<Int32> nb(1);
+		CHECK(throws([&] { n.generate(off, nb, util::seed_seq{1}); }));            // generate(edge_stream) not implemented
+		ring r; r(6, 5);
+		std::vector<Int> small(6);  std::vector<Int32> big(64);
+		CHECK(throws([&] { r.generate(small, big, util::seed_seq{1}); }));        // offsets.size() > src_count
+		std::vector<Int> ok(7); std::vector<Int32> tiny(3);
+		CHECK(throws([&] { r.generate(ok, tiny, util::seed_seq{1}); }));          // neighbors.size() >= size()
+		edge_stream es(ok, big);
+		CHECK(throws([&] { es << std::pair{Int32(7), Int32(0)}; }));               // src beyond the offsets
+		CHECK(throws([&] { Topology& t = r; t(-1, 3); }));
+	}
+	std::puts("ok");
+	return 0;
+}
+''')
+    exe = tmp_path / "topo"
+    inc = ROOT / "spice2_b200" / "csrc" / "include"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
