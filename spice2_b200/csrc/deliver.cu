@@ -44,6 +44,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "deliver.h"
+#include "deliver_plan.h"
 
 namespace spice::deliver {
 namespace {
@@ -233,12 +234,6 @@ __device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U,
 
 constexpr unsigned kPerRound = kWarps * kRoundBatches; // batches a CTA counts between two merges
 
-// rounds a unit of connection C takes when its step holds `total` spikes
-__device__ __forceinline__ unsigned rounds_of(conn_desc const& C, unsigned total, unsigned per_round) {
-	unsigned const nbatch = (total + 31) / 32;
-	return C.arranged ? max(1u, (nbatch + per_round - 1) / per_round) : 1u;
-}
-
 __device__ __forceinline__ unsigned ld_acquire(unsigned const* p) {
 	unsigned v;
 	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -264,7 +259,7 @@ __global__ void __launch_bounds__(256) plan_items(tiles_args a) {
 		if (j < ncs) {
 			conn_desc const& C = a.conns[j / a.nsteps];
 			long long const t  = a.t0 + j % a.nsteps;
-			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C, C.ring_cnt[(t % a.ring) * C.cnt_stride], a.round_batches);
+			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C.arranged != 0, C.ring_cnt[(t % a.ring) * C.cnt_stride], a.round_batches);
 		}
 		unsigned ex, agg;
 		scan_t(tmp).ExclusiveSum(v, ex, agg);
@@ -313,17 +308,14 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 				}
 				conn_desc const& C = a.conns[c];
 				if constexpr (kSplit) {
-					unsigned const local  = u - a.plan[cs];
-					unsigned const total  = C.ring_cnt[((a.t0 + s) % a.ring) * C.cnt_stride];
-					unsigned const nbatch = (total + 31) / 32;
-					unsigned const rounds = rounds_of(C, total, a.round_batches);
-					unsigned const per    = (nbatch + rounds - 1) / rounds; // batches per round (<= kPerRound), evened out
-					k                     = static_cast<int>(local / rounds);
-					r                     = local % rounds;
-					U.round               = r;
-					U.rounds              = rounds;
-					U.b0                  = r * per;
-					U.b1                  = min(nbatch, U.b0 + per);
+					unsigned const total = C.ring_cnt[((a.t0 + s) % a.ring) * C.cnt_stride];
+					item_pos const it    = locate_item(u - a.plan[cs], C.arranged != 0, total, a.round_batches);
+					k                    = static_cast<int>(it.tile);
+					r                    = it.round;
+					U.round              = it.round;
+					U.rounds             = it.rounds;
+					U.b0                 = it.b0;
+					U.b1                 = it.b1;
 					U.flag                = a.unit_flag + (static_cast<unsigned>(C.tile_prefix) * a.nsteps + static_cast<unsigned>(s) * C.tiles + k);
 				} else {
 					unsigned const local = u - static_cast<unsigned>(C.tile_prefix) * a.nsteps;

@@ -224,3 +224,56 @@ int main() {
     subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_delivery_plan_covers_every_batch(tmp_path):
+    """csrc/deliver_plan.h (the ticket -> (tile, round, batches) arithmetic of split delivery launches, shared with
+    the kernels): over random spike counts, the tickets of a (connection, step) visit every (tile, round) once, a
+    unit's rounds are adjacent with round 0 first, the rounds' batch ranges partition [0, nbatch) in order, and no
+    round exceeds the u8 counters' limit."""
+    src = tmp_path / "plan.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <random>
+#include "deliver_plan.h"
+using namespace spice::deliver;
+#define CHECK(c) do { if (!(c)) { std::printf("line %d: %s (total %u per %u tiles %u)\n", __LINE__, #c, total, per, tiles); return 1; } } while (0)
+int main() {
+	std::mt19937 g(7);
+	unsigned const totals[] = {0, 1, 31, 32, 33, 895, 896, 897, 1791, 1792, 1793, 2000, 2880, 3200, 100000, 1000000};
+	for (unsigned per : {28u, 20u, 7u, 1u})
+		for (int trial = 0; trial < 400; trial++) {
+			unsigned const total = trial < 16 ? totals[trial] : g() % (trial % 2 ? 5000 : 60000);
+			unsigned const tiles = 1 + g() % 7;
+			for (bool arranged : {true, false}) {
+				unsigned const nbatch = (total + 31) / 32, rounds = rounds_of(arranged, total, per);
+				CHECK(rounds >= 1);
+				CHECK(arranged ? (rounds == (nbatch + per - 1) / per || (nbatch <= per && rounds == 1)) : rounds == 1);
+				unsigned local = 0;
+				for (unsigned k = 0; k < tiles; k++) {
+					unsigned next = 0;
+					for (unsigned r = 0; r < rounds; r++, local++) {
+						item_pos const p = locate_item(local, arranged, total, per);
+						CHECK(p.tile == k && p.round == r && p.rounds == rounds);
+						if (rounds > 1 || arranged) {
+							CHECK(p.b0 == next || (p.b0 >= nbatch && p.b1 == nbatch));
+							CHECK(p.b1 <= nbatch);
+							CHECK(p.b1 <= p.b0 || p.b1 - p.b0 <= per);
+							if (p.b1 > p.b0)
+								next = p.b1;
+						}
+					}
+					if (arranged)
+						CHECK(next == nbatch);
+				}
+			}
+		}
+	std::puts("ok");
+	return 0;
+}
+''')
+    exe = tmp_path / "plan"
+    inc = ROOT / "spice2_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
