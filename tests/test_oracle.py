@@ -186,3 +186,15 @@ def test_oracle_vs_reference_brunel_plus(orc, ref_strict):
     r = ref_strict.brunel(seed=5, steps=200, plastic=True, **kw)
     assert np.array_equal(cnt, r["counts"]) and np.array_equal(flatten_raster(rows), r["ids"])
     assert np.array_equal(net.neurons(1), r["state_E"])
+
+
+def test_oracle_vs_reference_vogels_dense(orc, ref_strict):
+    """The dense Vogels network of tests/test_gpu_sim.py::test_delivery_whole_units_and_single_rounds (p = 0.5:
+    whole-population volleys, rows of 1600 + 400 entries): the restatement that checks the GPU there agrees with
+    the compiled reference here."""
+    net, pops = vogels_oracle(orc, p=0.5)
+    rows, cnt = run_raster(net, pops, 200)
+    r = ref_strict.vogels(p=0.5, steps=200)
+    assert cnt.max() == 3200
+    assert np.array_equal(cnt, r["counts"]) and np.array_equal(flatten_raster(rows), r["ids"])
+    assert np.array_equal(net.neurons(0), r["state_E"]) and np.array_equal(net.neurons(1), r["state_I"])
