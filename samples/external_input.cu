@@ -1,38 +1,39 @@
-// External input (reference: samples/external_input.cpp): a population whose spikes come from the
-// host — a neuron description with a per-population update(dt, rng, out_spikes) — fed step by step
-// into the simulation on the GPU.  Prints every step's spikes as JSON like the reference.
+// A population fed from the host (what the reference's samples/external_input.cpp demonstrates): the neuron type has a
+// per-population update(dt, rng, out) instead of a per-neuron one, the runtime calls it on the host once per step and
+// uploads the ids it returns into the population's spike ring on the GPU (spice_add_host_population).  Here the
+// "sensor" replays a fixed four-step train over nine channels, twenty steps long; stdout is the reference's JSON.
+#include <array>
 #include <vector>
 
 #include "spice/snn.h"
 
 #include "spike_sink.h"
 
-using namespace spice;
-using namespace spice::util;
+static constexpr Int kChannels = 9;
+static constexpr Int kSteps    = 20;
 
-// the spike train (it could as well come from a file or an event camera)
-std::vector<Int32> spikes[] = {{4, 5, 8}, {5}, {7, 8}, {5, 7}};
+// the recorded train; a file reader or an event-camera driver would sit here instead
+static std::array<std::vector<Int32>, 4> const kTrain = {{{4, 5, 8}, {5}, {7, 8}, {5, 7}}};
 
-struct input {
-	Int i = 0;
+struct replay {
+	std::size_t at = 0; // position in the train
 
-	void update(float, auto, std::vector<Int32>& out_spikes) {
-		out_spikes.insert(out_spikes.end(), spikes[i].begin(), spikes[i].end());
-		i = (i + 1) % 4;
+	void update(float /*dt*/, auto /*rng*/, std::vector<Int32>& fired) {
+		auto const& now = kTrain[at];
+		fired.insert(fired.end(), now.begin(), now.end());
+		at = (at + 1) % kTrain.size();
 	}
 };
-static_assert(CheckNeuron<input>());
+static_assert(spice::CheckNeuron<replay>());
 
 int main() {
-	snn single_pop(1, 1, {1337});
-	auto I = single_pop.add_population<input>(9);
+	spice::snn net(1, 1, {1337});
+	auto* sensor = net.add_population<replay>(kChannels);
 
-	spike_output_stream s("external_input");
-	for (Int i : range(20)) {
-		single_pop.step();
-		s << I << '\n';
-		pause(0.1);
-		(void)i;
+	spike_output_stream json("external_input");
+	for (Int step = 0; step < kSteps; step++) {
+		net.step();
+		json << sensor << '\n';
 	}
 	return 0;
 }

@@ -1,53 +1,51 @@
-// Ping-pong (reference: samples/ping_pong.cpp): two populations that alternate exciting each other
-// through 1:1 adj_list connections; a per-neuron init hook, a one-byte neuron state, a synapse whose
-// deliver() is idempotent.  Prints every step's spikes as JSON like the reference.
+// Two populations that wake each other up in turn (what the reference's samples/ping_pong.cpp demonstrates): 1:1
+// adj_list connections in both directions, a per-neuron init hook that arms one side, a one-byte neuron state and a
+// stateless synapse whose deliver() is idempotent.  Ten steps; stdout is the reference's JSON.
 #include "spice/snn.h"
 
 #include "spike_sink.h"
 
-using namespace spice;
-using namespace spice::util;
+static constexpr Int kPairs = 5'000; // 10,000 neurons
+static constexpr Int kSteps = 10;
 
-struct neuron_desc {
-	bool initial_spike;
+// fires once whenever it has been armed
+struct relay {
+	bool starts_armed;
 
 	struct neuron {
-		bool should_i_spike;
+		bool armed;
 	};
 
-	SPICE_HD void init(neuron& n, Int, auto&) const { n.should_i_spike = initial_spike; }
+	SPICE_HD void init(neuron& n, Int /*id*/, auto& /*rng*/) const { n.armed = starts_armed; }
 
-	SPICE_HD bool update(neuron& n, float, auto&) const {
-		bool const result = n.should_i_spike;
-		n.should_i_spike  = false;
-		return result;
+	SPICE_HD bool update(neuron& n, float /*dt*/, auto& /*rng*/) const {
+		bool const fires = n.armed;
+		n.armed          = false;
+		return fires;
 	}
 };
-static_assert(CheckNeuron<neuron_desc>());
+static_assert(spice::CheckNeuron<relay>());
 
-struct synapse_desc {
-	SPICE_HD void deliver(neuron_desc::neuron& n) const { n.should_i_spike = true; }
+struct arm {
+	SPICE_HD void deliver(relay::neuron& target) const { target.armed = true; }
 };
-static_assert(CheckSynapse<synapse_desc>());
+static_assert(spice::CheckSynapse<arm>());
 
 int main() {
-	Int const N = 10'000;
+	spice::snn net(1, 1, {1337});
+	auto* ping = net.add_population<relay>(kPairs, {true});
+	auto* pong = net.add_population<relay>(kPairs, {false});
 
-	snn ping_pong(1, 1, {1337});
-	auto ping = ping_pong.add_population<neuron_desc>(N / 2, {true});
-	auto pong = ping_pong.add_population<neuron_desc>(N / 2, {false});
+	spice::adj_list one_to_one;
+	for (Int i = 0; i < kPairs; i++)
+		one_to_one.connect(i, i);
+	net.connect<arm>(ping, pong, one_to_one, 1);
+	net.connect<arm>(pong, ping, one_to_one, 1);
 
-	adj_list adj;
-	for (Int i : range(N / 2))
-		adj.connect(i, i);
-	ping_pong.connect<synapse_desc>(ping, pong, adj, 1);
-	ping_pong.connect<synapse_desc>(pong, ping, adj, 1);
-
-	spike_output_stream s("ping-pong");
-	for (Int i : range(10)) {
-		ping_pong.step();
-		s << ping << pong << '\n';
-		(void)i;
+	spike_output_stream json("ping-pong");
+	for (Int step = 0; step < kSteps; step++) {
+		net.step();
+		json << ping << pong << '\n';
 	}
 	return 0;
 }

@@ -1,89 +1,94 @@
-// Single-source shortest paths (reference: samples/sssp.cpp): vertices are neurons that fire when
-// they have found a shorter path, edges are stateful, non-plastic synapses whose deliver() reads the
-// SOURCE neuron (DeliverFromTo) and whose weight comes from a per-synapse init hook; the vertices are
-// set up by a per-population init hook.  Self-checking like the reference (distances of vertices 0
-// and 4), and prints every vertex's distance.
+// Single-source shortest paths as a spiking network (what the reference's samples/sssp.cpp demonstrates): a vertex is
+// a neuron that fires in the step after its distance improved; an edge is a stateful, non-plastic synapse whose
+// deliver() reads the SOURCE neuron (DeliverFromTo) and relaxes the target; edge weights are set by a per-synapse init
+// hook, the source vertex by a per-population init hook.  After |V| - 1 steps every distance is final.  Prints the
+// distances and checks the two the reference's sample asserts.
 #include <cstdio>
 #include <limits>
+#include <span>
 
 #include "spice/snn.h"
 
-using namespace spice;
-using namespace spice::util;
+//        w3      w3
+//     1 ----> 2 ----> 3
+//  w1 ^                \ w1
+//     0                 v
+//  w1 v                 4
+//     5 ------------> 6 ^ w1
+//            w5
+struct weighted_edge {
+	Int from, to, weight;
+};
+static constexpr weighted_edge kGraph[] = {{0, 1, 1}, {0, 5, 1}, {1, 2, 3}, {2, 3, 3}, {3, 4, 1}, {5, 6, 5}, {6, 4, 1}};
+static constexpr Int kVertices   = 7;
 
-//      3 2 3
-//   1.---*---.3
-//  1/         \1
-// 0*           *4
-//  1\         /1
-//    *-------*
-//    5   5   6
-static Int adj_matrix[7][7] = {{0, 1, 0, 0, 0, 1, 0}, {0, 0, 3, 0, 0, 0, 0}, {0, 0, 0, 3, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0},
-                               {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 5}, {0, 0, 0, 0, 1, 0, 0}};
+static Int weight_of(Int const from, Int const to) {
+	for (auto const& e : kGraph)
+		if (e.from == from && e.to == to)
+			return e.weight;
+	return 0;
+}
 
 struct vertex {
-	Int src; // the source vertex
+	Int source;
 
 	struct neuron {
-		Int distance           = std::numeric_limits<Int>::max();
-		neuron const* previous = nullptr;
-		bool fire              = false;
+		Int dist   = std::numeric_limits<Int>::max();
+		neuron const* via = nullptr; // the neighbour the best path arrives through
+		bool improved     = false;
 	};
 
-	// per-population init (runs on the host)
-	void init(std::span<neuron> neurons, auto&) {
-		neurons[src].distance = 0;
-		neurons[src].previous = &neurons[src];
-		neurons[src].fire     = true;
+	// per-population init hook (host): distance 0 at the source, which announces itself in the first step
+	void init(std::span<neuron> all, auto& /*rng*/) {
+		neuron& s  = all[static_cast<std::size_t>(source)];
+		s.dist     = 0;
+		s.via      = &s;
+		s.improved = true;
 	}
 
-	SPICE_HD bool update(neuron& n, float, auto&) const {
-		bool const result = n.fire;
-		n.fire            = false;
-		return result;
+	SPICE_HD bool update(neuron& v, float /*dt*/, auto& /*rng*/) const {
+		bool const announce = v.improved;
+		v.improved          = false;
+		return announce;
 	}
 };
-static_assert(CheckNeuron<vertex>());
+static_assert(spice::CheckNeuron<vertex>());
 
-struct edge {
+struct relax {
 	struct synapse {
 		Int weight;
 	};
 
-	// per-synapse init (runs on the host)
-	void init(synapse& syn, Int src, Int dst, auto&) const { syn.weight = adj_matrix[src][dst]; }
+	// per-synapse init hook (host)
+	void init(synapse& s, Int const from, Int const to, auto& /*rng*/) const { s.weight = weight_of(from, to); }
 
-	SPICE_HD void deliver(synapse const& syn, vertex::neuron const& src, vertex::neuron& dst) const {
-		if (src.distance + syn.weight < dst.distance) {
-			dst.distance = src.distance + syn.weight;
-			dst.previous = &src;
-			dst.fire     = true;
+	SPICE_HD void deliver(synapse const& s, vertex::neuron const& from, vertex::neuron& to) const {
+		Int const through = from.dist + s.weight;
+		if (through < to.dist) {
+			to.dist     = through;
+			to.via      = &from;
+			to.improved = true;
 		}
 	}
 };
-static_assert(CheckSynapse<edge>());
+static_assert(spice::CheckSynapse<relax>());
 
 int main() {
-	snn sssp(1, 1, {1337});
-	auto vertices = sssp.add_population<vertex>(7, {0});
+	spice::snn net(1, 1, {1337});
+	auto* vertices = net.add_population<vertex>(kVertices, {0});
 
-	adj_list adj;
-	for (Int src : range(7))
-		for (Int dst : range(7))
-			if (adj_matrix[src][dst])
-				adj.connect(src, dst);
+	spice::adj_list edges;
+	for (auto const& e : kGraph)
+		edges.connect(e.from, e.to);
+	net.connect<relax>(vertices, vertices, edges, 1);
 
-	sssp.connect<edge>(vertices, vertices, adj, 1);
+	for (Int step = 0; step + 1 < vertices->size(); step++)
+		net.step();
 
-	for (Int i : range(vertices->size() - 1)) {
-		sssp.step();
-		(void)i;
-	}
-
-	auto const result = vertices->get_neurons();
-	for (Int v : range(7))
-		std::printf("%lld%s", static_cast<long long>(result[v].distance), v == 6 ? "\n" : " ");
-	SPICE_ASSERT(result[0].distance == 0);
-	SPICE_ASSERT(result[4].distance == 7);
+	auto const found = vertices->get_neurons();
+	for (Int v = 0; v < kVertices; v++)
+		std::printf("%lld%s", static_cast<long long>(found[static_cast<std::size_t>(v)].dist), v + 1 == kVertices ? "\n" : " ");
+	SPICE_ASSERT(found[0].dist == 0);
+	SPICE_ASSERT(found[4].dist == 7);
 	return 0;
 }
