@@ -34,7 +34,10 @@
 //     tile's counters to counts[slot(step + delay)][tile] with plain vector accesses: it is the
 //     only writer of that range, and the target's update kernel (the only reader) runs in a
 //     later window.  Units are handed out by a global counter to a persistent grid, heaviest
-//     connections first.
+//     connections first;
+//   * windows with few, long units (a rank of a multi-GPU run) are handed out round by round
+//     instead (deliver_plan.h, plan_items, deliver_tiles<true>): round 0 of a unit stores and
+//     publishes a flag, the later rounds wait for it and add with global reductions.
 #include <cuda_runtime.h>
 
 #include <algorithm>

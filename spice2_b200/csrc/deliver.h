@@ -73,10 +73,9 @@ int pack_runs(void* stream, std::int32_t const* neighbors, long long const* tile
 int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets, long long src_count,
                 int tile, int tiles, int cap, std::int32_t* out);
 
-// One launch delivers every spike of the window on every connection.  `blocks` <= 0 picks a
-// persistent grid filling the device.  Windows with few units per CTA are launched split (plan_items +
-// deliver_tiles<true>, deliver.cu); `launches` receives the number of kernels launched.  Returns a
-// cudaError_t as int.
+// Delivers every spike of the window on every connection with a persistent grid filling the device.  Windows
+// with few units per CTA are launched split (plan_items + deliver_tiles<true>, deliver.cu); `launches` receives the
+// number of kernels launched.  Returns a cudaError_t as int.
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches = nullptr);
 
 // Loads the delivery kernels (a lazily loaded kernel can synchronise the context at its first launch).
