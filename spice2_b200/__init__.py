@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
             "spice_ctx_destroy": (i32, [vp]),
             "spice_last_error": (C.c_char_p, [vp]),
             "spice_ctx_set_stream": (i32, [vp, vp]),
+            "spice_ctx_seed": (i32, [vp, C.POINTER(C.c_uint64)]),
             "spice_add_population": (i32, [vp, vp, i64, vp, C.POINTER(i32)]),
             "spice_add_host_population": (i32, [vp, i64, vp, vp, C.POINTER(i32)]),
             "spice_population_size": (i64, [vp, i32]),
@@ -327,6 +328,12 @@ class snn:
         ids = np.empty(max(nids.value, 1), np.int32)
         self._check(lib().spice_raster_read(self._h, n.value, _ptr(counts), _ptr(ids)))
         return counts, ids[: nids.value]
+
+    def seed(self):
+        """snn::_seed (snn.h:69): (lo, hi) of the seed the next `seed++` hands out."""
+        out = (C.c_uint64 * 2)()
+        self._check(lib().spice_ctx_seed(self._h, out))
+        return int(out[0]), int(out[1])
 
     def stats(self):
         ev, sp, kl = C.c_int64(), C.c_int64(), C.c_int64()

@@ -127,6 +127,18 @@ def test_synaptic_event_count(sp, orc):
     assert net.stats()["synaptic_events"] == onet.events()
 
 
+def test_seed_bookkeeping(sp, golden):
+    """snn.h:21-56: a stateful population consumes one seed++, a stateless one none, every connection
+    one; a step consumes one more (snn.cpp:12).  Brunel: 2 + 6 increments before the first step."""
+    from spice2_b200.samples import brunel
+
+    net, _ = brunel(N=3000)
+    assert [hx(x) for x in net.seed()] == golden["seed_1337"]["8"]
+    net.step(15)
+    net.sync()
+    assert list(net.seed()) == list(sp.seed_seq([1337], 8 + 15))
+
+
 def test_preconditions(sp):
     net = sp.snn(1e-4, 15e-4)
     a = net.add_population("brunel.poisson", 10)
