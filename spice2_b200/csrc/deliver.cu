@@ -426,8 +426,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_a
 //   dump:    2 cap + 4 bank + byte   (never read back)
 // Two targets that share a bank in A never share one in B (for tiles of <= 32 rows), which is what
 // makes the 2-choice balancing effective.
-__host__ __device__ __forceinline__ int rot_fwd(int t) { return (t & ~0x7c) | ((t + ((t >> 7) << 2)) & 0x7c); }
-__host__ __device__ __forceinline__ int rot_inv(int u) { return (u & ~0x7c) | ((u - ((u >> 7) << 2)) & 0x7c); }
+// rot_fwd / rot_inv: deliver_plan.h
 
 // groups of every run: run_ptr[id] = ceil(len / 4) (scanned afterwards); id = row * tiles + k
 __global__ void __launch_bounds__(256) run_groups_kernel(long long const* tile_ptr, long long n_runs, int tiles, unsigned* run_ptr) {

@@ -277,3 +277,42 @@ int main() {
     subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_counter_address_rotation(tmp_path):
+    """csrc/deliver_plan.h rot_fwd / rot_inv (the address of a target's second u8 counter in the delivery stream):
+    a bijection on every 128-byte row of a tile, and two targets in the same bank of array A never share a bank of
+    array B (tiles of <= 32 rows = 4096 targets; the 5120-target maximum wraps only for rows 32..39)."""
+    src = tmp_path / "rot.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <set>
+#include "deliver_plan.h"
+using namespace spice::deliver;
+#define CHECK(c) do { if (!(c)) { std::printf("line %d: %s (t %d)\n", __LINE__, #c, t); return 1; } } while (0)
+int main() {
+	int const cap = 5120;
+	std::set<int> seen;
+	for (int t = 0; t < cap; t++) {
+		int const u = rot_fwd(t);
+		CHECK(u >= 0 && u < cap);
+		CHECK((u >> 7) == (t >> 7));  // stays in its 128-byte row
+		CHECK((u & 3) == (t & 3));    // and in its byte of the word
+		CHECK(rot_inv(u) == t);
+		CHECK(seen.insert(u).second);
+		CHECK((((u >> 2) & 31) == (((t >> 2) + (t >> 7)) & 31))); // bank of B = bank of A + row
+	}
+	for (int t = 0; t < 4096; t++)
+		for (int s = t + 128; s < 4096; s += 128) { // same bank and byte in A, another row
+			int const bt = (rot_fwd(t) >> 2) & 31, bs = (rot_fwd(s) >> 2) & 31;
+			if (bt == bs) { std::printf("targets %d and %d share bank %d in both arrays\n", t, s, bt); return 1; }
+		}
+	std::puts("ok");
+	return 0;
+}
+''')
+    exe = tmp_path / "rot"
+    inc = ROOT / "spice2_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
