@@ -204,6 +204,9 @@ SPICE_API int spice_adjacency_destroy(spice_adjacency* a);
 SPICE_API int spice_ctx_seed(spice_ctx const* ctx, uint64_t out[2]);
 SPICE_API void spice_seed_seq(uint32_t const* words, int n, uint64_t out[2]);
 SPICE_API void spice_seed_next(uint64_t seed[2]);
+/* FNV-1a (64 bit) over host bytes: the digest of the adjacency golden vectors (tests/golden/golden.json;
+ * the reference's own bench/connectivity.cpp has no checksum -- this is the harness's). */
+SPICE_API uint64_t spice_fnv1a64(void const* data, int64_t bytes);
 
 /* ---- model tables of the built-in sample models ---------------------------------------------
  * names: "brunel.poisson", "brunel.lif", "vogels.lif"    (samples/brunel.cpp:23-62, vogels.cpp:10-47)

@@ -18,7 +18,7 @@ import numpy as np
 
 from .build import build as _build
 
-__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "seed_seq",
+__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "seed_seq", "fnv1a64",
            "MODE_DETERMINISTIC", "MODE_FAST"]
 
 MODE_DETERMINISTIC, MODE_FAST = 0, 1
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
             "spice_builtin_synapse": (vp, [C.c_char_p]),
             "spice_selftest_libm": (i32, [i32, i32, vp, vp, vp, i64]),
             "spice_device_check": (i32, [i32]),
+            "spice_fnv1a64": (C.c_uint64, [vp, i64]),
             "spice_version": (C.c_char_p, []),
         }
         for name, (res, args) in sig.items():
@@ -362,6 +363,12 @@ class snn:
     def set_peers(self, handles: list[bytes]):
         blob = b"".join(handles)
         self._check(lib().spice_ctx_set_peers(self._h, blob, len(handles[0])))
+
+
+def fnv1a64(a) -> str:
+    """FNV-1a (64 bit) of an array's bytes as 16 hex digits — the digest the golden fixtures use."""
+    a = np.ascontiguousarray(a)
+    return f"{int(lib().spice_fnv1a64(_ptr(a), a.nbytes)):016x}"
 
 
 def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True):

@@ -591,7 +591,13 @@ int finalize(spice_ctx* ctx) {
 			ctx->window       = 1;
 			ctx->any_stateful = true;
 		}
-	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay, 2ll * ctx->window));
+	// Spike ring: a slot is read until max_delay - 1 steps after it was written (stateful delivery of a
+	// connection with delay == max_delay, spikes(max_delay - 1)), and the delivery of a window reads the
+	// slots that window's updates wrote.  With several ranks a peer that has passed wait_window(w) already
+	// stores the spikes of window w + 1 into this rank's ring while this rank may still be reading, so the
+	// ring keeps one whole window of slack behind the oldest slot anyone reads: peers are never more than
+	// one window ahead (they cannot pass wait_window(w + 1) before this rank has published w + 1).
+	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay + (ctx->world > 1 ? ctx->window : 0), 2ll * ctx->window));
 	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
 	for (auto& p : ctx->pops)
 		if (p.host_update) {
@@ -2098,6 +2104,14 @@ int spice_ctx_seed(spice_ctx const* ctx, uint64_t out[2]) {
 	out[0] = ctx->seed.seed().lo;
 	out[1] = ctx->seed.seed().hi;
 	return SPICE_OK;
+}
+
+uint64_t spice_fnv1a64(void const* data, int64_t bytes) {
+	auto const* b = static_cast<unsigned char const*>(data);
+	uint64_t h    = 0xcbf29ce484222325ull;
+	for (int64_t i = 0; i < bytes; i++)
+		h = (h ^ b[i]) * 0x100000001b3ull;
+	return h;
 }
 
 void spice_seed_seq(uint32_t const* words, int n, uint64_t out[2]) {

@@ -9,8 +9,8 @@
 // counter addresses arranged so that the 32 lanes of one counting instruction hit 32 different banks (what pack_runs
 // produces), and both count them into a warp-private 2 x 5 KB tile like unit_walker does.
 //
-// STATUS: written at the end of round 1, after the GPU budget was spent: it compiles for sm_100a and has NOT been run.
-// Round 2 starts by running it:  nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/bulk_run_bench.cu -o
+// Variants C / D (round 2) put the same two questions to CTA-shared u32 counters bumped with red.shared.add.
+// Results: profiles/microbench_r02_bulk_runs.txt.  Build and run:  nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/bulk_run_bench.cu -o
 // tools/build/bulk_run_bench && tools/build/bulk_run_bench [GiB]
 #include <cuda_runtime.h>
 
@@ -160,6 +160,98 @@ __global__ void __launch_bounds__(128) count_bulk(int4 const* buf, unsigned long
 	if (sum == 0x12345678u) out[0] = sum;
 }
 
+// ---- variants C / D: CTA-shared u32 counters bumped with red.shared.add (no read-modify-write chain, no __syncwarp
+// between runs, no u8 limit); C lands the runs in registers, D in shared memory with bulk copies -------------------------
+// group i of the u32 stream: element e is the BYTE address of a u32 counter whose word index is congruent to the lane
+__global__ void fill_u32(int4* buf, unsigned long long ngroups) {
+	unsigned long long const i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= ngroups) return;
+	int const lane = static_cast<int>(i & 31);
+	unsigned long long const h = mix(i);
+	int const rows = 2 * kCap / 32;
+	buf[i] = make_int4((static_cast<int>(h % rows) * 32 + lane) * 4, (static_cast<int>((h >> 16) % rows) * 32 + lane) * 4,
+	                   (static_cast<int>((h >> 32) % rows) * 32 + lane) * 4, (static_cast<int>((h >> 48) % rows) * 32 + lane) * 4);
+}
+__device__ __forceinline__ void reds(unsigned base, int4 v) {
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v.x) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v.y) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v.z) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v.w) : "memory");
+}
+constexpr int kCntBytes32 = 2 * kCap * 4;
+
+template <int FLIGHT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) reds_registers(int4 const* buf, unsigned long long ngroups, int groups, int runs_per_warp, unsigned* out) {
+	extern __shared__ uint4 smem4[];
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < kCntBytes32 / 16; i += WARPS * 32) smem4[i] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+	unsigned const base = smem_u32(smem4);
+	unsigned long long r = (static_cast<unsigned long long>(blockIdx.x) * WARPS + warp) * 0x9e3779b97f4a7c15ull;
+	int4 v[FLIGHT];
+#pragma unroll
+	for (int j = 0; j < FLIGHT; j++) {
+		v[j] = make_int4(-1, 0, 0, 0);
+		if (lane < groups) v[j] = ldg_stream(buf + run_at(r++, ngroups) + lane);
+	}
+	for (int i = 0; i < runs_per_warp; i += FLIGHT) {
+#pragma unroll
+		for (int j = 0; j < FLIGHT; j++) {
+			if (v[j].x >= 0) reds(base, v[j]);
+			v[j] = make_int4(-1, 0, 0, 0);
+			if (lane < groups) v[j] = ldg_stream(buf + run_at(r++, ngroups) + lane);
+		}
+	}
+	__syncthreads();
+	unsigned s = 0;
+	for (int i = threadIdx.x; i < kCntBytes32 / 4; i += WARPS * 32) s += reinterpret_cast<unsigned const*>(smem4)[i];
+	if (s == 0x12345678u) out[0] = s;
+}
+
+template <int RUNS, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) reds_bulk(int4 const* buf, unsigned long long ngroups, int groups, int runs_per_warp, unsigned* out) {
+	extern __shared__ uint4 smem4[];
+	constexpr int kStageBytes = RUNS * 512;
+	__shared__ unsigned long long bars[WARPS][STAGES];
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned char* stage = reinterpret_cast<unsigned char*>(smem4) + kCntBytes32 + warp * STAGES * kStageBytes;
+	for (int i = threadIdx.x; i < kCntBytes32 / 16; i += WARPS * 32) smem4[i] = make_uint4(0, 0, 0, 0);
+	if (lane < STAGES) mbar_init(&bars[warp][lane], 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncthreads();
+	unsigned const base = smem_u32(smem4);
+	unsigned long long r = (static_cast<unsigned long long>(blockIdx.x) * WARPS + warp) * 0x9e3779b97f4a7c15ull;
+	unsigned const bytes = static_cast<unsigned>(groups) * 16;
+	auto fetch = [&](int s) {
+		if (lane == 0) mbar_expect_tx(&bars[warp][s], bytes * RUNS);
+		__syncwarp();
+		if (lane < RUNS) bulk_g2s(stage + s * kStageBytes + lane * 512, buf + run_at(r + lane, ngroups), bytes, &bars[warp][s]);
+		r += RUNS;
+	};
+#pragma unroll
+	for (int s = 0; s < STAGES; s++) fetch(s);
+	int const nstage = runs_per_warp / RUNS;
+	for (int it = 0; it < nstage; it++) {
+		int const s = it % STAGES;
+		mbar_wait(&bars[warp][s], (it / STAGES) & 1);
+		int4 v[RUNS];
+#pragma unroll
+		for (int j = 0; j < RUNS; j++) {
+			v[j] = make_int4(-1, 0, 0, 0);
+			if (lane < groups) v[j] = *reinterpret_cast<int4 const*>(stage + s * kStageBytes + j * 512 + lane * 16);
+		}
+#pragma unroll
+		for (int j = 0; j < RUNS; j++)
+			if (v[j].x >= 0) reds(base, v[j]);
+		__syncwarp(); // every lane has read the stage's slots
+		if (it + STAGES < nstage) fetch(s);
+	}
+	__syncthreads();
+	unsigned s = 0;
+	for (int i = threadIdx.x; i < kCntBytes32 / 4; i += WARPS * 32) s += reinterpret_cast<unsigned const*>(smem4)[i];
+	if (s == 0x12345678u) out[0] = s;
+}
+
 template <class K>
 float time_kernel(K launch) {
 	cudaEvent_t e0, e1;
@@ -209,5 +301,43 @@ int main(int argc, char** argv) {
 	bulk(count_bulk<8, 4>, "bulk copies, 4 stages x 8 runs", 8, 4);
 	bulk(count_bulk<16, 2>, "bulk copies, 2 stages x 16 runs", 16, 2);
 	bulk(count_bulk<16, 3>, "bulk copies, 3 stages x 16 runs", 16, 3);
+
+	// CTA-shared u32 counters + red.shared
+	fill_u32<<<static_cast<unsigned>((ngroups + 255) / 256), 256>>>(buf, ngroups);
+	CK(cudaDeviceSynchronize());
+	auto report_w = [&](char const* name, int warps, int ctas_per_sm, size_t smem, float ms) {
+		double const gb = static_cast<double>(sms) * ctas_per_sm * warps * runs * groups * 16 / 1e9;
+		printf("%-52s %2d warps x %2d CTAs/SM %6zu B smem/CTA %8.3f ms %8.1f GB/s\n", name, warps, ctas_per_sm, smem, ms, gb / (ms * 1e-3));
+	};
+	auto reds_reg = [&](auto kernel, char const* name, int warps) {
+		size_t const smem = kCntBytes32;
+		CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		int occ = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, warps * 32, smem));
+		for (int c = occ; c >= 1 && c >= occ - 1; c--)
+			report_w(name, warps, c, smem, time_kernel([&] { kernel<<<sms * c, warps * 32, smem>>>(buf, ngroups, groups, runs, out); }));
+	};
+	reds_reg(reds_registers<16, 4>, "red.shared, registers, 16 in flight", 4);
+	reds_reg(reds_registers<16, 8>, "red.shared, registers, 16 in flight", 8);
+	reds_reg(reds_registers<8, 8>, "red.shared, registers, 8 in flight", 8);
+	reds_reg(reds_registers<8, 16>, "red.shared, registers, 8 in flight", 16);
+	auto reds_blk = [&](auto kernel, char const* name, int warps, int runs_per_stage, int stages) {
+		size_t const smem = kCntBytes32 + static_cast<size_t>(warps) * stages * runs_per_stage * 512;
+		if (smem > 227 * 1024) return;
+		CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		int occ = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, warps * 32, smem));
+		for (int c = occ; c >= 1 && c >= occ - 1; c--)
+			report_w(name, warps, c, smem, time_kernel([&] { kernel<<<sms * c, warps * 32, smem>>>(buf, ngroups, groups, runs, out); }));
+	};
+	reds_blk(reds_bulk<8, 2, 4>, "red.shared, bulk, 2 stages x 8 runs", 4, 8, 2);
+	reds_blk(reds_bulk<8, 3, 4>, "red.shared, bulk, 3 stages x 8 runs", 4, 8, 3);
+	reds_blk(reds_bulk<8, 2, 8>, "red.shared, bulk, 2 stages x 8 runs", 8, 8, 2);
+	reds_blk(reds_bulk<8, 3, 8>, "red.shared, bulk, 3 stages x 8 runs", 8, 8, 3);
+	reds_blk(reds_bulk<8, 4, 8>, "red.shared, bulk, 4 stages x 8 runs", 8, 8, 4);
+	reds_blk(reds_bulk<16, 2, 8>, "red.shared, bulk, 2 stages x 16 runs", 8, 16, 2);
+	reds_blk(reds_bulk<8, 2, 16>, "red.shared, bulk, 2 stages x 8 runs", 16, 8, 2);
+	reds_blk(reds_bulk<8, 3, 16>, "red.shared, bulk, 3 stages x 8 runs", 16, 8, 3);
+	reds_blk(reds_bulk<4, 4, 16>, "red.shared, bulk, 4 stages x 4 runs", 16, 4, 4);
 	return 0;
 }
