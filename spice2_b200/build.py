@@ -41,6 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     digest = _digest()
     if not force and OUT.exists() and stamp.exists() and stamp.read_text() == digest:
         return OUT
+    if not force and OUT.exists() and os.environ.get("SPICE_PREBUILT") == "1":
+        return OUT  # the library that travelled with the snapshot, whatever the sources say (gpurun calls)
     if not Path(NVCC).exists():
         if OUT.exists():
             return OUT  # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot

@@ -3,47 +3,42 @@
 // for all connections whose events are integer counts (every stateless synapse), one launch per
 // window of steps.
 //
-// Why not one atomic per event: a B200 SM retires global reductions at ~1.3 cycles per lane and
-// shared-memory atomics at ~2 cycles per lane, i.e. <= 2e11 events/s for the whole GPU, an
-// eighth of what HBM can stream (4 B of CSR per event).  The rows of a connection are strictly
-// ascending target lists, so the entries of ONE row never collide with each other: a warp that
-// works on one row at a time can bump its counters with plain shared-memory load/add/store.
+// Why not one global atomic per event: a B200 SM retires global reductions at ~1.3 cycles per lane,
+// i.e. <= 2e11 events/s for the whole GPU, an eighth of what HBM can stream (4 B of CSR per event).
+// Shared-memory reductions are another matter: a warp-wide red.shared.add.u32 whose 32 lanes fall
+// into 32 different banks retires in ~1 SM cycle (tools/smem_rmw_bench.cu), 32 events per cycle and
+// SM, far above what HBM can feed.
 //
 // Layout of the work:
-//   * the targets of a connection are cut into tiles of <= 5120 neurons; tile_ptr[src][k] says
-//     where tile k's share of row src starts (built once per connection), so a tile's share of
-//     a row is one contiguous run of ~p * tile entries;
-//   * a unit = (connection, step of the window, tile).  A CTA of 4 warps owns a unit.  Every
-//     warp keeps its own counters for the tile in 10 KB of shared memory and takes every 4th
-//     batch of 32 spikes of the step's spike list; it streams each spiking source's run with
-//     one 16-byte load per lane (16 runs in flight, in registers) and counts with non-atomic
-//     shared-memory read-modify-writes — inside a warp no barrier and no atomic;
-//   * bank conflicts.  A counting instruction scatters 32 lanes over the tile; at random that
-//     costs ~3.1 shared-memory wavefronts per instruction instead of 1 and made the first
-//     version of this kernel LSU-bound at 39 % of the HBM roofline.  So every target has TWO
-//     u8 counters (arrays A and B, whose bank assignments differ by a per-row rotation), and
-//     once per connection pack_runs() rewrites each run into the kernel's own stream format:
-//     every entry becomes the byte address of one of its target's two counters, chosen
-//     (2-choice balancing) and ordered so that the lanes of one instruction fall into
-//     different banks; a run is padded to whole 16-byte groups with addresses of a 128-byte
-//     dump area (in banks the instruction does not use), so the counting code needs no length,
-//     no alignment and no per-entry predicate: a lane either holds a whole group or nothing.
-//     The canonical ascending CSR row is recovered by decoding and sorting (unpack_rows);
-//   * a u8 counter holds 255: a warp counts at most 224 runs (7 batches) per round; after each
-//     round the CTA adds its 4 x 2 arrays and stores (first round) or adds (later rounds) the
-//     tile's counters to counts[slot(step + delay)][tile] with plain vector accesses: it is the
-//     only writer of that range, and the target's update kernel (the only reader) runs in a
-//     later window.  Units are handed out by a global counter to a persistent grid, heaviest
-//     connections first;
-//   * windows with few, long units (a rank of a multi-GPU run) are handed out round by round
-//     instead (deliver_plan.h, plan_items, deliver_tiles<true>): round 0 of a unit stores and
-//     publishes a flag, the later rounds wait for it and add with global reductions.
+//   * the targets of a connection are cut into tiles of <= 5120 neurons; a tile's share of a row
+//     is one contiguous RUN of ~p * tile entries (sized for ~100: one 16-byte group per lane);
+//   * a unit = (connection, step of the window, tile).  A CTA owns a unit at a time and keeps the
+//     tile's event counters in shared memory: TWO u32 counters per target (arrays A and B whose
+//     bank assignments differ by a per-row rotation, deliver_plan.h).  Once per connection
+//     pack_runs() rewrites every run into the kernel's own stream format: each entry becomes the
+//     byte offset of one of its target's two counters, chosen (2-choice balancing) and ordered so
+//     that the lanes of one counting instruction fall into 32 different banks, the run padded to
+//     whole 16-byte groups with offsets of a dump area.  The counting code therefore needs no
+//     length, no alignment and no per-entry predicate: a lane holds a whole group or nothing;
+//   * the warps of the CTA split the step's spike list in batches of 32 spikes (one run per lane).
+//     A warp fetches its runs with cp.async.bulk (1-D TMA), one copy per run issued by the run's
+//     lane, eight runs to a stage whose mbarrier collects the bytes; the landed groups are read
+//     back with LDS.128 and counted with four red.shared.add per lane.  Nothing sits on the
+//     register scoreboards while it is in flight, and the reductions return nothing, so a warp's
+//     instruction stream never waits for its own counting;
+//   * everything a warp fetches is a few batches ahead of what it counts — spike ids, then run
+//     pointers, then the runs — ACROSS unit boundaries: a CTA's next units are known in advance
+//     (deliver_plan.h: its first units are fixed by its index, later ones are claimed from a
+//     global counter four units ahead), so the pipeline stays full while the CTA merges a unit;
+//   * at the end of a unit the CTA adds A + B per target, stores the tile's range of
+//     counts[slot(step + delay)] with 16-byte stores and zeroes the counters on the way: it is the
+//     only writer of that range, and the target's update kernel (the only reader) runs in a later
+//     window, so nobody zeroes anything in global memory.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdlib>
 
-#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "deliver.h"
@@ -52,381 +47,370 @@
 namespace spice::deliver {
 namespace {
 
-constexpr int kWarps       = 4;  // warps per CTA: they share a unit, each with its own copy of the tile
-constexpr int kCtasPerSm   = 5;  // register budget: 20 warps per SM
-constexpr int kRing        = 16; // runs in flight per warp (16 bytes per lane and run, in registers)
-constexpr int kRoundBatches = 7; // batches of 32 runs a warp counts between two merges (224 <= 255: u8 counters)
+constexpr int kRuns        = 8;   // runs per pipeline stage
+constexpr int kSlotBytes   = 512; // landing slot of one run: the first 32 groups (longer runs: see count_stage)
+constexpr int kStageBytes  = kRuns * kSlotBytes;
+constexpr int kQuarters    = 32 / kRuns; // stages per batch of 32 runs
+constexpr int kLookahead   = kStaticUnits - 1; // units beyond the one being counted whose tickets a warp may read
 constexpr unsigned kFull   = 0xffffffffu;
 
-// count the 4 entries of `v` (counter addresses of 4 distinct targets, so the loads may all
-// precede the stores); a lane without a group holds v.x < 0
-__device__ __forceinline__ void tally(unsigned char* cnt, int4 v) {
-	if (v.x >= 0) {
-		unsigned char const c0 = cnt[v.x], c1 = cnt[v.y], c2 = cnt[v.z], c3 = cnt[v.w];
-		cnt[v.x] = c0 + 1;
-		cnt[v.y] = c1 + 1;
-		cnt[v.z] = c2 + 1;
-		cnt[v.w] = c3 + 1;
-	}
+__device__ __forceinline__ unsigned smem_u32(void const* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-
-// zero counters [0, bytes) of array A and of array B (bytes a multiple of 128)
-__device__ __forceinline__ void zero_tile(unsigned char* cnt, int cap, int bytes, int lane) {
-	uint4* a4 = reinterpret_cast<uint4*>(cnt);
-	uint4* b4 = reinterpret_cast<uint4*>(cnt + cap);
-	for (int i = lane; i < bytes / 16; i += 32) {
-		a4[i] = make_uint4(0, 0, 0, 0);
-		b4[i] = make_uint4(0, 0, 0, 0);
-	}
-	__syncwarp();
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(bar), "r"(parity)
+	    : "memory");
+}
+// 1-D bulk copy global -> shared, completion (bytes) on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, void const* src, unsigned bytes, unsigned bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+	             : "memory");
+}
+__device__ __forceinline__ int4 lds128(unsigned addr) {
+	int4 v;
+	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
 __device__ __forceinline__ int4 ldg_stream(void const* p) {
 	int4 v;
 	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
 	return v;
 }
-
-// groups [32, ng) of a long run; out of line: the pipeline's loop is unrolled 32 times and should stay small
-__device__ __noinline__ void tally_rest(unsigned char* cnt, int4 const* g, unsigned ng, int lane) {
-	__syncwarp();
-	for (unsigned off = 32; off < ng; off += 32) {
-		int4 w = make_int4(-1, 0, 0, 0);
-		if (off + lane < ng)
-			w = ldg_stream(g + off);
-		tally(cnt, w);
-	}
-	__syncwarp();
+// count the 4 entries of a group: byte offsets of 4 u32 counters
+__device__ __forceinline__ void tally(unsigned cnt, int4 v) {
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.x) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.y) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.z) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.w) : "memory");
 }
 
-// One run (a tile's share of one spiking source's row) as the pipeline sees it: groups
-// [g0, g0 + ng) of the connection's packed stream (a group = 16 bytes = 4 entries).
-struct alignas(8) run_desc {
-	unsigned g0, ng;
+// static shared state of a CTA
+template <int kW, int kStages>
+struct cta_state {
+	unsigned long long bars[kW][kStages];
+	unsigned tickets[kTicketRing];       // the CTA's unit sequence: tickets[seq % kTicketRing]
+	unsigned tot[kMaxConns * spice::detail::kMaxWindow]; // spikes of (connection, step)
+	int prefix[kMaxConns + 1];           // tile_prefix of the connections, + total_tiles
 };
 
-// shared memory of one warp: [descriptors: 2 batches x 32 x 8 B][counters: 2 arrays x tile_cap x 1 B][dump: 128 B]
-constexpr int kDescBytes = 2 * 32 * static_cast<int>(sizeof(run_desc));
-constexpr int kDumpBytes = 128;
-__host__ __device__ constexpr size_t warp_smem(int tile_cap) {
-	return static_cast<size_t>(kDescBytes) + 2 * static_cast<size_t>(tile_cap) + kDumpBytes;
-}
-
-// What a unit needs to know, worked out once per CTA.
-struct unit_info {
+// A unit as a warp needs it (warp-uniform)
+struct unit_view {
 	conn_desc const* C;
-	int lo, width;            // the tile's targets [lo, lo + width) (local indices)
-	std::uint32_t* out;       // counts[slot(step + delay)] + lo
-	std::int32_t const* ids0; // the step's slot of the source population's spike ring
-	unsigned const* gp;       // run_ptr + tile index: run of source i = groups [gp[i * tiles], gp[i * tiles + 1])
-	long long const* tile_ptr; // plain connections: tile_ptr + tile index, stride tiles + 1
-	int stride;               // tiles (packed) / tiles + 1 (plain)
-	unsigned total;           // spikes of the step (all ranks)
-	long long ring_slot;
-	// split launches (an item = one round of a unit):
-	unsigned b0, b1;          // the item's batches [b0, b1) of the step's spike list
-	unsigned round, rounds;   // which of the unit's rounds this is
-	unsigned* flag;           // set to the window's epoch once round 0 has stored the unit's counters
+	int s, k;
+	unsigned total;
+	bool valid;
 };
 
-// One warp's pipeline over its share of a unit: the batches b = first, first + step, ... of the
-// step's spike list (a batch = 32 consecutive spikes = 32 runs, padded with empty runs).
-// In flight at any time:
-//   * registers: the spike ids of the batch after next, the run pointers of the next batch;
-//   * shared memory: the descriptors of the current and the next batch;
-//   * registers: the entries of the next kRing runs on their way from HBM (one 16-byte load per
-//     lane and run), and the run being counted.
-// The loop over a half batch is fully unrolled, so the kRing landing slots are plain registers.
-// One call counts the batches of one round (at most kRoundBatches, so no u8 counter can wrap).
-struct unit_walker {
-	tiles_args const& a;
-	unit_info const& U;
-	unsigned char* smem; // this warp's
-	int lane;
-	unsigned char* cnt;
-	int4 const* stream;  // the connection's packed stream
-	unsigned p_g0, p_ng; // this lane's run of the batch whose descriptors are written next
-	std::int32_t id_next; // this lane's spike of the batch after that
-
-	__device__ __forceinline__ std::int32_t spike_id(unsigned q) const { return q < U.total ? U.ids0[q] : 0; } // source neuron (0 past the end)
-	__device__ __forceinline__ void load_ptrs(unsigned q, std::int32_t id) {
-		p_g0 = 0, p_ng = 0;
-		if (q < U.total) {
-			unsigned const* p = U.gp + static_cast<long long>(id) * U.stride;
-			p_g0              = p[0];
-			p_ng              = p[1] - p_g0;
-		}
-	}
-	// publish the descriptors of the i-th batch of this warp (from p_g0 / p_ng), then start
-	// fetching the pointers of batch `b_next` and the ids of batch `b_next + step`
-	__device__ __forceinline__ void write_desc(unsigned i, unsigned b_next, unsigned step) {
-		reinterpret_cast<run_desc*>(smem)[(i & 1) * 32 + lane] = run_desc{p_g0, p_ng};
-		unsigned const q = b_next * 32 + lane;
-		load_ptrs(q, id_next);
-		id_next = spike_id(q + step * 32);
-		__syncwarp();
-	}
-
-	// start fetching the run described by `d`; returns this lane's group of it (in flight)
-	__device__ __forceinline__ int4 issue(run_desc const* d) {
-		run_desc const r = *d;
-		int4 const* g    = stream + r.g0 + lane;
-		int4 v           = make_int4(-1, 0, 0, 0);
-		if (static_cast<unsigned>(lane) < r.ng)
-			v = ldg_stream(g);
-		if (r.ng > 32) // run longer than one warp-wide load (rare: tiles are sized for ~100 entries):
-			tally_rest(cnt, g, r.ng, lane); // count the rest right away, between two other runs' turns
-		return v;
-	}
-
-	// batches first, first + step, ... (< nbatch)
-	__device__ __forceinline__ void run(unsigned first, unsigned step, unsigned nbatch) {
-		cnt    = smem + kDescBytes;
-		stream = reinterpret_cast<int4 const*>(U.C->packed);
-
-		zero_tile(cnt, a.tile_cap, (U.width + 127) & ~127, lane);
-		unsigned const mine = first < nbatch ? (nbatch - first + step - 1) / step : 0; // batches of this warp
-		if (mine > 0) {
-			id_next = spike_id(first * 32 + lane);
-			load_ptrs(first * 32 + lane, id_next);
-			id_next = spike_id((first + step) * 32 + lane);
-
-			run_desc const* const desc = reinterpret_cast<run_desc const*>(smem);
-			write_desc(0, first + step, step);
-			int4 v[kRing];
-#pragma unroll
-			for (int j = 0; j < kRing; j++)
-				v[j] = issue(desc + j);
-			// half batch h: count runs [16h, 16h + 16) of this warp's sequence while fetching [16h + 16, 16h + 32)
-			for (unsigned h = 0; h < 2 * mine; h++) {
-				if (h & 1) {
-					unsigned const i = (h + 1) >> 1; // its descriptors come from batch first + i * step
-					write_desc(i, first + (i + 1) * step, step);
-				}
-				run_desc const* const id = desc + (((h + 1) >> 1) & 1) * 32 + ((h + 1) & 1) * 16;
-				bool const more          = h + 1 < 2 * mine;
-#pragma unroll
-				for (int j = 0; j < kRing; j++) {
-					tally(cnt, v[j]);
-					__syncwarp();
-					// nothing is fetched behind the call's last half batch: the descriptors there belong to the
-					// unit's next round (issue() would count the tails of its long runs into this one)
-					if (more)
-						v[j] = issue(id + j);
-				}
-			}
-		}
-	}
+// One batch of 32 runs, one run per lane
+struct batch {
+	unsigned long long addr; // global address of this lane's run (its first group)
+	unsigned ng;             // its groups (0: no run)
+	unsigned seq;            // the unit (CTA sequence number) it belongs to — warp-uniform
+	bool valid;              // warp-uniform
 };
 
 // Rare path, out of line: connections whose entries are plain columns (rows that may repeat a
 // target: adj_list multapses).  One global atomic per event into the tile's (zeroed) range.
-__device__ __noinline__ void walk_plain(tiles_args const& a, unit_info const& U, int lane, int warp) {
-	long long ev = 0;
-	for (unsigned j = warp; j < U.total; j += kWarps) {
-		long long const id  = U.ids0[j];
-		long long const* tp = U.tile_ptr + id * U.stride;
+template <int kW>
+__device__ __noinline__ unsigned long long walk_plain(conn_desc const& C, int k, std::int32_t const* ids0, unsigned total, std::uint32_t* out, int lo,
+                                                      int lane, int warp) {
+	unsigned long long ev = 0;
+	long long const* tp0 = C.tile_ptr + k;
+	int const stride     = C.tiles + 1;
+	for (unsigned j = warp; j < total; j += kW) {
+		long long const id  = ids0[j];
+		long long const* tp = tp0 + id * stride;
 		long long const beg = tp[0], end = tp[1];
 		for (long long e = beg + lane; e < end; e += 32)
-			atomicAdd(U.out + (U.C->neighbors[e] - U.lo), 1u);
-		ev += end - beg;
+			atomicAdd(out + (C.neighbors[e] - lo), 1u);
+		ev += lane == 0 ? static_cast<unsigned long long>(end - beg) : 0ull;
 	}
-	if (lane == 0 && ev)
-		atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
+	return ev;
 }
 
-constexpr unsigned kPerRound = kWarps * kRoundBatches; // batches a CTA counts between two merges
-
-__device__ __forceinline__ unsigned ld_acquire(unsigned const* p) {
-	unsigned v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Split launches: plan[c * nsteps + s] = first item of (connection c, step s), plan[nconns * nsteps] = items.
-// (connection, step) holds tiles x rounds items, a unit's rounds next to each other, round 0 first.
-__global__ void __launch_bounds__(256) plan_items(tiles_args a) {
-	using scan_t = cub::BlockScan<unsigned, 256>;
-	__shared__ typename scan_t::TempStorage tmp;
-	__shared__ unsigned running;
-	int const ncs = a.nconns * a.nsteps;
-	if (threadIdx.x == 0)
-		running = 0;
-	__syncthreads();
-	for (int base = 0; base < ncs; base += 256) {
-		int const j = base + threadIdx.x;
-		unsigned v  = 0;
-		if (j < ncs) {
-			conn_desc const& C = a.conns[j / a.nsteps];
-			long long const t  = a.t0 + j % a.nsteps;
-			v                  = static_cast<unsigned>(C.tiles) * rounds_of(C.arranged != 0, C.ring_cnt[(t % a.ring) * C.cnt_stride], a.round_batches);
-		}
-		unsigned ex, agg;
-		scan_t(tmp).ExclusiveSum(v, ex, agg);
-		unsigned const r0 = running;
-		if (j < ncs)
-			a.plan[j] = r0 + ex;
-		__syncthreads();
-		if (threadIdx.x == 0)
-			running = r0 + agg;
-		__syncthreads();
-	}
-	if (threadIdx.x == 0)
-		a.plan[ncs] = running;
-}
-
-// kSplit = false: a CTA claims whole units and loops over their rounds.
-// kSplit = true:  a CTA claims single rounds (plan_items); round 0 of a unit stores the counters and
-//                 publishes the unit's flag, later rounds wait for the flag and add with atomics.  The
-//                 wait cannot deadlock: round 0 has a lower ticket, so a running CTA holds it, and
-//                 round 0 never waits.  For windows with few, long units (a rank of a multi-GPU run).
-template <bool kSplit>
-__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm) deliver_tiles(tiles_args a) {
+template <int kW, int kStages>
+__global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_args a) {
 	extern __shared__ uint4 smem4[];
-	__shared__ unit_info U;
-	__shared__ unsigned claimed;
-	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	size_t const wbytes  = warp_smem(a.tile_cap);
-	unsigned char* smem  = reinterpret_cast<unsigned char*>(smem4) + warp * wbytes;
-	unsigned const units = kSplit ? a.plan[a.nconns * a.nsteps] : static_cast<unsigned>(a.total_tiles) * a.nsteps;
-	int cs = 0; // thread 0, split launches: the (connection, step) of the last ticket; tickets only grow
-	for (;;) {
-		if (threadIdx.x == 0) {
-			unsigned const u = atomicAdd(a.work, 1u);
-			claimed          = u;
-			if (u < units) {
-				int c = 0, s, k;
-				unsigned r = 0;
-				if constexpr (kSplit) {
-					while (a.plan[cs + 1] <= u)
-						cs++;
-					c = cs / a.nsteps;
-					s = cs % a.nsteps;
-				} else {
-					while (c + 1 < a.nconns && static_cast<unsigned>(a.conns[c + 1].tile_prefix) * a.nsteps <= u)
-						c++;
+	__shared__ cta_state<kW, kStages> sh;
+	int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned const units  = static_cast<unsigned>(a.total_tiles) * a.nsteps;
+	unsigned const cnt    = smem_u32(smem4);                                  // counters: arrays A, B, dump
+	int const cnt_words   = 2 * a.tile_cap + 32;
+	unsigned const ring   = cnt + static_cast<unsigned>(cnt_words) * 4 + static_cast<unsigned>(warp) * (kStages * kStageBytes);
+	unsigned const bar0   = smem_u32(&sh.bars[warp][0]);
+
+	// ---- CTA prologue -----------------------------------------------------------------------------------
+	for (int i = tid; i < a.nconns * a.nsteps; i += kW * 32) {
+		conn_desc const& C = a.conns[i / a.nsteps];
+		sh.tot[i]          = C.ring_cnt[((a.t0 + i % a.nsteps) % a.ring) * C.cnt_stride];
+	}
+	for (int i = tid; i <= a.nconns; i += kW * 32)
+		sh.prefix[i] = i < a.nconns ? a.conns[i].tile_prefix : a.total_tiles;
+	if (tid < kTicketRing)
+		sh.tickets[tid] = tid < kStaticUnits ? static_ticket(blockIdx.x, gridDim.x, tid) : 0xffffffffu;
+	for (int i = tid; i < (cnt_words + 3) / 4; i += kW * 32)
+		smem4[i] = make_uint4(0, 0, 0, 0);
+	if (lane < kStages)
+		mbar_init(bar0 + lane * 8, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	// the first dynamically claimed ticket (unit kStaticUnits of this CTA) is on its way while the first unit runs
+	unsigned pending = 0;
+	if (tid == 0)
+		pending = atomicAdd(a.work, 1u);
+	__syncthreads();
+
+	auto view = [&](unsigned seq) {
+		unit_view v{};
+		unsigned const ticket = sh.tickets[seq % kTicketRing];
+		v.valid               = ticket < units;
+		if (v.valid) {
+			unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
+			v.C     = a.conns + p.c;
+			v.s     = p.s;
+			v.k     = p.k;
+			v.total = sh.tot[p.c * a.nsteps + p.s];
+		}
+		return v;
+	};
+
+	// ---- per-warp pipeline state -------------------------------------------------------------------------
+	unsigned done = 0; // units of this CTA merged so far = the unit being counted
+	// cursor: the next batch of this warp whose spike ids have not been requested yet
+	unsigned cs_seq = 0, cs_b = warp, cs_total = 0, cs_nbatch = 0;
+	bool cs_known = false, cs_end = false;
+	std::int32_t const* cs_ids = nullptr;
+	unsigned const* cs_gp      = nullptr;
+	int cs_stride              = 0;
+	char const* cs_stream      = nullptr;
+	// ids requested (stage I), run pointers requested (stage P = nxt), runs being fetched and counted (cur)
+	bool id_valid = false;
+	unsigned id_seq = 0;
+	std::int32_t id_src = -1;
+	unsigned const* id_gp = nullptr;
+	int id_stride         = 0;
+	char const* id_stream = nullptr;
+	batch nxt{0, 0, 0, false}, cur{0, 0, 0, false};
+	unsigned q_cnt = 0;              // quarters of cur counted
+	unsigned q_cur = 0, q_nxt = 0;   // quarters of cur / nxt whose copies have been issued
+	unsigned n_issue = 0, n_count = 0; // stages issued / counted by this warp since the kernel began
+	unsigned long long ev = 0;       // Syn::deliver invocations this thread has merged
+
+	auto cursor_next = [&](unsigned& seq_out, unsigned& b_out) -> bool {
+		for (;;) {
+			if (cs_end || cs_seq > done + kLookahead)
+				return false;
+			if (!cs_known) {
+				unit_view const v = view(cs_seq);
+				if (!v.valid) {
+					cs_end = true;
+					return false;
 				}
-				conn_desc const& C = a.conns[c];
-				if constexpr (kSplit) {
-					unsigned const total = C.ring_cnt[((a.t0 + s) % a.ring) * C.cnt_stride];
-					item_pos const it    = locate_item(u - a.plan[cs], C.arranged != 0, total, a.round_batches);
-					k                    = static_cast<int>(it.tile);
-					r                    = it.round;
-					U.round              = it.round;
-					U.rounds             = it.rounds;
-					U.b0                 = it.b0;
-					U.b1                 = it.b1;
-					U.flag                = a.unit_flag + (static_cast<unsigned>(C.tile_prefix) * a.nsteps + static_cast<unsigned>(s) * C.tiles + k);
-				} else {
-					unsigned const local = u - static_cast<unsigned>(C.tile_prefix) * a.nsteps;
-					s                    = static_cast<int>(local / C.tiles);
-					k                    = static_cast<int>(local % C.tiles);
+				long long const slot = (a.t0 + v.s) % a.ring;
+				cs_total  = v.total;
+				cs_nbatch = v.C->arranged ? (v.total + 31) / 32 : 0; // plain units are walked at their merge
+				cs_ids    = v.C->ring_ids + slot * v.C->ring_cap;
+				cs_gp     = v.C->run_ptr + v.k;
+				cs_stride = v.C->tiles;
+				cs_stream = reinterpret_cast<char const*>(v.C->packed);
+				cs_known  = true;
+			}
+			if (cs_b < cs_nbatch) {
+				seq_out = cs_seq;
+				b_out   = cs_b;
+				cs_b += kW;
+				return true;
+			}
+			cs_seq++;
+			cs_b     = warp;
+			cs_known = false;
+		}
+	};
+	// keep the three prefetch stages full: ids -> run pointers -> (cur)
+	auto refill = [&]() {
+#pragma unroll
+		for (int pass = 0; pass < 3; pass++) {
+			if (!cur.valid && nxt.valid) {
+				cur       = nxt;
+				q_cnt     = 0;
+				q_cur     = q_nxt;
+				q_nxt     = 0;
+				nxt.valid = false;
+			}
+			if (!nxt.valid && id_valid) {
+				nxt.valid = true;
+				nxt.seq   = id_seq;
+				nxt.ng    = 0;
+				nxt.addr  = 0;
+				if (id_src >= 0) {
+					unsigned const* p = id_gp + static_cast<long long>(id_src) * id_stride;
+					unsigned const g0 = p[0];
+					nxt.ng            = p[1] - g0;
+					nxt.addr          = reinterpret_cast<unsigned long long>(id_stream) + static_cast<unsigned long long>(g0) * 16;
 				}
-				long long const t = a.t0 + s;
-				U.C         = &C;
-				U.lo        = k * C.tile;
-				U.width     = static_cast<int>(min(static_cast<long long>(C.tile), C.n_dst - U.lo));
-				U.out       = C.counts + ((t + C.delay) % C.cring) * C.cstride + U.lo;
-				U.ring_slot = t % a.ring;
-				U.ids0      = C.ring_ids + U.ring_slot * C.ring_cap;
-				U.gp        = C.run_ptr + k;
-				U.tile_ptr  = C.tile_ptr + k;
-				U.stride    = C.arranged ? C.tiles : C.tiles + 1;
-				unsigned const total = C.ring_cnt[U.ring_slot * C.cnt_stride];
-				U.total              = total;
-				if (k == 0 && r == 0 && total)
-					atomicAdd(a.stats + 1, static_cast<unsigned long long>(total));
+				id_valid = false;
+			}
+			if (!id_valid) {
+				unsigned seq, b;
+				if (cursor_next(seq, b)) {
+					unsigned const q = b * 32 + lane;
+					id_valid  = true;
+					id_seq    = seq;
+					id_src    = q < cs_total ? cs_ids[q] : -1;
+					id_gp     = cs_gp;
+					id_stride = cs_stride;
+					id_stream = cs_stream;
+				}
 			}
 		}
+	};
+	// issue the copies of quarter `q` of batch `b` into the next free stage
+	auto issue = [&](batch const& b, unsigned q) {
+		unsigned const st  = n_issue % kStages;
+		unsigned const bar = bar0 + st * 8;
+		bool const mine    = (static_cast<unsigned>(lane) / kRuns) == q;
+		unsigned const bytes = mine ? min(b.ng, 32u) * 16 : 0;
+		unsigned const tot   = __reduce_add_sync(kFull, bytes);
+		if (lane == 0)
+			mbar_arrive_expect_tx(bar, tot);
+		__syncwarp();
+		if (bytes)
+			bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, reinterpret_cast<void const*>(b.addr), bytes, bar);
+		n_issue++;
+	};
+	auto issue_ahead = [&]() {
+		while (n_issue - n_count < kStages) {
+			if (cur.valid && q_cur < kQuarters)
+				issue(cur, q_cur++);
+			else if (nxt.valid && q_nxt < kQuarters)
+				issue(nxt, q_nxt++);
+			else
+				break;
+		}
+	};
+	// count quarter q_cnt of cur (its stage has been issued)
+	auto count_stage = [&]() {
+		unsigned const st = n_count % kStages;
+		mbar_wait(bar0 + st * 8, (n_count / kStages) & 1);
+		unsigned const base = ring + st * kStageBytes + lane * 16;
+		int4 v[kRuns];
+		unsigned n[kRuns];
+#pragma unroll
+		for (int j = 0; j < kRuns; j++) {
+			n[j] = __shfl_sync(kFull, cur.ng, q_cnt * kRuns + j);
+			v[j] = make_int4(-1, 0, 0, 0);
+			if (static_cast<unsigned>(lane) < n[j])
+				v[j] = lds128(base + j * kSlotBytes);
+		}
+		bool longer = false;
+#pragma unroll
+		for (int j = 0; j < kRuns; j++) {
+			if (v[j].x >= 0)
+				tally(cnt, v[j]);
+			longer |= n[j] > 32;
+		}
+		if (longer) { // a run of more than 32 groups (rare: tiles are sized for ~25): the rest straight from global memory
+#pragma unroll 1
+			for (int j = 0; j < kRuns; j++) {
+				unsigned long long const g = __shfl_sync(kFull, cur.addr, q_cnt * kRuns + j);
+				unsigned const nj          = __shfl_sync(kFull, cur.ng, q_cnt * kRuns + j);
+				for (unsigned off = 32 + lane; off < nj; off += 32)
+					tally(cnt, ldg_stream(reinterpret_cast<void const*>(g + static_cast<unsigned long long>(off) * 16)));
+			}
+		}
+		__syncwarp(); // every lane has read the stage's slots: they may be overwritten
+		n_count++;
+		if (++q_cnt == kQuarters)
+			cur.valid = false;
+	};
+	// end of unit `done`: all warps arrive; merge + zero the counters, store the tile's range; publish the next ticket
+	auto boundary = [&](unit_view const& U) {
 		__syncthreads();
-		if (claimed >= units)
-			break;
-		unsigned const nbatch = (U.total + 31) / 32;
-		int const words       = (U.width + 3) / 4; // 4 targets per 32-bit word of u8 counters
-		if (!U.C->arranged) {
-			for (int i = threadIdx.x; i < words * 4; i += kWarps * 32)
-				U.out[i] = 0;
+		conn_desc const& C = *U.C;
+		int const lo       = U.k * C.tile;
+		int const width    = static_cast<int>(min(static_cast<long long>(C.tile), C.n_dst - lo));
+		long long const t  = a.t0 + U.s;
+		std::uint32_t* out = C.counts + ((t + C.delay) % C.cring) * C.cstride + lo;
+		int const quads    = (width + 3) / 4;
+		uint4* o           = reinterpret_cast<uint4*>(out);
+		if (tid == 0 && U.k == 0 && U.total)
+			atomicAdd(a.stats + 1, static_cast<unsigned long long>(U.total));
+		if (!C.arranged) {
+			for (int i = tid; i < quads; i += kW * 32)
+				o[i] = make_uint4(0, 0, 0, 0);
 			__threadfence_block();
 			__syncthreads();
-			walk_plain(a, U, lane, warp);
-			__syncthreads();
+			if (U.total)
+				ev += walk_plain<kW>(C, U.k, C.ring_ids + ((a.t0 + U.s) % a.ring) * C.ring_cap, U.total, out, lo, lane, warp);
+		} else if (U.total == 0) {
+			for (int i = tid; i < quads; i += kW * 32)
+				o[i] = make_uint4(0, 0, 0, 0);
+		} else {
+			unsigned const cap4 = static_cast<unsigned>(a.tile_cap) * 4;
+			for (int i = tid; i < quads; i += kW * 32) {
+				int const t0     = 4 * i;
+				unsigned const A = cnt + 16u * i;
+				int4 ca          = lds128(A);
+				asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(A), "r"(0u) : "memory");
+				int const sh_    = rotw_amount(t0 >> 5);
+				unsigned const B = cnt + cap4 + 4u * (t0 & ~31);
+				unsigned cb[4];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					unsigned const at = B + 4u * ((t0 + j + sh_) & 31);
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cb[j]) : "r"(at));
+					asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(0u) : "memory");
+				}
+				uint4 const c = make_uint4(ca.x + cb[0], ca.y + cb[1], ca.z + cb[2], ca.w + cb[3]);
+				ev += c.x + c.y + c.z + c.w;
+				o[i] = c;
+			}
+		}
+		if (tid == 0) { // the ticket claimed while this unit ran becomes unit done + kStaticUnits; claim the one after it
+			sh.tickets[(done + kStaticUnits) % kTicketRing] = dynamic_ticket(gridDim.x, pending);
+			pending                                         = atomicAdd(a.work, 1u);
+		}
+		__syncthreads();
+		done++;
+	};
+
+	// ---- main loop ---------------------------------------------------------------------------------------
+	for (;;) {
+		refill();
+		issue_ahead();
+		if (cur.valid && cur.seq == done) {
+			count_stage();
 			continue;
 		}
-		constexpr unsigned per_round = kPerRound;
-		unsigned const rounds        = kSplit ? 1u : max(1u, (nbatch + per_round - 1) / per_round);
-		for (unsigned round = 0; round < rounds; round++) {
-			unsigned const b0 = kSplit ? U.b0 : round * per_round;
-			unit_walker w{a, U, smem, lane};
-			w.run(b0 + warp, kWarps, kSplit ? U.b1 : min(nbatch, b0 + per_round));
-			if constexpr (kSplit)
-				if (U.round > 0 && threadIdx.x == 0) // round 0 has stored the unit's counters?
-					while (ld_acquire(U.flag) != a.epoch)
-						__nanosleep(64);
-			__syncthreads();
-			// add the warps' arrays and store / accumulate: this CTA is the only writer of the range.
-			// Word wd of array A holds targets 4 wd .. 4 wd + 3; their B counters sit in the same
-			// 128-byte row r = wd / 32, rotated by r words.  The sum of all counters is the number
-			// of Syn::deliver invocations this round stands for.
-			uint4* o    = reinterpret_cast<uint4*>(U.out);
-			unsigned ev = 0;
-			for (int wd = threadIdx.x; wd < words; wd += kWarps * 32) {
-				int const r = wd >> 5;
-				int const wb = (wd & ~31) | ((wd + r) & 31);
-				unsigned even = 0, odd = 0; // two 16-bit lanes each: targets (0, 2) and (1, 3)
-#pragma unroll
-				for (int w2 = 0; w2 < kWarps; w2++) {
-					unsigned char const* base = reinterpret_cast<unsigned char const*>(smem4) + w2 * wbytes + kDescBytes;
-					unsigned const ca = reinterpret_cast<unsigned const*>(base)[wd];
-					unsigned const cb = reinterpret_cast<unsigned const*>(base + a.tile_cap)[wb];
-					even += (ca & 0x00ff00ffu) + (cb & 0x00ff00ffu);
-					odd += ((ca >> 8) & 0x00ff00ffu) + ((cb >> 8) & 0x00ff00ffu);
-				}
-				uint4 c = make_uint4(even & 0xffffu, odd & 0xffffu, even >> 16, odd >> 16);
-				ev += c.x + c.y + c.z + c.w;
-				if constexpr (kSplit) {
-					if (U.round == 0)
-						o[wd] = c;
-					else {
-						if (c.x) atomicAdd(U.out + 4 * wd + 0, c.x);
-						if (c.y) atomicAdd(U.out + 4 * wd + 1, c.y);
-						if (c.z) atomicAdd(U.out + 4 * wd + 2, c.z);
-						if (c.w) atomicAdd(U.out + 4 * wd + 3, c.w);
-					}
-				} else {
-					if (round) {
-						uint4 const prev = o[wd];
-						c.x += prev.x, c.y += prev.y, c.z += prev.z, c.w += prev.w;
-					}
-					o[wd] = c;
-				}
-			}
-			for (int off = 16; off; off >>= 1)
-				ev += __shfl_xor_sync(kFull, ev, off);
-			if (lane == 0 && ev)
-				atomicAdd(a.stats + 0, static_cast<unsigned long long>(ev));
-			if constexpr (kSplit)
-				if (U.round == 0 && U.rounds > 1)
-					__threadfence(); // the counters before the flag
-			__syncthreads();
-			if constexpr (kSplit)
-				if (U.round == 0 && U.rounds > 1 && threadIdx.x == 0)
-					st_release(U.flag, a.epoch);
-		}
+		// this warp has nothing left in unit `done` (its next batch, if any, belongs to a later unit)
+		unit_view const U = view(done);
+		if (!U.valid)
+			break;
+		boundary(U);
 	}
+	for (int off = 16; off; off >>= 1)
+		ev += __shfl_xor_sync(kFull, ev, off);
+	if (lane == 0 && ev)
+		atomicAdd(a.stats + 0, ev);
 }
 
 // ---- pack_runs / unpack_rows ---------------------------------------------------------------------
-// Counter addresses of local target t of a tile (t < cap, cap a multiple of 128):
-//   array A: t                       (bank (t >> 2) & 31)
-//   array B: cap + rot(t),  rot(t) = t with its bank field rotated by the 128-byte row number
-//                                      (bank ((t >> 2) + (t >> 7)) & 31)
-//   dump:    2 cap + 4 bank + byte   (never read back)
-// Two targets that share a bank in A never share one in B (for tiles of <= 32 rows), which is what
-// makes the 2-choice balancing effective.
-// rot_fwd / rot_inv: deliver_plan.h
+// Counter words of local target t of a tile (t < cap, cap a multiple of 128), deliver_plan.h:
+//   array A: word t                  (bank t & 31)
+//   array B: word cap + rotw_fwd(t)  (bank (t + rotw_amount(t / 32)) & 31)
+//   dump:    word 2 cap + bank       (never read back)
+// A stream entry is 4 x the word index (the byte offset red.shared takes).
 
 // groups of every run: run_ptr[id] = ceil(len / 4) (scanned afterwards); id = row * tiles + k
 __global__ void __launch_bounds__(256) run_groups_kernel(long long const* tile_ptr, long long n_runs, int tiles, unsigned* run_ptr) {
@@ -468,7 +452,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 		for (int j = 0; j < m; j++) {
 			int const tt = __ldg(nb + g0 + j) - lo;
 			t[j]         = static_cast<unsigned short>(tt);
-			int const bA = (tt >> 2) & 31, bB = ((tt >> 2) + (tt >> 7)) & 31;
+			int const bA = tt & 31, bB = (tt + rotw_amount(tt >> 5)) & 31;
 			bool const pickB = load[bB] < load[bA];
 			int const b      = pickB ? bB : bA;
 			load[b]++;
@@ -477,7 +461,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 		for (int pass = 0; pass < 2; pass++)
 			for (int j = 0; j < m; j++) {
 				int const tt  = t[j];
-				int const bA  = (tt >> 2) & 31, bB = ((tt >> 2) + (tt >> 7)) & 31;
+				int const bA  = tt & 31, bB = (tt + rotw_amount(tt >> 5)) & 31;
 				bool const inB = (bank[j] & 0x80) != 0;
 				int const cur = inB ? bB : bA, alt = inB ? bA : bB;
 				if (load[cur] > load[alt] + 1) {
@@ -531,7 +515,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 					rem[best]--;
 					int const j  = order[first[b] + i];
 					int const tt = t[j];
-					out[next[best]] = (bank[j] & 0x80) ? cap + rot_fwd(tt) : tt;
+					out[next[best]] = 4 * ((bank[j] & 0x80) ? cap + rotw_fwd(tt) : tt);
 					next[best] += 4;
 				}
 			}
@@ -541,7 +525,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 				unsigned const free_banks = ~used_banks[c];
 				int const b               = free_banks ? __ffs(free_banks) - 1 : 0;
 				used_banks[c] |= 1u << b;
-				out[next[c]] = 2 * cap + 4 * b + c;
+				out[next[c]] = 4 * (2 * cap + b);
 			}
 	}
 }
@@ -561,10 +545,10 @@ __global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed,
 			present[i] = 0;
 		long long const beg = static_cast<long long>(run_ptr[row * tiles + k]) * 4, end = static_cast<long long>(run_ptr[row * tiles + k + 1]) * 4;
 		for (long long e = beg; e < end; e++) {
-			int const v = packed[e];
+			int const v = packed[e] >> 2;
 			if (v >= 2 * cap)
 				continue;
-			int const t = v < cap ? v : rot_inv(v - cap);
+			int const t = v < cap ? v : rotw_inv(v - cap);
 			present[t >> 5] |= 1u << (t & 31);
 		}
 		for (int i = 0; i < words; i++) {
@@ -654,79 +638,76 @@ int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_pt
 	return static_cast<int>(cudaGetLastError());
 }
 
-// experiments (read once): SPICE_DELIVER_CTAS_PER_SM / SPICE_DELIVER_GRID shrink the persistent grid,
-// SPICE_DELIVER_SPLIT = 0 / 1 forces whole-unit / single-round work items, SPICE_DELIVER_ROUND = batches of 32
-// spikes per single-round item (<= kPerRound)
+// experiments (read once): SPICE_DELIVER_WARPS = 8 / 16 picks the CTA shape, SPICE_DELIVER_GRID shrinks the persistent grid
 static int env_int(char const* name, int dflt) {
 	char const* e = std::getenv(name);
 	return e && *e ? std::atoi(e) : dflt;
 }
-// Split when a window has fewer than 2.5 units per resident CTA.  Measured on one B200 with the per-rank shapes of
-// the weak-scaled Brunel benchmark (tools/rank_shape_probe.py, rates oscillating by +-50 %; single rounds vs whole
-// units): 1 rank, 4.4 units per CTA: -6 %; 2 ranks, 3.0: -4 %; 4 ranks, 2.3: +7 %; 8 ranks, 1.5: +8 % (+22 % at +-80 %).
-constexpr long long kSplitBelowNum = 5, kSplitBelowDen = 2;
+
+namespace {
+size_t cta_smem(int tile_cap, int warps, int stages) {
+	return static_cast<size_t>(2 * tile_cap + 32) * 4 + static_cast<size_t>(warps) * stages * kStageBytes;
+}
+using kernel_t = void (*)(tiles_args);
+struct shape {
+	kernel_t kernel;
+	int warps, stages;
+};
+// two CTAs of 8 warps per SM (one merges while the other streams), or one of 16 warps: windows with few, long units
+// (a rank of a multi-GPU run sees every source but few target tiles)
+shape const kShapes[2] = {{deliver_units<8, 2>, 8, 2}, {deliver_units<16, 2>, 16, 2}};
+}
 
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
-	static int const ctas_env = env_int("SPICE_DELIVER_CTAS_PER_SM", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
-	                 split_env = env_int("SPICE_DELIVER_SPLIT", -1), round_env = env_int("SPICE_DELIVER_ROUND", 0);
-	static int blocks_per_sm[64] = {};
-	static int sms[64]           = {};
-	static int smem_set[64]      = {};
-	size_t const smem = static_cast<size_t>(kWarps) * warp_smem(a.tile_cap);
+	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0);
+	static int blocks_per_sm[64][2] = {};
+	static int sms[64]              = {};
+	static int smem_set[64]         = {};
 	if (device < 0 || device >= 64)
 		return static_cast<int>(cudaErrorInvalidDevice);
-	if (smem_set[device] < static_cast<int>(smem)) {
-		int nb = 1 << 30;
-		for (auto kernel : {deliver_tiles<false>, deliver_tiles<true>}) {
-			cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+	if (a.nconns > kMaxConns || a.nsteps > spice::detail::kMaxWindow)
+		return static_cast<int>(cudaErrorInvalidValue);
+	if (smem_set[device] < a.tile_cap) {
+		for (int i = 0; i < 2; i++) {
+			size_t const smem = cta_smem(a.tile_cap, kShapes[i].warps, kShapes[i].stages);
+			cudaError_t e = cudaFuncSetAttribute(kShapes[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 			if (e != cudaSuccess)
 				return static_cast<int>(e);
-			e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			e = cudaFuncSetAttribute(kShapes[i].kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 			if (e != cudaSuccess)
 				return static_cast<int>(e);
 			int n = 0;
-			e     = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kWarps * 32, smem);
+			e     = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kShapes[i].kernel, kShapes[i].warps * 32, smem);
 			if (e != cudaSuccess)
 				return static_cast<int>(e);
-			nb = std::min(nb, n);
+			blocks_per_sm[device][i] = std::max(n, 1);
 		}
 		cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);
-		blocks_per_sm[device] = std::max(nb, 1);
-		if (ctas_env > 0)
-			blocks_per_sm[device] = std::clamp(ctas_env, 1, blocks_per_sm[device]);
-		smem_set[device] = static_cast<int>(smem);
+		smem_set[device] = a.tile_cap;
 	}
 	long long const units = static_cast<long long>(a.total_tiles) * a.nsteps;
 	if (units <= 0)
 		return 0;
-	long long const full = static_cast<long long>(sms[device]) * blocks_per_sm[device];
+	// fewer than ~6 units per 8-warp CTA: the tail of the window would run on a few CTAs; put 16 warps on a unit
+	int which = units < 6ll * sms[device] * blocks_per_sm[device][0] ? 1 : 0;
+	if (warps_env == 8 || warps_env == 16)
+		which = warps_env == 16;
+	shape const& S       = kShapes[which];
+	long long const full = static_cast<long long>(sms[device]) * blocks_per_sm[device][which];
 	int grid             = static_cast<int>(std::min<long long>(units, full));
 	if (grid_env > 0)
 		grid = std::clamp(grid_env, 1, grid);
-	// few units per CTA (a rank of a multi-GPU run: many sources, few tiles): hand out single rounds
-	bool split = a.plan && a.unit_flag && kSplitBelowDen * units < kSplitBelowNum * full;
-	if (split_env >= 0)
-		split = split_env != 0 && a.plan && a.unit_flag;
 	if (launches)
-		*launches = split ? 2 : 1;
-	if (split) {
-		grid = static_cast<int>(grid_env > 0 ? std::min<long long>(grid_env, full) : full); // items >= units; idle CTAs leave at once
-		tiles_args b    = a;
-		b.round_batches = round_env > 0 ? std::min<unsigned>(round_env, kPerRound) : kPerRound;
-		plan_items<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
-		deliver_tiles<true><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(b);
-	} else
-		deliver_tiles<false><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+		*launches = 1;
+	S.kernel<<<grid, S.warps * 32, cta_smem(a.tile_cap, S.warps, S.stages), static_cast<cudaStream_t>(stream)>>>(a);
 	return static_cast<int>(cudaGetLastError());
 }
 
 int preload() {
 	cudaFuncAttributes fa{};
-	cudaError_t e = cudaFuncGetAttributes(&fa, deliver_tiles<false>);
-	if (e == cudaSuccess)
-		e = cudaFuncGetAttributes(&fa, deliver_tiles<true>);
-	if (e == cudaSuccess)
-		e = cudaFuncGetAttributes(&fa, plan_items);
+	cudaError_t e = cudaSuccess;
+	for (int i = 0; i < 2 && e == cudaSuccess; i++)
+		e = cudaFuncGetAttributes(&fa, kShapes[i].kernel);
 	return static_cast<int>(e);
 }
 }

@@ -7,7 +7,7 @@
 
 namespace spice::deliver {
 
-constexpr int kTileMax = 5120; // targets per tile: one warp keeps two u8 counters per target in shared memory (10 KB)
+constexpr int kTileMax = 5120; // targets per tile: a CTA keeps two u32 counters per target in shared memory (40 KB)
 
 // One connection as the delivery kernel sees it (lives in device memory, one array per context,
 // in schedule order: heaviest connections first).
@@ -43,16 +43,13 @@ struct tiles_args {
 	int ring, world;
 	long long t0;
 	int nsteps;
-	unsigned* work;            // dynamic unit counter, zeroed by the window prologue
+	unsigned* work;            // dynamic ticket counter, zeroed by the window prologue
 	unsigned long long* stats; // [0] events, [1] spikes
 	int* error;                // bit 16: internal error in the delivery kernel
-	int tile_cap;              // targets per warp-private counter array (max conns[].tile rounded up to 128)
-	// split launches (work items = single rounds of a unit; null: never split):
-	unsigned* plan;      // [nconns * window + 1] first item of every (connection, step), rewritten by every launch
-	unsigned* unit_flag; // [total_tiles * window] epoch of the launch whose round 0 has stored the unit's counters
-	unsigned epoch;      // this launch's, > 0 and different from the previous launches'
-	unsigned round_batches; // set by launch_tiles: batches of 32 spikes per item
+	int tile_cap;              // targets per counter array (max conns[].tile rounded up to 128)
 };
+
+constexpr int kMaxConns = 32; // connections per launch (their per-step spike totals are staged in shared memory)
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
 // (k = tiles: the row end).  Returns a cudaError_t as int.
@@ -60,10 +57,10 @@ int build_tile_ptr(void* stream, long long const* offsets, std::int32_t const* n
                    int tiles, long long* tile_ptr);
 
 // The fast path's own stream format, built once per duplicate-free connection from its CSR:
-// every run (a tile's share of a row) becomes whole 16-byte groups of counter byte addresses —
-// array A at [0, cap), array B at [cap, 2 cap) with the bank rotated by the 128-byte row, a dump
-// area at [2 cap, 2 cap + 128) for padding — permuted so that the 32 lanes of one counting
-// instruction hit 32 different shared-memory banks.  `cap` must equal tiles_args::tile_cap.
+// every run (a tile's share of a row) becomes whole 16-byte groups of counter BYTE offsets (deliver_plan.h) —
+// array A at word t, array B at word cap + rotw_fwd(t), a dump area of 32 words behind them for padding —
+// permuted so that the 32 lanes of one counting instruction hit 32 different shared-memory banks.
+// `cap` must equal tiles_args::tile_cap.
 //   count_groups: run_ptr[src * tiles + 1] (exclusive scan of the runs' group counts) and their sum;
 //   pack_runs:    fills `packed` (4 * groups entries);
 //   unpack_rows:  the canonical (ascending, local column) CSR entries of [0, edges) into `out`.
@@ -73,9 +70,8 @@ int pack_runs(void* stream, std::int32_t const* neighbors, long long const* tile
 int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets, long long src_count,
                 int tile, int tiles, int cap, std::int32_t* out);
 
-// Delivers every spike of the window on every connection with a persistent grid filling the device.  Windows
-// with few units per CTA are launched split (plan_items + deliver_tiles<true>, deliver.cu); `launches` receives the
-// number of kernels launched.  Returns a cudaError_t as int.
+// Delivers every spike of the window on every connection with a persistent grid filling the device; `launches`
+// receives the number of kernels launched.  Returns a cudaError_t as int.
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches = nullptr);
 
 // Loads the delivery kernels (a lazily loaded kernel can synchronise the context at its first launch).

@@ -1,11 +1,5 @@
-// Pure arithmetic of the delivery kernels (deliver.cu), shared with the host tests
-// (tests/test_host.py::test_delivery_plan_covers_every_batch, ::test_counter_address_rotation).
-//
-// Work items of a split delivery launch (deliver_tiles<true>):
-// A unit = (connection, step, tile).  Its step holds `total` spikes = ceil(total / 32) batches; a CTA may count at most
-// `per_round` batches between two merges (u8 counters), so the unit takes rounds_of() rounds.  A split launch hands
-// out single rounds: (connection, step) owns tiles * rounds consecutive tickets, a unit's rounds next to each other,
-// round 0 first (it stores the counters, the later rounds wait for it and add), batches spread evenly.
+// Pure arithmetic of the delivery kernel (deliver.cu), shared with the host tests
+// (tests/test_host.py::test_delivery_tickets_cover_every_unit, ::test_counter_address_rotation).
 #pragma once
 
 #ifdef __CUDACC__
@@ -15,36 +9,41 @@
 #endif
 
 namespace spice::deliver {
-SPICE_PLAN_HD unsigned rounds_of(bool arranged, unsigned total, unsigned per_round) {
-	unsigned const nbatch = (total + 31) / 32;
-	unsigned const rounds = (nbatch + per_round - 1) / per_round;
-	return arranged && rounds > 1 ? rounds : 1u; // plain (multapse) connections are walked whole
-}
 
-// The two u8 counters of local target t of a tile (stream format, deliver.h): array A at byte t (shared-memory bank
-// (t >> 2) & 31), array B at byte cap + rot_fwd(t), where the bank field of t is rotated by the number of t's 128-byte
-// row.  Targets that share a bank in A (same bank field, different rows) therefore sit in different banks in B as
-// long as the tile has at most 32 rows — what makes pack_runs' 2-choice bank balancing effective.
-SPICE_PLAN_HD int rot_fwd(int t) { return (t & ~0x7c) | ((t + ((t >> 7) << 2)) & 0x7c); }
-SPICE_PLAN_HD int rot_inv(int u) { return (u & ~0x7c) | ((u - ((u >> 7) << 2)) & 0x7c); }
+// ---- counter addresses ------------------------------------------------------------------------------
+// Every local target t of a tile (t < cap, cap a multiple of 128) has TWO u32 counters in the CTA's shared memory:
+//   array A: word t                (bank t & 31)
+//   array B: word cap + rotw_fwd(t) (bank (t + row + row / 32) & 31, row = t / 32: the bank field of t rotated by
+//                                    a per-row amount, so targets that share a bank in A mostly do not in B)
+//   dump:    words 2 cap .. 2 cap + 31 (padding entries; never read)
+// A stream entry is the BYTE offset of one of them (4 x the word index), which is what red.shared takes.
+SPICE_PLAN_HD int rotw_amount(int row) { return (row + (row >> 5)) & 31; }
+SPICE_PLAN_HD int rotw_fwd(int t) { return (t & ~31) | ((t + rotw_amount(t >> 5)) & 31); }
+SPICE_PLAN_HD int rotw_inv(int u) { return (u & ~31) | ((u - rotw_amount(u >> 5)) & 31); }
 
-struct item_pos {
-	unsigned tile;   // k
-	unsigned round;  // of `rounds`
-	unsigned rounds;
-	unsigned b0, b1; // the item's batches [b0, b1) of the step's spike list
+// ---- work tickets ---------------------------------------------------------------------------------------
+// A unit = (connection, step of the window, tile); units are numbered connection by connection in schedule order
+// (heaviest first), inside a connection step-major: unit = tile_prefix[c] * nsteps + s * tiles[c] + k.
+// A CTA works through a private sequence of units: the first kStaticUnits of it are fixed by its index
+// (cta, cta + grid, ...), so their spike lists can be prefetched before anything has been claimed; the rest are
+// claimed from a global counter, one per finished unit, kStaticUnits units ahead of the one being counted.
+constexpr int kStaticUnits = 4;  // = how far ahead of the unit being counted a warp may prefetch, plus one
+constexpr int kTicketRing  = 8;  // slots of the CTA's ticket ring (> kStaticUnits)
+
+SPICE_PLAN_HD unsigned static_ticket(unsigned cta, unsigned grid, unsigned j) { return cta + j * grid; }
+SPICE_PLAN_HD unsigned dynamic_ticket(unsigned grid, unsigned claimed) { return kStaticUnits * grid + claimed; }
+
+struct unit_pos {
+	int c, s, k;
 };
-
-// ticket `local` (0-based within its (connection, step)) -> tile, round and batch range
-SPICE_PLAN_HD item_pos locate_item(unsigned local, bool arranged, unsigned total, unsigned per_round) {
-	unsigned const nbatch = (total + 31) / 32;
-	item_pos p;
-	p.rounds           = rounds_of(arranged, total, per_round);
-	unsigned const per = (nbatch + p.rounds - 1) / p.rounds; // <= per_round
-	p.tile             = local / p.rounds;
-	p.round            = local % p.rounds;
-	p.b0               = p.round * per;
-	p.b1               = p.b0 + per < nbatch ? p.b0 + per : nbatch;
-	return p;
+// tile_prefix[c] = tiles of the connections scheduled before c (tile_prefix[nconns] = total_tiles)
+template <class Prefix>
+SPICE_PLAN_HD unit_pos locate_unit(unsigned unit, Prefix const& tile_prefix, int nconns, int nsteps) {
+	int c = 0;
+	while (c + 1 < nconns && static_cast<unsigned>(tile_prefix[c + 1]) * nsteps <= unit)
+		c++;
+	unsigned const local = unit - static_cast<unsigned>(tile_prefix[c]) * nsteps;
+	unsigned const tiles = static_cast<unsigned>(tile_prefix[c + 1] - tile_prefix[c]);
+	return unit_pos{c, static_cast<int>(local / tiles), static_cast<int>(local % tiles)};
 }
 }

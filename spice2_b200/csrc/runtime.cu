@@ -484,9 +484,6 @@ struct spice_ctx {
 	bool tiled                        = true;    // SPICE_DELIVER=atomic selects the one-atomic-per-event kernel
 	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
 	unsigned* d_work                  = nullptr;
-	unsigned* d_plan                  = nullptr; // split delivery launches (deliver.h)
-	unsigned* d_unit_flag             = nullptr;
-	unsigned deliver_epoch            = 0;
 	int total_tiles = 0, tile_cap = 0, n_desc = 0;
 
 	// device tables
@@ -760,13 +757,10 @@ int finalize(spice_ctx* ctx) {
 		ctx->n_desc = static_cast<int>(descs.size());
 		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_work, sizeof(unsigned)));
 		CHECK_CUDA(ctx, cudaMemset(ctx->d_work, 0, sizeof(unsigned)));
-		if (ctx->n_desc > 0) {
-			size_t const nflag = static_cast<size_t>(ctx->total_tiles) * ctx->window;
-			CHECK_CUDA(ctx, cudaMalloc(&ctx->d_plan, sizeof(unsigned) * (static_cast<size_t>(ctx->n_desc) * ctx->window + 1)));
-			CHECK_CUDA(ctx, cudaMalloc(&ctx->d_unit_flag, sizeof(unsigned) * nflag));
-			CHECK_CUDA(ctx, cudaMemset(ctx->d_unit_flag, 0, sizeof(unsigned) * nflag));
+		if (ctx->n_desc > deliver::kMaxConns)
+			return fail(ctx, SPICE_ERR_UNSUPPORTED, "more than 32 stateless connections in one network");
+		if (ctx->n_desc > 0)
 			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::preload()));
-		}
 	}
 	for (auto const& p : ctx->pops)
 		if (p.incoming.size() > static_cast<size_t>(kMaxIncoming))
@@ -1146,9 +1140,6 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ta.stats       = ctx->d_stats;
 			ta.error       = ctx->d_error;
 			ta.tile_cap    = ctx->tile_cap;
-			ta.plan        = ctx->d_plan;
-			ta.unit_flag   = ctx->d_unit_flag;
-			ta.epoch       = ++ctx->deliver_epoch;
 			int launched   = 0;
 			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device, &launched);
 			if (e != 0)
@@ -1449,8 +1440,6 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_nib);
 	cudaFree(ctx->d_conn_desc);
 	cudaFree(ctx->d_work);
-	cudaFree(ctx->d_plan);
-	cudaFree(ctx->d_unit_flag);
 	cudaFree(ctx->d_stats);
 	cudaFree(ctx->d_error);
 	cudaFree(ctx->d_pop_size);

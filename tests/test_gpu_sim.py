@@ -410,11 +410,12 @@ np.savez({dest!r}, **out)
 """
 
 
-@pytest.mark.parametrize("split", [0, 1])
-def test_delivery_whole_units_and_single_rounds(sp, orc, golden, tmp_path, split):
-    """Both work distributions of the delivery kernel (deliver.cu: a CTA claims whole units / single
-    rounds of a unit, stored by round 0 and added by the later rounds) give the golden rasters.  The
-    vogels run starts with one volley of all 4000 neurons: 3200 spikes in one step = 4 rounds per unit."""
+@pytest.mark.parametrize("split", [8, 16])
+def test_delivery_cta_shapes(sp, orc, golden, tmp_path, split):
+    """Both CTA shapes of the delivery kernel (deliver.cu: 2 x 8 warps per SM, or 16 warps on a unit for
+    windows with few, long units) give the golden rasters.  The vogels run starts with one volley of all
+    4000 neurons; the dense variant (p = 0.5) has 3200-spike volleys and runs of 128 groups, four times a
+    landing slot (the count_stage tail path)."""
     import os
     import subprocess
     import sys
@@ -422,7 +423,7 @@ def test_delivery_whole_units_and_single_rounds(sp, orc, golden, tmp_path, split
 
     root = str(Path(__file__).resolve().parent.parent)
     dest = str(tmp_path / f"split{split}.npz")
-    env = dict(os.environ, SPICE_DELIVER_SPLIT=str(split))
+    env = dict(os.environ, SPICE_DELIVER_WARPS=str(split))
     subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT.format(root=root, dest=dest)], check=True, env=env, timeout=600)
     got = np.load(dest)
     for name, key in (("brunel", "brunel_300_strict"), ("vogels", "vogels_1500_strict")):

@@ -226,52 +226,54 @@ int main() {
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
 
 
-def test_delivery_plan_covers_every_batch(tmp_path):
-    """csrc/deliver_plan.h (the ticket -> (tile, round, batches) arithmetic of split delivery launches, shared with
-    the kernels): over random spike counts, the tickets of a (connection, step) visit every (tile, round) once, a
-    unit's rounds are adjacent with round 0 first, the rounds' batch ranges partition [0, nbatch) in order, and no
-    round exceeds the u8 counters' limit."""
+def test_delivery_tickets_cover_every_unit(tmp_path):
+    """csrc/deliver_plan.h (the ticket arithmetic of the delivery kernel, shared with it): the static tickets of a
+    grid's CTAs plus the dynamically claimed ones visit every unit exactly once whatever the grid size, and
+    locate_unit() inverts unit = tile_prefix[c] * nsteps + s * tiles[c] + k."""
     src = tmp_path / "plan.cpp"
-    src.write_text(r'''
+    src.write_text(r"""
 #include <cstdio>
 #include <random>
+#include <vector>
 #include "deliver_plan.h"
 using namespace spice::deliver;
-#define CHECK(c) do { if (!(c)) { std::printf("line %d: %s (total %u per %u tiles %u)\n", __LINE__, #c, total, per, tiles); return 1; } } while (0)
+#define CHECK(c) do { if (!(c)) { std::printf("line %d: %s\n", __LINE__, #c); return 1; } } while (0)
 int main() {
 	std::mt19937 g(7);
-	unsigned const totals[] = {0, 1, 31, 32, 33, 895, 896, 897, 1791, 1792, 1793, 2000, 2880, 3200, 100000, 1000000};
-	for (unsigned per : {28u, 20u, 7u, 1u})
-		for (int trial = 0; trial < 400; trial++) {
-			unsigned const total = trial < 16 ? totals[trial] : g() % (trial % 2 ? 5000 : 60000);
-			unsigned const tiles = 1 + g() % 7;
-			for (bool arranged : {true, false}) {
-				unsigned const nbatch = (total + 31) / 32, rounds = rounds_of(arranged, total, per);
-				CHECK(rounds >= 1);
-				CHECK(arranged ? (rounds == (nbatch + per - 1) / per || (nbatch <= per && rounds == 1)) : rounds == 1);
-				unsigned local = 0;
-				for (unsigned k = 0; k < tiles; k++) {
-					unsigned next = 0;
-					for (unsigned r = 0; r < rounds; r++, local++) {
-						item_pos const p = locate_item(local, arranged, total, per);
-						CHECK(p.tile == k && p.round == r && p.rounds == rounds);
-						if (rounds > 1 || arranged) {
-							CHECK(p.b0 == next || (p.b0 >= nbatch && p.b1 == nbatch));
-							CHECK(p.b1 <= nbatch);
-							CHECK(p.b1 <= p.b0 || p.b1 - p.b0 <= per);
-							if (p.b1 > p.b0)
-								next = p.b1;
-						}
-					}
-					if (arranged)
-						CHECK(next == nbatch);
+	for (int trial = 0; trial < 300; trial++) {
+		int const nconns = 1 + g() % 7, nsteps = 1 + g() % 15;
+		std::vector<int> prefix(nconns + 1, 0);
+		for (int c = 0; c < nconns; c++)
+			prefix[c + 1] = prefix[c] + 1 + g() % 60;
+		unsigned const units = static_cast<unsigned>(prefix[nconns]) * nsteps;
+		// locate_unit inverts the numbering
+		unsigned u = 0;
+		for (int c = 0; c < nconns; c++)
+			for (int s = 0; s < nsteps; s++)
+				for (int k = 0; k < prefix[c + 1] - prefix[c]; k++, u++) {
+					unit_pos const p = locate_unit(u, prefix, nconns, nsteps);
+					CHECK(p.c == c && p.s == s && p.k == k);
 				}
+		CHECK(u == units);
+		// static + dynamic tickets: a partition of [0, units) for any grid
+		unsigned const grid = 1 + g() % 400;
+		std::vector<int> seen(units, 0);
+		for (unsigned cta = 0; cta < grid; cta++)
+			for (unsigned j = 0; j < static_cast<unsigned>(kStaticUnits); j++) {
+				unsigned const t = static_ticket(cta, grid, j);
+				if (t < units)
+					seen[t]++;
 			}
-		}
+		for (unsigned claimed = 0; dynamic_ticket(grid, claimed) < units; claimed++)
+			seen[dynamic_ticket(grid, claimed)]++;
+		for (unsigned i = 0; i < units; i++)
+			CHECK(seen[i] == 1);
+		CHECK(kTicketRing > kStaticUnits);
+	}
 	std::puts("ok");
 	return 0;
 }
-''')
+""")
     exe = tmp_path / "plan"
     inc = ROOT / "spice2_b200" / "csrc"
     subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
@@ -280,11 +282,11 @@ int main() {
 
 
 def test_counter_address_rotation(tmp_path):
-    """csrc/deliver_plan.h rot_fwd / rot_inv (the address of a target's second u8 counter in the delivery stream):
-    a bijection on every 128-byte row of a tile, and two targets in the same bank of array A never share a bank of
-    array B (tiles of <= 32 rows = 4096 targets; the 5120-target maximum wraps only for rows 32..39)."""
+    """csrc/deliver_plan.h rotw_fwd / rotw_inv (the word of a target's second u32 counter in the delivery stream):
+    a bijection on every 32-word row of a tile, and of the targets that share a bank with a given target in array A
+    (one per row), few share its bank in array B as well — what makes pack_runs' 2-choice balancing effective."""
     src = tmp_path / "rot.cpp"
-    src.write_text(r'''
+    src.write_text(r"""
 #include <cstdio>
 #include <set>
 #include "deliver_plan.h"
@@ -294,23 +296,26 @@ int main() {
 	int const cap = 5120;
 	std::set<int> seen;
 	for (int t = 0; t < cap; t++) {
-		int const u = rot_fwd(t);
+		int const u = rotw_fwd(t);
 		CHECK(u >= 0 && u < cap);
-		CHECK((u >> 7) == (t >> 7));  // stays in its 128-byte row
-		CHECK((u & 3) == (t & 3));    // and in its byte of the word
-		CHECK(rot_inv(u) == t);
+		CHECK((u >> 5) == (t >> 5)); // stays in its 128-byte row
+		CHECK(rotw_inv(u) == t);
 		CHECK(seen.insert(u).second);
-		CHECK((((u >> 2) & 31) == (((t >> 2) + (t >> 7)) & 31))); // bank of B = bank of A + row
+		CHECK((u & 31) == ((t + rotw_amount(t >> 5)) & 31));
 	}
-	for (int t = 0; t < 4096; t++)
-		for (int s = t + 128; s < 4096; s += 128) { // same bank and byte in A, another row
-			int const bt = (rot_fwd(t) >> 2) & 31, bs = (rot_fwd(s) >> 2) & 31;
-			if (bt == bs) { std::printf("targets %d and %d share bank %d in both arrays\n", t, s, bt); return 1; }
-		}
+	// rows r and r + 1 .. r + 31 never rotate by the same amount; over the 160 rows of the largest tile at most 5 do
+	for (int r = 0; r < 160; r++) {
+		int same = 0;
+		for (int q = 0; q < 160; q++)
+			same += rotw_amount(q) == rotw_amount(r);
+		if (same > 5) { std::printf("row %d shares its rotation with %d rows\n", r, same); return 1; }
+		for (int q = r + 1; q < r + 32 && q < 160; q++)
+			if ((q >> 5) == (r >> 5) && rotw_amount(q) == rotw_amount(r)) { std::printf("rows %d and %d\n", r, q); return 1; }
+	}
 	std::puts("ok");
 	return 0;
 }
-''')
+""")
     exe = tmp_path / "rot"
     inc = ROOT / "spice2_b200" / "csrc"
     subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
