@@ -113,12 +113,12 @@ struct unit_view {
 	bool valid;
 };
 
-// One batch of 32 runs, one run per lane
+// One batch of this warp: 32 runs, one per lane — kQuarters stages of kRuns consecutive spikes each
 struct batch {
-	unsigned long long addr; // global address of this lane's run (its first group)
-	unsigned ng;             // its groups (0: no run)
-	unsigned seq;            // the unit (CTA sequence number) it belongs to — warp-uniform
-	bool valid;              // warp-uniform
+	char const* stream; // the connection's packed stream — warp-uniform
+	unsigned g0, ng;    // this lane's run: groups [g0, g0 + ng) of the stream (ng = 0: no run)
+	unsigned seq;       // the unit (CTA sequence number) it belongs to — warp-uniform
+	bool valid;         // warp-uniform
 };
 
 // Rare path, out of line: connections whose entries are plain columns (rows that may repeat a
@@ -140,8 +140,22 @@ __device__ __noinline__ unsigned long long walk_plain(conn_desc const& C, int k,
 	return ev;
 }
 
-template <int kW, int kStages>
+// The spikes of a unit's step are handed to the CTA's warps in QUARTERS of kRuns consecutive spikes, round robin
+// (quarter Q goes to warp Q % kW), so the warps' shares of a unit differ by at most one quarter; a warp's batch b is its
+// quarters 4 b .. 4 b + 3: lane l holds spike kRuns * (warp + kW * (4 b + l / kRuns)) + l % kRuns of the list.
+template <int kW>
+__device__ __forceinline__ unsigned warp_batches(unsigned total, int warp) {
+	unsigned const nq = (total + kRuns - 1) / kRuns;                                       // quarters of the unit
+	unsigned const mine = nq > static_cast<unsigned>(warp) ? (nq - warp + kW - 1) / kW : 0; // quarters of this warp
+	return (mine + kQuarters - 1) / kQuarters;
+}
+
+// kBulk = true: a run is fetched by its lane with one cp.async.bulk (1-D TMA) against the stage's mbarrier;
+// kBulk = false: by the whole warp with one 16-byte cp.async per lane (LDGSTS), stages = commit groups.  Either way
+// the run lands in shared memory and nothing waits on a register scoreboard.
+template <int kW, int kStages, bool kBulk>
 __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_args a) {
+	static_assert(kStages == 2 || kStages == 4, "the stage slots and mbarrier phases below are static for 2 or 4 stages");
 	extern __shared__ uint4 smem4[];
 	__shared__ cta_state<kW, kStages> sh;
 	int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -188,24 +202,23 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	// ---- per-warp pipeline state -------------------------------------------------------------------------
 	unsigned done = 0; // units of this CTA merged so far = the unit being counted
 	// cursor: the next batch of this warp whose spike ids have not been requested yet
-	unsigned cs_seq = 0, cs_b = warp, cs_total = 0, cs_nbatch = 0;
+	unsigned cs_seq = 0, cs_b = 0, cs_total = 0, cs_nbatch = 0;
 	bool cs_known = false, cs_end = false;
 	std::int32_t const* cs_ids = nullptr;
 	unsigned const* cs_gp      = nullptr;
 	int cs_stride              = 0;
 	char const* cs_stream      = nullptr;
-	// ids requested (stage I), run pointers requested (stage P = nxt), runs being fetched and counted (cur)
+	// spike ids requested (idn), run pointers requested (nxt), runs being fetched and counted (cur)
 	bool id_valid = false;
 	unsigned id_seq = 0;
 	std::int32_t id_src = -1;
 	unsigned const* id_gp = nullptr;
 	int id_stride         = 0;
 	char const* id_stream = nullptr;
-	batch nxt{0, 0, 0, false}, cur{0, 0, 0, false};
-	unsigned q_cnt = 0;              // quarters of cur counted
-	unsigned q_cur = 0, q_nxt = 0;   // quarters of cur / nxt whose copies have been issued
-	unsigned n_issue = 0, n_count = 0; // stages issued / counted by this warp since the kernel began
-	unsigned long long ev = 0;       // Syn::deliver invocations this thread has merged
+	batch nxt{nullptr, 0, 0, 0, false}, cur{nullptr, 0, 0, 0, false};
+	unsigned q_cur = 0;        // quarters of cur whose copies have been issued (kStages in the steady state)
+	unsigned parity = 0;       // kStages == 4: the mbarriers' phase of the batch being counted
+	unsigned long long ev = 0; // Syn::deliver invocations this thread has merged
 
 	auto cursor_next = [&](unsigned& seq_out, unsigned& b_out) -> bool {
 		for (;;) {
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				}
 				long long const slot = (a.t0 + v.s) % a.ring;
 				cs_total  = v.total;
-				cs_nbatch = v.C->arranged ? (v.total + 31) / 32 : 0; // plain units are walked at their merge
+				cs_nbatch = v.C->arranged ? warp_batches<kW>(v.total, warp) : 0; // plain units are walked at their merge
 				cs_ids    = v.C->ring_ids + slot * v.C->ring_cap;
 				cs_gp     = v.C->run_ptr + v.k;
 				cs_stride = v.C->tiles;
@@ -228,43 +241,38 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			}
 			if (cs_b < cs_nbatch) {
 				seq_out = cs_seq;
-				b_out   = cs_b;
-				cs_b += kW;
+				b_out   = cs_b++;
 				return true;
 			}
 			cs_seq++;
-			cs_b     = warp;
+			cs_b     = 0;
 			cs_known = false;
 		}
 	};
-	// keep the three prefetch stages full: ids -> run pointers -> (cur)
+	// move every prefetch stage forward as far as it goes: ids -> run pointers (nxt) -> cur.  Once per batch.
 	auto refill = [&]() {
 #pragma unroll
 		for (int pass = 0; pass < 3; pass++) {
 			if (!cur.valid && nxt.valid) {
 				cur       = nxt;
-				q_cnt     = 0;
-				q_cur     = q_nxt;
-				q_nxt     = 0;
 				nxt.valid = false;
 			}
 			if (!nxt.valid && id_valid) {
-				nxt.valid = true;
-				nxt.seq   = id_seq;
-				nxt.ng    = 0;
-				nxt.addr  = 0;
+				nxt.valid  = true;
+				nxt.seq    = id_seq;
+				nxt.stream = id_stream;
+				nxt.g0 = nxt.ng = 0;
 				if (id_src >= 0) {
 					unsigned const* p = id_gp + static_cast<long long>(id_src) * id_stride;
-					unsigned const g0 = p[0];
-					nxt.ng            = p[1] - g0;
-					nxt.addr          = reinterpret_cast<unsigned long long>(id_stream) + static_cast<unsigned long long>(g0) * 16;
+					nxt.g0            = p[0];
+					nxt.ng            = p[1]; // end of the run for now: issue() and count_stage() subtract (the loads are still in flight)
 				}
 				id_valid = false;
 			}
 			if (!id_valid) {
 				unsigned seq, b;
 				if (cursor_next(seq, b)) {
-					unsigned const q = b * 32 + lane;
+					unsigned const q = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
 					id_valid  = true;
 					id_seq    = seq;
 					id_src    = q < cs_total ? cs_ids[q] : -1;
@@ -275,64 +283,64 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			}
 		}
 	};
-	// issue the copies of quarter `q` of batch `b` into the next free stage
-	auto issue = [&](batch const& b, unsigned q) {
-		unsigned const st  = n_issue % kStages;
-		unsigned const bar = bar0 + st * 8;
-		bool const mine    = (static_cast<unsigned>(lane) / kRuns) == q;
-		unsigned const bytes = mine ? min(b.ng, 32u) * 16 : 0;
-		unsigned const tot   = __reduce_add_sync(kFull, bytes);
-		if (lane == 0)
-			mbar_arrive_expect_tx(bar, tot);
-		__syncwarp();
-		if (bytes)
-			bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, reinterpret_cast<void const*>(b.addr), bytes, bar);
-		n_issue++;
-	};
-	auto issue_ahead = [&]() {
-		while (n_issue - n_count < kStages) {
-			if (cur.valid && q_cur < kQuarters)
-				issue(cur, q_cur++);
-			else if (nxt.valid && q_nxt < kQuarters)
-				issue(nxt, q_nxt++);
-			else
-				break;
+	// issue the copies of quarter q of batch b into stage slot `st`
+	auto issue = [&](batch const& b, unsigned q, unsigned st) {
+		if constexpr (kBulk) {
+			unsigned const bar   = bar0 + st * 8;
+			bool const mine      = (static_cast<unsigned>(lane) / kRuns) == q;
+			unsigned const bytes = mine ? min(b.ng - b.g0, 32u) * 16 : 0;
+			unsigned const tot   = __reduce_add_sync(kFull, bytes);
+			if (lane == 0)
+				mbar_arrive_expect_tx(bar, tot);
+			__syncwarp();
+			if (bytes)
+				bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, b.stream + static_cast<unsigned long long>(b.g0) * 16, bytes, bar);
+		} else {
+			unsigned const dst = ring + st * kStageBytes + lane * 16;
+			char const* src    = b.stream + lane * 16;
+#pragma unroll
+			for (int j = 0; j < kRuns; j++) {
+				unsigned const g0 = __shfl_sync(kFull, b.g0, q * kRuns + j);
+				unsigned const g1 = __shfl_sync(kFull, b.ng, q * kRuns + j);
+				if (static_cast<unsigned>(lane) < g1 - g0)
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * kSlotBytes), "l"(src + static_cast<unsigned long long>(g0) * 16) : "memory");
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 	};
-	// count quarter q_cnt of cur (its stage has been issued)
-	auto count_stage = [&]() {
-		unsigned const st = n_count % kStages;
-		mbar_wait(bar0 + st * 8, (n_count / kStages) & 1);
+	// count quarter q of cur, landed in stage slot `st`
+	auto count_stage = [&](unsigned q, unsigned st, unsigned ph) {
+		if constexpr (kBulk)
+			mbar_wait(bar0 + st * 8, ph);
+		else // groups complete in order: all but the kStages - 1 youngest have landed (each lane reads back only what it copied)
+			asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
 		unsigned const base = ring + st * kStageBytes + lane * 16;
+		unsigned const mine = cur.ng - cur.g0;
 		int4 v[kRuns];
 		unsigned n[kRuns];
 #pragma unroll
 		for (int j = 0; j < kRuns; j++) {
-			n[j] = __shfl_sync(kFull, cur.ng, q_cnt * kRuns + j);
-			v[j] = make_int4(-1, 0, 0, 0);
+			n[j] = __shfl_sync(kFull, mine, q * kRuns + j);
 			if (static_cast<unsigned>(lane) < n[j])
 				v[j] = lds128(base + j * kSlotBytes);
 		}
 		bool longer = false;
 #pragma unroll
 		for (int j = 0; j < kRuns; j++) {
-			if (v[j].x >= 0)
+			if (static_cast<unsigned>(lane) < n[j])
 				tally(cnt, v[j]);
 			longer |= n[j] > 32;
 		}
 		if (longer) { // a run of more than 32 groups (rare: tiles are sized for ~25): the rest straight from global memory
 #pragma unroll 1
 			for (int j = 0; j < kRuns; j++) {
-				unsigned long long const g = __shfl_sync(kFull, cur.addr, q_cnt * kRuns + j);
-				unsigned const nj          = __shfl_sync(kFull, cur.ng, q_cnt * kRuns + j);
+				unsigned const g0 = __shfl_sync(kFull, cur.g0, q * kRuns + j);
+				unsigned const nj = __shfl_sync(kFull, mine, q * kRuns + j);
 				for (unsigned off = 32 + lane; off < nj; off += 32)
-					tally(cnt, ldg_stream(reinterpret_cast<void const*>(g + static_cast<unsigned long long>(off) * 16)));
+					tally(cnt, ldg_stream(cur.stream + static_cast<unsigned long long>(g0 + off) * 16));
 			}
 		}
 		__syncwarp(); // every lane has read the stage's slots: they may be overwritten
-		n_count++;
-		if (++q_cnt == kQuarters)
-			cur.valid = false;
 	};
 	// end of unit `done`: all warps arrive; merge + zero the counters, store the tile's range; publish the next ticket
 	auto boundary = [&](unit_view const& U) {
@@ -385,19 +393,36 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		done++;
 	};
 
-	// ---- main loop ---------------------------------------------------------------------------------------
+	// ---- main loop: one iteration per batch of this warp ---------------------------------------------------
+	// Steady state: on entry the first kStages quarters of cur are in flight (issued while the previous batch was
+	// counted); quarter q is counted from stage slot q % kStages, and the slot is refilled at once with the quarter
+	// kStages further on — of cur, or of nxt.  A batch uses every slot 4 / kStages times, so slots and (for two
+	// stages) mbarrier phases are compile-time constants.
 	for (;;) {
 		refill();
-		issue_ahead();
-		if (cur.valid && cur.seq == done) {
-			count_stage();
+		if (!cur.valid || cur.seq != done) {
+			// nothing left for this warp in unit `done` (its next batch, if any, belongs to a later unit)
+			unit_view const U = view(done);
+			if (!U.valid)
+				break;
+			boundary(U);
 			continue;
 		}
-		// this warp has nothing left in unit `done` (its next batch, if any, belongs to a later unit)
-		unit_view const U = view(done);
-		if (!U.valid)
-			break;
-		boundary(U);
+		for (; q_cur < static_cast<unsigned>(kStages); q_cur++) // after a pipeline bubble only
+			issue(cur, q_cur, q_cur);
+#pragma unroll
+		for (int q = 0; q < kQuarters; q++) {
+			count_stage(q, q % kStages, kStages == 2 ? (q >> 1) & 1 : parity);
+			if (q + kStages < kQuarters)
+				issue(cur, q + kStages, q % kStages);
+			else if (nxt.valid)
+				issue(nxt, q + kStages - kQuarters, q % kStages);
+			else if constexpr (!kBulk) // keep the stage being counted kStages - 1 commit groups behind the youngest
+				asm volatile("cp.async.commit_group;" ::: "memory");
+		}
+		parity ^= 1;
+		q_cur     = nxt.valid ? kStages : 0;
+		cur.valid = false;
 	}
 	for (int off = 16; off; off >>= 1)
 		ev += __shfl_xor_sync(kFull, ev, off);
@@ -655,12 +680,14 @@ struct shape {
 };
 // two CTAs of 8 warps per SM (one merges while the other streams), or one of 16 warps: windows with few, long units
 // (a rank of a multi-GPU run sees every source but few target tiles)
-shape const kShapes[2] = {{deliver_units<8, 2>, 8, 2}, {deliver_units<16, 2>, 16, 2}};
+shape const kShapes[4] = {{deliver_units<8, 2, true>, 8, 2}, {deliver_units<16, 2, true>, 16, 2},
+                          {deliver_units<8, 2, false>, 8, 2}, {deliver_units<16, 2, false>, 16, 2}};
 }
 
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
-	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0);
-	static int blocks_per_sm[64][2] = {};
+	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
+	                 path_env = env_int("SPICE_DELIVER_PATH", 0); // 0: cp.async.bulk, 1: cp.async (experiment)
+	static int blocks_per_sm[64][4] = {};
 	static int sms[64]              = {};
 	static int smem_set[64]         = {};
 	if (device < 0 || device >= 64)
@@ -668,7 +695,7 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	if (a.nconns > kMaxConns || a.nsteps > spice::detail::kMaxWindow)
 		return static_cast<int>(cudaErrorInvalidValue);
 	if (smem_set[device] < a.tile_cap) {
-		for (int i = 0; i < 2; i++) {
+		for (int i = 0; i < 4; i++) {
 			size_t const smem = cta_smem(a.tile_cap, kShapes[i].warps, kShapes[i].stages);
 			cudaError_t e = cudaFuncSetAttribute(kShapes[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 			if (e != cudaSuccess)
@@ -692,6 +719,7 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	int which = units < 6ll * sms[device] * blocks_per_sm[device][0] ? 1 : 0;
 	if (warps_env == 8 || warps_env == 16)
 		which = warps_env == 16;
+	which += path_env == 1 ? 2 : 0;
 	shape const& S       = kShapes[which];
 	long long const full = static_cast<long long>(sms[device]) * blocks_per_sm[device][which];
 	int grid             = static_cast<int>(std::min<long long>(units, full));
@@ -706,7 +734,7 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 int preload() {
 	cudaFuncAttributes fa{};
 	cudaError_t e = cudaSuccess;
-	for (int i = 0; i < 2 && e == cudaSuccess; i++)
+	for (int i = 0; i < 4 && e == cudaSuccess; i++)
 		e = cudaFuncGetAttributes(&fa, kShapes[i].kernel);
 	return static_cast<int>(e);
 }
