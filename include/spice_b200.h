@@ -48,8 +48,11 @@ enum {
 	 * in connect() order: bit-exact with the reference's sequential float accumulation for
 	 * stateless synapses.  Stateful synapses are applied in (connection, source rank, row) order. */
 	SPICE_MODE_DETERMINISTIC = 0,
-	/* stateful synapses accumulate their float contributions with atomics (order not defined);
-	 * stateless synapses use the same integer counters as the deterministic mode. */
+	/* stateful synapses: the per-target event lists are filled with atomics and applied in arrival order, without the
+	 * sort into the reference's (source, row) order, so the order of a target's float accumulation is not defined:
+	 * membrane potentials agree with the deterministic mode to float rounding of the sums, firing rates within the
+	 * tolerance tests/test_gpu_sim.py::test_fast_mode_tolerances states.  Stateless synapses use the same integer
+	 * counters as the deterministic mode (already order-free and exact). */
 	SPICE_MODE_FAST = 1
 };
 

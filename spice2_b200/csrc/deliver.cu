@@ -101,23 +101,27 @@ template <int kW, int kStages>
 struct cta_state {
 	unsigned long long bars[kW][kStages];
 	unsigned tickets[kTicketRing];       // the CTA's unit sequence: tickets[seq % kTicketRing]
-	unsigned tot[kMaxConns * spice::detail::kMaxWindow]; // spikes of (connection, step)
+	unsigned cnts[kMaxCounts];           // spikes of (connection, step): world == 1 the total; else the inclusive prefix over ranks
 	int prefix[kMaxConns + 1];           // tile_prefix of the connections, + total_tiles
+	char const* stream[kMaxConns];       // the connections' packed streams ...
+	unsigned const* run_ptr[kMaxConns];  // ... run pointers ...
+	int tiles[kMaxConns];                // ... and tile counts
 };
 
 // A unit as a warp needs it (warp-uniform)
 struct unit_view {
 	conn_desc const* C;
-	int s, k;
+	int c, s, k;
+	int cs; // (connection, step) index
 	unsigned total;
 	bool valid;
 };
 
 // One batch of this warp: 32 runs, one per lane — kQuarters stages of kRuns consecutive spikes each
 struct batch {
-	char const* stream; // the connection's packed stream — warp-uniform
-	unsigned g0, ng;    // this lane's run: groups [g0, g0 + ng) of the stream (ng = 0: no run)
+	unsigned g0, ng;    // this lane's run: groups [g0, ng) of the connection's stream (ng == g0: no run)
 	unsigned seq;       // the unit (CTA sequence number) it belongs to — warp-uniform
+	int c;              // its connection — warp-uniform
 	bool valid;         // warp-uniform
 };
 
@@ -166,12 +170,39 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	unsigned const bar0   = smem_u32(&sh.bars[warp][0]);
 
 	// ---- CTA prologue -----------------------------------------------------------------------------------
-	for (int i = tid; i < a.nconns * a.nsteps; i += kW * 32) {
-		conn_desc const& C = a.conns[i / a.nsteps];
-		sh.tot[i]          = C.ring_cnt[((a.t0 + i % a.nsteps) % a.ring) * C.cnt_stride];
+	int const world = a.world;
+	if (a.flags) { // several ranks: every peer's spikes of this window have landed in this rank's ring (NVLink peer stores)
+		if (tid < world) {
+			volatile unsigned long long const* f = a.flags + tid;
+			long long const start                = clock64();
+			while (*f < a.seq) {
+				if (clock64() - start > 20000000000ll) { // ~10 s: a peer died; do not hang the GPU
+					atomicOr(a.error, 1);
+					break;
+				}
+				__nanosleep(100);
+			}
+			__threadfence_system();
+		}
+		__syncthreads();
 	}
-	for (int i = tid; i <= a.nconns; i += kW * 32)
+	for (int i = tid; i < a.nconns * a.nsteps; i += kW * 32) {
+		conn_desc const& C        = a.conns[i / a.nsteps];
+		std::uint32_t const* from = C.ring_cnt + ((a.t0 + i % a.nsteps) % a.ring) * C.cnt_stride;
+		unsigned run              = 0;
+		for (int r = 0; r < world; r++) {
+			run += world > 1 ? *reinterpret_cast<volatile std::uint32_t const*>(from + r) : from[r];
+			sh.cnts[i * world + r] = run;
+		}
+	}
+	for (int i = tid; i <= a.nconns; i += kW * 32) {
 		sh.prefix[i] = i < a.nconns ? a.conns[i].tile_prefix : a.total_tiles;
+		if (i < a.nconns) {
+			sh.stream[i]  = reinterpret_cast<char const*>(a.conns[i].packed);
+			sh.run_ptr[i] = a.conns[i].run_ptr;
+			sh.tiles[i]   = a.conns[i].tiles;
+		}
+	}
 	if (tid < kTicketRing)
 		sh.tickets[tid] = tid < kStaticUnits ? static_ticket(blockIdx.x, gridDim.x, tid) : 0xffffffffu;
 	for (int i = tid; i < (cnt_words + 3) / 4; i += kW * 32)
@@ -192,9 +223,11 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		if (v.valid) {
 			unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
 			v.C     = a.conns + p.c;
+			v.c     = p.c;
 			v.s     = p.s;
 			v.k     = p.k;
-			v.total = sh.tot[p.c * a.nsteps + p.s];
+			v.total = sh.cnts[(p.c * a.nsteps + p.s) * world + world - 1];
+			v.cs    = p.c * a.nsteps + p.s;
 		}
 		return v;
 	};
@@ -205,17 +238,14 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	unsigned cs_seq = 0, cs_b = 0, cs_total = 0, cs_nbatch = 0;
 	bool cs_known = false, cs_end = false;
 	std::int32_t const* cs_ids = nullptr;
-	unsigned const* cs_gp      = nullptr;
-	int cs_stride              = 0;
-	char const* cs_stream      = nullptr;
+	std::int32_t const* cs_seg = nullptr; // several ranks: the source population's segment starts
+	int cs_cs = 0, cs_c = 0, cs_k = 0;
 	// spike ids requested (idn), run pointers requested (nxt), runs being fetched and counted (cur)
 	bool id_valid = false;
 	unsigned id_seq = 0;
 	std::int32_t id_src = -1;
-	unsigned const* id_gp = nullptr;
-	int id_stride         = 0;
-	char const* id_stream = nullptr;
-	batch nxt{nullptr, 0, 0, 0, false}, cur{nullptr, 0, 0, 0, false};
+	int id_c = 0, id_k = 0;
+	batch nxt{0, 0, 0, 0, false}, cur{0, 0, 0, 0, false};
 	unsigned q_cur = 0;        // quarters of cur whose copies have been issued (kStages in the steady state)
 	unsigned parity = 0;       // kStages == 4: the mbarriers' phase of the batch being counted
 	unsigned long long ev = 0; // Syn::deliver invocations this thread has merged
@@ -234,9 +264,10 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				cs_total  = v.total;
 				cs_nbatch = v.C->arranged ? warp_batches<kW>(v.total, warp) : 0; // plain units are walked at their merge
 				cs_ids    = v.C->ring_ids + slot * v.C->ring_cap;
-				cs_gp     = v.C->run_ptr + v.k;
-				cs_stride = v.C->tiles;
-				cs_stream = reinterpret_cast<char const*>(v.C->packed);
+				cs_seg    = v.C->seg_lo;
+				cs_cs     = v.cs;
+				cs_c      = v.c;
+				cs_k      = v.k;
 				cs_known  = true;
 			}
 			if (cs_b < cs_nbatch) {
@@ -260,10 +291,10 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			if (!nxt.valid && id_valid) {
 				nxt.valid  = true;
 				nxt.seq    = id_seq;
-				nxt.stream = id_stream;
+				nxt.c      = id_c;
 				nxt.g0 = nxt.ng = 0;
 				if (id_src >= 0) {
-					unsigned const* p = id_gp + static_cast<long long>(id_src) * id_stride;
+					unsigned const* p = sh.run_ptr[id_c] + (static_cast<long long>(id_src) * sh.tiles[id_c] + id_k);
 					nxt.g0            = p[0];
 					nxt.ng            = p[1]; // end of the run for now: issue() and count_stage() subtract (the loads are still in flight)
 				}
@@ -275,10 +306,20 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 					unsigned const q = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
 					id_valid  = true;
 					id_seq    = seq;
-					id_src    = q < cs_total ? cs_ids[q] : -1;
-					id_gp     = cs_gp;
-					id_stride = cs_stride;
-					id_stream = cs_stream;
+					id_src    = -1;
+					if (q < cs_total) {
+						if (world == 1)
+							id_src = cs_ids[q];
+						else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
+							unsigned const* pre = sh.cnts + cs_cs * world;
+							int r               = 0;
+							while (pre[r] <= q)
+								r++;
+							id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + cs_seg[r] + (q - (r ? pre[r - 1] : 0u)));
+						}
+					}
+					id_c      = cs_c;
+					id_k      = cs_k;
 				}
 			}
 		}
@@ -294,10 +335,10 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				mbar_arrive_expect_tx(bar, tot);
 			__syncwarp();
 			if (bytes)
-				bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, b.stream + static_cast<unsigned long long>(b.g0) * 16, bytes, bar);
+				bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, sh.stream[b.c] + static_cast<unsigned long long>(b.g0) * 16, bytes, bar);
 		} else {
 			unsigned const dst = ring + st * kStageBytes + lane * 16;
-			char const* src    = b.stream + lane * 16;
+			char const* src    = sh.stream[b.c] + lane * 16;
 #pragma unroll
 			for (int j = 0; j < kRuns; j++) {
 				unsigned const g0 = __shfl_sync(kFull, b.g0, q * kRuns + j);
@@ -316,20 +357,23 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
 		unsigned const base = ring + st * kStageBytes + lane * 16;
 		unsigned const mine = cur.ng - cur.g0;
-		int4 v[kRuns];
-		unsigned n[kRuns];
-#pragma unroll
-		for (int j = 0; j < kRuns; j++) {
-			n[j] = __shfl_sync(kFull, mine, q * kRuns + j);
-			if (static_cast<unsigned>(lane) < n[j])
-				v[j] = lds128(base + j * kSlotBytes);
-		}
 		bool longer = false;
 #pragma unroll
-		for (int j = 0; j < kRuns; j++) {
-			if (static_cast<unsigned>(lane) < n[j])
-				tally(cnt, v[j]);
-			longer |= n[j] > 32;
+		for (int h = 0; h < kRuns; h += 4) { // four runs at a time: their groups are read back, then counted
+			int4 v[4];
+			unsigned n[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				n[j] = __shfl_sync(kFull, mine, q * kRuns + h + j);
+				if (static_cast<unsigned>(lane) < n[j])
+					v[j] = lds128(base + (h + j) * kSlotBytes);
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (static_cast<unsigned>(lane) < n[j])
+					tally(cnt, v[j]);
+				longer |= n[j] > 32;
+			}
 		}
 		if (longer) { // a run of more than 32 groups (rare: tiles are sized for ~25): the rest straight from global memory
 #pragma unroll 1
@@ -337,7 +381,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				unsigned const g0 = __shfl_sync(kFull, cur.g0, q * kRuns + j);
 				unsigned const nj = __shfl_sync(kFull, mine, q * kRuns + j);
 				for (unsigned off = 32 + lane; off < nj; off += 32)
-					tally(cnt, ldg_stream(cur.stream + static_cast<unsigned long long>(g0 + off) * 16));
+					tally(cnt, ldg_stream(sh.stream[cur.c] + static_cast<unsigned long long>(g0 + off) * 16));
 			}
 		}
 		__syncwarp(); // every lane has read the stage's slots: they may be overwritten
@@ -359,8 +403,15 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				o[i] = make_uint4(0, 0, 0, 0);
 			__threadfence_block();
 			__syncthreads();
-			if (U.total)
-				ev += walk_plain<kW>(C, U.k, C.ring_ids + ((a.t0 + U.s) % a.ring) * C.ring_cap, U.total, out, lo, lane, warp);
+			if (U.total) {
+				std::int32_t const* ids = C.ring_ids + ((a.t0 + U.s) % a.ring) * C.ring_cap;
+				unsigned before         = 0;
+				for (int r = 0; r < world; r++) { // one segment per rank (one rank: the whole list)
+					unsigned const upto = sh.cnts[U.cs * world + r];
+					ev += walk_plain<kW>(C, U.k, ids + (world > 1 ? C.seg_lo[r] : 0), upto - before, out, lo, lane, warp);
+					before = upto;
+				}
+			}
 		} else if (U.total == 0) {
 			for (int i = tid; i < quads; i += kW * 32)
 				o[i] = make_uint4(0, 0, 0, 0);
@@ -692,7 +743,7 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	static int smem_set[64]         = {};
 	if (device < 0 || device >= 64)
 		return static_cast<int>(cudaErrorInvalidDevice);
-	if (a.nconns > kMaxConns || a.nsteps > spice::detail::kMaxWindow)
+	if (a.nconns > kMaxConns || a.nsteps > spice::detail::kMaxWindow || a.nconns * a.nsteps * a.world > kMaxCounts)
 		return static_cast<int>(cudaErrorInvalidValue);
 	if (smem_set[device] < a.tile_cap) {
 		for (int i = 0; i < 4; i++) {

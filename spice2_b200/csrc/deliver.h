@@ -12,13 +12,15 @@ constexpr int kTileMax = 5120; // targets per tile: a CTA keeps two u32 counters
 // One connection as the delivery kernel sees it (lives in device memory, one array per context,
 // in schedule order: heaviest connections first).
 struct conn_desc {
-	// spike lists of the SOURCE population, one per ring slot, flat: ids[slot * ring_cap .. + cnt[slot * cnt_stride]).
-	// One rank: the spike ring itself; several ranks: the ring's per-rank segments concatenated once per window
-	// (flatten_window in runtime.cu), so the kernel never deals with segments.
+	// spike lists of the SOURCE population, one per ring slot.  tiles_args::world == 1: flat,
+	// ids[slot * ring_cap .. + cnt[slot * cnt_stride]).  Several ranks: one segment per rank inside the slot, rank r's
+	// spikes at ids[slot * ring_cap + seg_lo[r] ..], their number at cnt[slot * cnt_stride + r] (cnt_stride == world):
+	// the spike ring as the update kernels and the peers' stores leave it.
 	std::int32_t const* ring_ids;
 	std::uint32_t const* ring_cnt;
 	long long ring_cap;
 	long long cnt_stride;
+	std::int32_t seg_lo[spice::detail::kMaxWorld]; // first neuron of each rank's range in the source population
 	std::int32_t const* packed;    // arranged connections: the delivery stream (see pack_runs)
 	unsigned const* run_ptr;       // arranged connections: [src * tiles + 1] first 16-byte group of every run
 	std::int32_t const* neighbors; // plain connections: CSR entries (local columns)
@@ -47,9 +49,13 @@ struct tiles_args {
 	unsigned long long* stats; // [0] events, [1] spikes
 	int* error;                // bit 16: internal error in the delivery kernel
 	int tile_cap;              // targets per counter array (max conns[].tile rounded up to 128)
+	// several ranks: the launch itself waits until every peer has published window `seq` (runtime.cu publish_window)
+	unsigned long long const* flags; // this rank's flag array [world], or null
+	unsigned long long seq;
 };
 
-constexpr int kMaxConns = 32; // connections per launch (their per-step spike totals are staged in shared memory)
+constexpr int kMaxConns  = 32;   // connections per launch
+constexpr int kMaxCounts = 1536; // nconns * nsteps * world spike counts staged in shared memory per launch
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
 // (k = tiles: the row end).  Returns a cudaError_t as int.

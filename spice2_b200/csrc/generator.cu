@@ -6,22 +6,28 @@
 // index reaches max_degree), and that terminating draw is discarded.  Row r therefore starts at
 // stream position sum_{r'<r} (deg_r' + 1): data dependent, which is what makes the loop serial.
 //
-// B200 design — four kernels per chunk of the stream:
-//   A  fp_values   : every stream position in parallel: jump-ahead into the stream (GF(2)
-//                    polynomials, spice/util/random.h), u -> y = log(u) with the bit-exact
-//                    glibc restatement (spice/detail/glibc_log.h), stored as f64; plus exact
-//                    fixed-point block sums of y.
-//   S  fp_segscan  : exclusive scan of the per-segment sums.
-//   B  fp_orbit    : the only sequential part: one warp hops from row start to row start using
-//                    the prefix sums (32 candidate end positions per ballot).  A hop is decided
-//                    from interval bounds on round(noise); if the bounds disagree (probability
-//                    ~1e-8 per row) one lane replays that row with the exact recurrence.
-//   C  fp_rows     : one thread per row replays the reference's exact float recurrence
-//                    noise = fma(y, c, noise); dst = index + trunc(noise + 0.49999999999999994)
-//                    over its row, writes the row, and CHECKS that it ends exactly where the
-//                    orbit said the next row starts.  By induction from row 0 the adjacency is
-//                    then bit-identical to the sequential algorithm; any failed check is reported
-//                    (SPICE_ERR_INTERNAL), never papered over.
+// B200 design — per chunk of the stream:
+//   J  fp_checkpoints : engine states every 1024 positions by polynomial jump (GF(2), spice/util/random.h).
+//   A  fp_values      : every stream position in parallel: u -> y = log(u) with the bit-exact glibc restatement
+//                       (spice/detail/glibc_log.h), stored as f64; plus exact fixed-point block sums of y.
+//   S  fp_segscan     : exclusive scan of the per-segment sums, so that the exact prefix Q(t) = sum_{i<t} q(y_i) of
+//                       any position is one block base plus a warp scan of 32 values.
+//   N  fp_next        : for EVERY position s of the chunk, where the row that starts at s ends.  With
+//                       Z(t) = t K - Q(t + 1) (K = 2^F / scale, an integer) the row from s ends at the first t with
+//                       Z(t) - (s K - Q(s)) >= C: Z is increasing, so next(s) = end + 1 is a lower bound in a sorted
+//                       array and non-decreasing in s — a warp sweeps 1024 consecutive starts with a sliding window.
+//                       C comes in two flavours from interval bounds on round(noise); where they disagree (~1e-8 of
+//                       the positions) the entry is marked and decided by an exact replay if the orbit ever lands on it.
+//   D  fp_double      : next^(2) .. next^(kHop) by pointer doubling; next is monotone, so the gathers are nearly coalesced.
+//   B  fp_chase       : the only sequential part: one thread follows next^(kHop) from the chunk's first row start,
+//                       one dependent load per kHop rows.
+//   F  fp_fill        : the kHop - 1 row starts between two anchors of the chase, one thread per anchor.
+//   C  fp_rows        : element-parallel: entry n of a row is n + round(noise_n), and noise_n is known from the prefix
+//                       sums to within delta; where that decides the rounding (all but ~1e-6 of the entries) the entry
+//                       is written at once, coalesced.  A row with an undecided entry is replayed by one thread with
+//                       the reference's exact float recurrence (fp_rows_exact).  Every row is CHECKED: no entry before
+//                       its end may terminate it, its terminating draw must; any failed check is reported
+//                       (SPICE_ERR_INTERNAL), never papered over.
 //
 // Floating-point forms are those of the reference build (g++ 13.3 -O2 -ffast-math
 // -march=haswell), taken from its disassembly (DESIGN.md lists them).
@@ -30,6 +36,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +51,11 @@ constexpr int kSeg        = 1024;        // stream positions generated sequentia
 constexpr int kBlk        = 32;          // positions per prefix-sum block (one warp ballot)
 constexpr int kWarpSpan   = 32 * kSeg;   // positions covered by one warp of fp_values
 constexpr int kGroupSegs  = 4;           // segments whose checkpoints one fp_checkpoints thread steps through
+constexpr int kHopLog     = 5;           // the chase follows next^(2^kHopLog)
+constexpr int kHop        = 1 << kHopLog;
+constexpr unsigned kAmbig = 0x80000000u; // next[]: the end of the row could not be decided from the bounds
+constexpr unsigned kStop  = 0x40000000u; // next^(k)[]: fewer than k rows could be followed inside the chunk
+constexpr unsigned kPosMask = 0x3fffffffu;
 constexpr double kHalfLo  = 0x1.fffffffffffffp-2; // the reference build's round(): trunc(x + 0.49999999999999994)
 
 #define GEN_CUDA(expr)                                                                          \
@@ -68,7 +80,8 @@ struct params {
 	double inv_fix;            // 2^-F
 	double fix;                // 2^F
 	double delta;              // bound on |approximate - exact| noise
-	long long guess;           // draws that can be skipped safely before looking for a row end
+	long long K;               // round(2^F / scale): one draw's worth of index in units of the fixed-point sums
+	long long c_hi, c_lo;      // row end thresholds on Z(t) - Z'(s): may have ended (>= c_hi), has certainly ended (>= c_lo)
 };
 
 // ---- device helpers --------------------------------------------------------------------------
@@ -228,24 +241,13 @@ __global__ void __launch_bounds__(1024) fp_segscan(long long const* seg_sum, lon
 	}
 }
 
-// ---- kernel B: the orbit of row starts -------------------------------------------------------------
-struct orbit_state {
-	long long row;       // next row to start
-	long long pos;       // its stream position (global)
-	long long exact_rows; // rows decided by the exact replay
-	long long rows_done_in_chunk;
-};
-
-struct orbit_args {
-	params P;
+// ---- exact prefixes ---------------------------------------------------------------------------------
+struct prefix_view {
 	double const* y;
 	long long const* blk_local;
 	long long const* seg_base;
-	long long base;   // global position of y[0]
-	long long limit;  // rows starting at or after this global position belong to the next chunk
-	long long len;    // draws held in y (chunk + overlap)
-	long long* row_start; // [src + 1], global positions
-	orbit_state* st;
+	long long len; // draws held in y (chunk + overlap)
+	double fix;
 };
 
 __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
@@ -258,199 +260,376 @@ __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
 	return v;
 }
 
-__global__ void __launch_bounds__(32) fp_orbit(orbit_args a) {
-	int const lane   = threadIdx.x;
-	params const& P  = a.P;
-	long long row    = a.st->row;
-	long long s      = a.st->pos;
-	long long nexact = a.st->exact_rows;
-	long long const row0 = row;
+// Q(t + 1) = sum_{i <= t} q(y_i) for the 32 positions t = 32 blk + lane of one aligned block (chunk frame);
+// `own` receives q(y_t).  Positions at or behind `len` contribute nothing.
+__device__ __forceinline__ long long block_prefix(prefix_view const& V, long long blk, int lane, long long& own) {
+	long long const t = blk * kBlk + lane;
+	own               = t < V.len ? quantize(V.y[t], V.fix) : 0;
+	long long base    = 0;
+	if (blk * kBlk < V.len)
+		base = V.seg_base[(blk * kBlk) / kSeg] + V.blk_local[blk];
+	return base + warp_incl_scan(own, lane);
+}
 
-	// exact fixed-point prefix at position t (chunk frame): block base + partial block
-	auto prefix_at = [&](long long tl) {
-		long long const b = tl / kBlk;
-		long long const t = b * kBlk + lane;
-		long long q       = (t < tl) ? quantize(a.y[t], P.fix) : 0;
-		for (int off = 16; off; off >>= 1)
-			q += __shfl_xor_sync(0xffffffffu, q, off);
-		return a.seg_base[tl / kSeg] + a.blk_local[b] + q;
-	};
-	long long Ps = (row < P.src && s < a.limit) ? prefix_at(s - a.base) : 0;
+// Z(t) = t K - Q(t + 1) (and Z'(s) = s K - Q(s)) modulo 2^64: t K alone exceeds 64 bits over a chunk, but only differences
+// of nearby positions are ever compared, and those are small
+__device__ __forceinline__ long long zval(long long t, long long K, long long prefix) {
+	return static_cast<long long>(static_cast<unsigned long long>(t) * static_cast<unsigned long long>(K) - static_cast<unsigned long long>(prefix));
+}
+__device__ __forceinline__ long long zdiff(long long a, long long b) {
+	return static_cast<long long>(static_cast<unsigned long long>(a) - static_cast<unsigned long long>(b));
+}
 
-	while (row < P.src && s < a.limit) {
-		long long const sl  = s - a.base;
-		long long const sb  = sl / kBlk;
-		// scan forward block by block from a safe guess
-		long long blk     = (sl + P.guess) / kBlk;
-		bool first_block  = true;
-		long long e       = -1; // local position of the terminating draw
-		long long Pnext   = 0;
-		bool need_exact   = false;
-		{
-			// Coarse step: index + round(noise) never decreases along a row, so the row cannot have ended
-			// before a draw at which it provably has not.  Test the first draw of the next 32 blocks at
-			// once (one round trip instead of one per block) and start the fine scan in the block before
-			// the first one that may be past the end.
-			long long const B = blk + lane;
-			long long const t = B * kBlk;
-			bool may_be_past  = true;
-			if (t < a.len) {
-				may_be_past        = false;
-				long long const n  = t - sl;
-				if (n >= 0) {
-					long long const Pt = a.seg_base[t / kSeg] + a.blk_local[B] + quantize(a.y[t], P.fix); // P(t + 1)
-					double const v     = __dmul_rn(__dmul_rn(__ll2double_rn(Pt - Ps), P.inv_fix), P.c);
-					long long const rh = __double2ll_rd(v + P.delta + 0.5);
-					may_be_past        = (n >= P.max_degree) | (n + rh >= P.dst);
-				}
-			}
-			unsigned const m = __ballot_sync(0xffffffffu, may_be_past);
-			int const j      = m ? __ffs(m) - 1 : 32;
-			if (j >= 2) {
-				blk += j - 1;
-				first_block = false; // its first draw provably precedes the end
-			}
+// ---- kernel N: next(s) for every position of the chunk ------------------------------------------------------
+struct next_args {
+	params P;
+	prefix_view V;
+	long long ch;       // positions [0, ch) get an entry (multiple of kSeg)
+	unsigned* next;     // [ch]: (end of the row that starts at s) + 1, | kAmbig
+};
+
+constexpr int kWinBlocks = 5; // window of Z values a warp searches at a time: 160 positions
+
+__global__ void __launch_bounds__(128) fp_next(next_args a) {
+	__shared__ long long win_s[4][kWinBlocks * kBlk];
+	int const lane      = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	long long const seg = static_cast<long long>(blockIdx.x) * 4 + warp;
+	long long const s0  = seg * kSeg;
+	if (s0 >= a.ch)
+		return;
+	params const& P = a.P;
+	long long* win  = win_s[warp];
+	long long own;
+
+	// Z'(s0) = s0 K - Q(s0): s0 opens an aligned block, so Q(s0) is that block's base
+	long long const q_s0 = block_prefix(a.V, s0 / kBlk, lane, own) - own; // exclusive prefix of this lane's position
+	long long const zp0  = zval(s0, P.K, __shfl_sync(0xffffffffu, q_s0, 0));
+
+	// anchor: the first position of a block that certainly does not lie behind the end of the row from s0.
+	// 32-ary search over block starts: may_end(t) is monotone in t.
+	long long blk_lo = s0 / kBlk;                                   // known: the row has not ended before this block's first draw
+	long long span   = (P.max_degree + 2 * kBlk) / kBlk + 1;        // blocks that certainly contain the end
+	while (span > 1) {
+		long long const st = (span + 31) / 32;
+		long long const B  = blk_lo + static_cast<long long>(lane + 1) * st;
+		long long const t  = B * kBlk;
+		bool may_end       = true;
+		if (t < a.V.len) {
+			long long const p1 = a.V.seg_base[t / kSeg] + a.V.blk_local[B] + quantize(a.V.y[t], a.V.fix); // Q(t + 1)
+			may_end            = (zdiff(zval(t, P.K, p1), zp0) >= P.c_hi) | (t - s0 >= P.max_degree);
 		}
-		for (;;) {
-			long long const t  = blk * kBlk + lane;
-			long long const in = quantize(a.y[t], P.fix);
-			long long const Pt = a.seg_base[t / kSeg] + a.blk_local[blk] + warp_incl_scan(in, lane); // P(t+1)
-			long long const n  = t - sl; // index of this draw within the row
-			bool lo_true = false, hi_true = false;
-			if (n >= 0) {
-				double const v   = __dmul_rn(__dmul_rn(__ll2double_rn(Pt - Ps), P.inv_fix), P.c);
-				long long const rl = __double2ll_rd(v - P.delta + 0.5);
-				long long const rh = __double2ll_rd(v + P.delta + 0.5);
-				bool const cap     = n >= P.max_degree;
-				lo_true            = cap | (n + rl >= P.dst);
-				hi_true            = cap | (n + rh >= P.dst);
-			}
-			unsigned const mh = __ballot_sync(0xffffffffu, hi_true);
-			unsigned const ml = __ballot_sync(0xffffffffu, lo_true);
-			if (mh) {
-				int const fh = __ffs(mh) - 1;
-				int const fl = ml ? __ffs(ml) - 1 : 32;
-				long long const tf = blk * kBlk + fh;
-				if (first_block && tf > sl && fh == 0) {
-					// the guess overshot (or cannot be proven not to have): rescan from the row start
-					blk         = sb;
-					first_block = false;
-					continue;
-				}
-				if (fh != fl) {
-					need_exact = true;
-				} else {
-					e     = tf;
-					Pnext = __shfl_sync(0xffffffffu, Pt, fh);
-				}
-				break;
-			}
-			first_block = false;
-			blk++;
-		}
-		if (need_exact) {
-			// exact replay of this row by one lane (rare)
-			long long ee = 0;
-			if (lane == 0) {
-				double noise = 0;
-				int index = 0, dst = 0;
-				long long t = sl;
-				while (!row_step(a.y[t], P, noise, index, dst)) {
-					index++;
-					t++;
-				}
-				ee = t;
-			}
-			e = __shfl_sync(0xffffffffu, ee, 0);
-			nexact++;
-			Pnext = prefix_at(e + 1);
-		}
-		Ps = Pnext;
-		row++;
-		s = a.base + e + 1;
-		if (lane == 0)
-			a.row_start[row] = s;
+		unsigned const m = __ballot_sync(0xffffffffu, may_end);
+		int const j      = m ? __ffs(m) - 1 : 32;
+		blk_lo += static_cast<long long>(j) * st; // the last probed block start that is not an end
+		span = st;
 	}
-	if (lane == 0) {
-		a.st->row                = row;
-		a.st->pos                = s;
-		a.st->exact_rows         = nexact;
-		a.st->rows_done_in_chunk = row - row0;
+	long long anchor = blk_lo; // block index
+
+	for (int i = 0; i < kSeg / kBlk; i++) {
+		long long const s   = s0 + i * kBlk + lane;
+		long long const p1s = block_prefix(a.V, s / kBlk, lane, own);
+		long long const zp  = zval(s, P.K, p1s - own);
+		long long const cap = s + P.max_degree; // the draw at which index == max_degree ends the row whatever its value
+		long long e         = -1;
+		bool certain        = false;
+		for (;;) {
+			// Z of the window's positions
+#pragma unroll
+			for (int b = 0; b < kWinBlocks; b++) {
+				long long o2;
+				long long const p1 = block_prefix(a.V, anchor + b, lane, o2);
+				win[b * kBlk + lane] = zval((anchor + b) * kBlk + lane, P.K, p1);
+			}
+			__syncwarp();
+			long long const w0 = anchor * kBlk;
+			if (e < 0) {
+				// first j with win[j] - zp >= c_hi (wrap-safe: differences of nearby prefixes are small)
+				int lo = 0, hi = kWinBlocks * kBlk; // answer in [lo, hi]; hi = not in this window
+				while (lo < hi) {
+					int const mid = (lo + hi) >> 1;
+					if ((w0 + mid >= a.V.len) | (zdiff(win[mid], zp) >= P.c_hi)) // (nothing is looked for behind the chunk's draws)
+						hi = mid;
+					else
+						lo = mid + 1;
+				}
+				long long const t = w0 + lo;
+				if (lo < kWinBlocks * kBlk && t <= cap) {
+					e       = t;
+					certain = (zdiff(win[lo], zp) >= P.c_lo) | (t == cap);
+				} else if (cap < w0 + kWinBlocks * kBlk) {
+					e       = cap;
+					certain = true;
+				}
+			}
+			__syncwarp();
+			if (__all_sync(0xffffffffu, e >= 0))
+				break;
+			anchor += kWinBlocks; // someone's row runs on: the next window
+		}
+		a.next[s] = static_cast<unsigned>(e + 1) | (certain ? 0u : kAmbig);
+		// rows end in the order they start: the next batch's ends are not before this batch's last one
+		anchor = __shfl_sync(0xffffffffu, e, 31) / kBlk;
 	}
 }
 
-// ---- kernel C: rows ------------------------------------------------------------------------------------
-struct rows_args {
+// ---- kernel D: pointer doubling -------------------------------------------------------------------------------
+// out[s] = in[in[s]]: twice as many rows ahead.  kStop when that leaves the positions the chunk has entries for, or
+// crosses an undecided entry.
+__global__ void __launch_bounds__(256) fp_double(unsigned const* in, unsigned* out, long long ch) {
+	long long const s = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (s >= ch)
+		return;
+	unsigned const v = in[s];
+	unsigned r       = kStop;
+	if (!(v & (kAmbig | kStop)) && static_cast<long long>(v) < ch) {
+		unsigned const w = in[v];
+		if (!(w & (kAmbig | kStop)))
+			r = w;
+	}
+	out[s] = r;
+}
+
+// ---- kernel B: the orbit of row starts --------------------------------------------------------------------------
+struct orbit_state {
+	long long row;        // next row to start
+	long long pos;        // its stream position (global)
+	long long exact_rows; // rows whose end was decided by the exact replay
+	long long rows_done_in_chunk;
+	long long anchors;    // anchors written by this chunk's chase
+};
+
+struct chase_args {
 	params P;
 	double const* y;
+	unsigned const* next;  // one row ahead
+	unsigned const* hop;   // kHop rows ahead
+	long long base;        // global position of the chunk's first draw
+	long long ch;
+	long long* row_start;  // [src + 1], global positions
+	unsigned* anchor_pos;  // chunk-frame position of every kHop-th row start the chase passed ...
+	unsigned* anchor_row;  // ... and its row, relative to the chunk's first row
+	int* row_flag;         // [src]: 2 = the row's end came from the exact replay: fp_rows must not judge it by the bounds
+	orbit_state* st;
+};
+
+__global__ void __launch_bounds__(32) fp_chase(chase_args a) {
+	if (threadIdx.x != 0)
+		return;
+	params const& P      = a.P;
+	long long row        = a.st->row;
+	long long const row0 = row;
+	long long s          = a.st->pos - a.base;
+	long long nexact     = a.st->exact_rows;
+	long long na         = 0;
+	while (row < P.src && s < a.ch) {
+		unsigned const h = a.hop[s];
+		if (!(h & (kAmbig | kStop)) && row + kHop <= P.src) {
+			a.anchor_pos[na] = static_cast<unsigned>(s);
+			a.anchor_row[na] = static_cast<unsigned>(row - row0);
+			na++;
+			s = h;
+			row += kHop;
+			continue;
+		}
+		unsigned const v = a.next[s];
+		long long nx     = v & kPosMask;
+		if (v & kAmbig) { // the bounds could not tell where this row ends: replay it
+			double noise = 0;
+			int index = 0, dst = 0;
+			long long t = s;
+			while (!row_step(a.y[t], P, noise, index, dst)) {
+				index++;
+				t++;
+			}
+			nx = t + 1;
+			nexact++;
+			a.row_flag[row] = 2;
+		}
+		row++;
+		s                = nx;
+		a.row_start[row] = a.base + s;
+	}
+	a.st->row                = row;
+	a.st->pos                = a.base + s;
+	a.st->exact_rows         = nexact;
+	a.st->rows_done_in_chunk = row - row0;
+	a.st->anchors            = na;
+}
+
+// ---- kernel F: the row starts between two anchors ------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fp_fill(unsigned const* next, unsigned const* anchor_pos, unsigned const* anchor_row, long long anchors,
+                                               long long row0, long long base, long long* row_start) {
+	long long const j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (j >= anchors)
+		return;
+	unsigned p         = anchor_pos[j];
+	long long const r  = row0 + anchor_row[j];
+	for (int i = 1; i <= kHop; i++) {
+		p                = next[p] & kPosMask;
+		row_start[r + i] = base + p;
+	}
+}
+
+// ---- kernel C: rows, element-parallel ---------------------------------------------------------------------------------
+struct rows_args {
+	params P;
+	prefix_view V;
 	long long base;
 	long long const* row_start;
 	long long row_lo, row_hi;  // rows of this chunk
-	long long* degree;         // [src] local (kept-column) degree, written in count mode
+	long long* degree;         // [src] kept-column degree (count mode)
+	long long* below;          // [src] entries of the row left of col_lo (count mode writes, write mode reads); null: unfiltered
 	long long const* offsets;  // [src + 1] output offsets (write mode)
 	int* neighbors;
 	long long capacity;
+	int* row_flag;             // [src] != 0: the row is left to fp_rows_exact
+	long long* fix_list;       // rows left to fp_rows_exact by this launch ...
+	unsigned* fix_count;       // ... and their number
 	int* error;                // bit 0: self-check failed, bit 1: capacity exceeded
 	int write;                 // 0 = count kept columns, 1 = write
+	int warps_per_row;         // 1 or 4
 };
 
 __global__ void __launch_bounds__(128) fp_rows(rows_args a) {
-	long long const r = a.row_lo + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int const wpr  = a.warps_per_row;
+	long long const r = a.row_lo + static_cast<long long>(blockIdx.x) * (4 / wpr) + warp / wpr;
 	if (r >= a.row_hi)
 		return;
-	params const& P    = a.P;
-	long long const s  = a.row_start[r] - a.base;
-	long long const en = a.row_start[r + 1] - a.base - 1; // where the orbit says the terminating draw is
-	long long out      = a.write ? a.offsets[r] : 0;
-	long long kept     = 0;
-	double noise       = 0;
-	int index = 0, dst = 0;
-	long long t        = s;
-	double const* y    = a.y;
-	// The recurrence is sequential, its inputs are not: the draws are fetched 8 at a time, one batch
-	// ahead (a chunk holds only ~1,700 rows, so a dependent load per step would leave the kernel
-	// waiting on memory latency).  Reads past the row's end stay inside the chunk's overlap margin.
-	constexpr int kAhead = 16;
-	double cur[kAhead], nxt[kAhead];
-#pragma unroll
-	for (int i = 0; i < kAhead; i++)
-		cur[i] = y[t + i];
-	for (bool done = false; !done;) {
-#pragma unroll
-		for (int i = 0; i < kAhead; i++)
-			nxt[i] = y[t + kAhead + i];
-#pragma unroll
-		for (int i = 0; i < kAhead; i++) {
-			if (done)
-				continue;
-			if (row_step(cur[i], P, noise, index, dst)) {
-				done = true;
-				continue;
-			}
-			if (dst >= P.col_lo && dst < P.col_hi) {
-				if (a.write) {
-					if (out < a.capacity)
-						a.neighbors[out] = dst - static_cast<int>(P.col_lo);
-					out++;
-				}
-				kept++;
-			}
-			index++;
-			t++;
-			if (t > en) // would run past the orbit's row end: the check below reports it
-				done = true;
-		}
-#pragma unroll
-		for (int i = 0; i < kAhead; i++)
-			cur[i] = nxt[i];
+	int const sub = warp % wpr; // this warp's share: aligned blocks sub, sub + wpr, ... of the row
+	params const& P = a.P;
+	if (a.row_flag[r]) { // decided by the exact replay (now or in an earlier pass): not judged by the bounds
+		if (sub == 0 && lane == 0)
+			a.fix_list[atomicAdd(a.fix_count, 1u)] = r;
+		return;
 	}
-	if (t != en)
-		atomicOr(a.error, 1);
-	if (a.write) {
-		if (out > a.capacity)
-			atomicOr(a.error, 2);
-	} else
-		a.degree[r] = kept;
+	long long const s = a.row_start[r] - a.base;
+	long long const e = a.row_start[r + 1] - a.base - 1; // the terminating draw
+	long long own;
+	long long const p1s = block_prefix(a.V, s / kBlk, lane, own);
+	long long const qs  = __shfl_sync(0xffffffffu, p1s - own, static_cast<int>(s % kBlk));
+	long long const out0 = a.write ? a.offsets[r] - (a.below ? a.below[r] : 0) : 0; // entry n goes to out0 + n
+	long long kept = 0, left = 0;
+	bool ambiguous = false, bad = false;
+	for (long long blk = s / kBlk + sub; blk <= e / kBlk; blk += wpr) {
+		long long const p1 = block_prefix(a.V, blk, lane, own);
+		long long const t  = blk * kBlk + lane;
+		if (t < s || t > e)
+			continue;
+		long long const n  = t - s;
+		double const v     = __dmul_rn(__dmul_rn(__ll2double_rn(p1 - qs), P.inv_fix), P.c);
+		long long const rl = __double2ll_rd(v - P.delta + 0.5);
+		long long const rh = __double2ll_rd(v + P.delta + 0.5);
+		if (t == e) { // must end the row
+			bool const ends = (n >= P.max_degree) | (n + rh >= P.dst);
+			bad |= !ends;
+			continue;
+		}
+		bad |= (n >= P.max_degree) | (n + rh >= P.dst); // must not
+		ambiguous |= rl != rh;
+		long long const d = n + rl;
+		if (d < P.col_lo)
+			left++;
+		else if (d < P.col_hi) {
+			kept++;
+			if (a.write) {
+				if (out0 + n < a.capacity)
+					a.neighbors[out0 + n] = static_cast<int>(d - P.col_lo);
+				else
+					bad = true;
+			}
+		}
+	}
+	if (__any_sync(0xffffffffu, ambiguous)) {
+		// an entry whose rounding the bounds cannot decide: the whole row is replayed exactly
+		if (lane == 0 && atomicExch(a.row_flag + r, 1) == 0)
+			a.fix_list[atomicAdd(a.fix_count, 1u)] = r;
+		return;
+	}
+	if (__any_sync(0xffffffffu, bad))
+		if (lane == 0)
+			atomicOr(a.error, 1);
+	if (!a.write) {
+		for (int off = 16; off; off >>= 1) {
+			kept += __shfl_xor_sync(0xffffffffu, kept, off);
+			left += __shfl_xor_sync(0xffffffffu, left, off);
+		}
+		if (lane == 0) {
+			if (wpr == 1) {
+				a.degree[r] = kept;
+				a.below[r]  = left;
+			} else {
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.degree + r), static_cast<unsigned long long>(kept));
+				atomicAdd(reinterpret_cast<unsigned long long*>(a.below + r), static_cast<unsigned long long>(left));
+			}
+		}
+	}
+}
+
+// One thread per listed row replays the reference's exact float recurrence, writes (or counts) the row and checks that
+// it ends exactly where the orbit said the next row starts.
+__global__ void __launch_bounds__(128) fp_rows_exact(rows_args a) {
+	unsigned const nfix = *a.fix_count;
+	for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < nfix; f += gridDim.x * blockDim.x) {
+		long long const r  = a.fix_list[f];
+		params const& P    = a.P;
+		long long const s  = a.row_start[r] - a.base;
+		long long const en = a.row_start[r + 1] - a.base - 1; // where the orbit says the terminating draw is
+		long long out      = a.write ? a.offsets[r] : 0;
+		long long kept = 0, left = 0;
+		double noise       = 0;
+		int index = 0, dst = 0;
+		long long t        = s;
+		double const* y    = a.V.y;
+		// The recurrence is sequential, its inputs are not: the draws are fetched 16 at a time, one batch ahead.
+		// Reads past the row's end stay inside the chunk's overlap margin.
+		constexpr int kAhead = 16;
+		double cur[kAhead], nxt[kAhead];
+#pragma unroll
+		for (int i = 0; i < kAhead; i++)
+			cur[i] = y[t + i];
+		for (bool done = false; !done;) {
+#pragma unroll
+			for (int i = 0; i < kAhead; i++)
+				nxt[i] = y[t + kAhead + i];
+#pragma unroll
+			for (int i = 0; i < kAhead; i++) {
+				if (done)
+					continue;
+				if (row_step(cur[i], P, noise, index, dst)) {
+					done = true;
+					continue;
+				}
+				if (dst < P.col_lo)
+					left++;
+				else if (dst < P.col_hi) {
+					if (a.write) {
+						if (out < a.capacity)
+							a.neighbors[out] = dst - static_cast<int>(P.col_lo);
+						out++;
+					}
+					kept++;
+				}
+				index++;
+				t++;
+				if (t > en) // would run past the orbit's row end: the check below reports it
+					done = true;
+			}
+#pragma unroll
+			for (int i = 0; i < kAhead; i++)
+				cur[i] = nxt[i];
+		}
+		if (t != en)
+			atomicOr(a.error, 1);
+		if (a.write) {
+			if (out > a.capacity)
+				atomicOr(a.error, 2);
+		} else {
+			a.degree[r] = kept;
+			if (a.below)
+				a.below[r] = left;
+		}
+	}
 }
 
 // offsets = exclusive scan(degree) when columns are filtered; closed form otherwise
@@ -495,16 +674,58 @@ long long max_degree(long long dst, double p) {
 	return static_cast<long long>(std::fma(std::sqrt((1.0 - p) * dp), 3.0, dp)); // topology.cpp:75-78 as compiled
 }
 
+namespace {
+// p == 1: scale == 0, noise stays 0, every row is 0 .. min(dst, max_degree) - 1 and consumes one draw more than that
+__global__ void fp_dense_rows(long long src, long long row_len, long long col_lo, long long col_hi, long long* offsets, int* neighbors) {
+	long long const lo = min(col_lo, row_len), hi = min(col_hi, row_len);
+	long long const w  = hi - lo;
+	long long const i  = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i <= src)
+		offsets[i] = i * w;
+	if (i < src * w)
+		neighbors[i] = static_cast<int>(i % w + lo - col_lo);
+}
+
+// everything a generation allocates; released on every path out of generate_fixed_probability
+struct scratch {
+	std::vector<void*> dev;
+	std::vector<void*> host;
+	std::vector<cudaEvent_t> events;
+	template <class T>
+	cudaError_t alloc(T** p, size_t n) {
+		cudaError_t const e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n * sizeof(T), 16));
+		if (e == cudaSuccess)
+			dev.push_back(*p);
+		return e;
+	}
+	cudaError_t event(cudaEvent_t* e) {
+		cudaError_t const r = cudaEventCreate(e);
+		if (r == cudaSuccess)
+			events.push_back(*e);
+		return r;
+	}
+	~scratch() {
+		for (void* p : dev)
+			cudaFree(p);
+		for (void* p : host)
+			cudaFreeHost(p);
+		for (cudaEvent_t e : events)
+			cudaEventDestroy(e);
+	}
+};
+}
+
 int generate_fixed_probability(void* stream_, long long src, long long dst, double p, unsigned long long seed_lo,
                                unsigned long long seed_hi, long long col_lo, long long col_hi, long long chunk_draws,
                                result* out, std::string* err) {
 	auto stream = static_cast<cudaStream_t>(stream_);
 	*out        = result{};
+	scratch S; // frees the scratch buffers and events on every return below; the result's arrays belong to the caller
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-	GEN_CUDA(cudaEventCreate(&ev0));
-	GEN_CUDA(cudaEventCreate(&ev1));
-	GEN_CUDA(cudaEventCreate(&evr0));
-	GEN_CUDA(cudaEventCreate(&evr1));
+	GEN_CUDA(S.event(&ev0));
+	GEN_CUDA(S.event(&ev1));
+	GEN_CUDA(S.event(&evr0));
+	GEN_CUDA(S.event(&evr1));
 	GEN_CUDA(cudaEventRecord(ev0, stream));
 
 	GEN_CUDA(cudaMalloc(&out->offsets, sizeof(long long) * static_cast<size_t>(src + 1)));
@@ -527,26 +748,51 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 			*err = "fixed_probability: p too small for 32-bit target arithmetic";
 		return 3;
 	}
-	// fixed-point scale: |sum of y over one row| <= (max_degree + 1) * 36.8 must stay below 2^61
+	if (scale == 0) { // p == 1
+		long long const row_len = std::min(dst, P.max_degree);
+		long long const w       = std::min(col_hi, row_len) - std::min(col_lo, row_len);
+		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(std::max<long long>(src * w, 0) + 8)));
+		long long const n = std::max(src * w, src + 1);
+		fp_dense_rows<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, row_len, col_lo, col_hi, out->offsets, out->neighbors);
+		GEN_CUDA(cudaGetLastError());
+		GEN_CUDA(cudaEventRecord(ev1, stream));
+		GEN_CUDA(cudaStreamSynchronize(stream));
+		out->edges    = src * w;
+		out->draws    = src * (row_len + 1);
+		out->launches = 1;
+		cudaEventElapsedTime(&out->total_ms, ev0, ev1);
+		return 0;
+	}
+	// fixed-point scale 2^F of the prefix sums: |sum of y over one row| <= (max_degree + 1) * 36.8 must stay below 2^60,
+	// and so must dst * K, K = 2^F / scale (the row-end thresholds below)
 	int bits = 1;
 	while (std::ldexp(1.0, bits) < (static_cast<double>(P.max_degree) + 2.0) * 37.0)
 		bits++;
-	int const F = std::min(44, 60 - bits);
+	int F = std::min(44, 60 - bits);
+	while (F > 8 && (static_cast<double>(dst) + 2.0) * std::ldexp(1.0, F) / scale >= std::ldexp(1.0, 60))
+		F--;
 	P.fix       = std::ldexp(1.0, F);
 	P.inv_fix   = std::ldexp(1.0, -F);
 	double const nmax = static_cast<double>(P.max_degree) + 2.0;
 	// |float-sequential noise - exact sum|: <= n * ulp(dst)/2 ; quantisation: n * 2^-(F+1) * scale ; slack x4
 	P.delta = 4.0 * (nmax * (std::ldexp(static_cast<double>(dst) + scale * 37.0 + 64.0, -52) + std::ldexp(scale + 1.0, -(F + 1)))) + 1e-9;
+	if (!(P.delta < 0.125)) {
+		if (err)
+			*err = "fixed_probability: p too close to 1 for the prefix-sum bounds";
+		return 3;
+	}
 	{
-		double const mean = static_cast<double>(dst) * p;
-		double const sd   = std::sqrt(mean * (1.0 - p));
-		long long g       = static_cast<long long>(mean - 5.0 * sd) - 2 * kBlk;
-		P.guess           = std::max<long long>(0, std::min(g, P.max_degree - 2 * kBlk));
+		// n + round(noise) >= dst  <=>  noise >= dst - n - 0.5 (up to delta)  <=>  Z(t) - Z'(s) >= (dst - 0.5 -+ delta) K,
+		// evaluated with the integer K: the difference is at most n / 2 <= max_degree units, added as slack
+		long double const Kr = static_cast<long double>(P.fix) / static_cast<long double>(scale);
+		P.K    = static_cast<long long>(llroundl(Kr));
+		P.c_hi = static_cast<long long>(floorl((static_cast<long double>(dst) - 0.5L - static_cast<long double>(P.delta)) * Kr)) - P.max_degree - 4;
+		P.c_lo = static_cast<long long>(ceill((static_cast<long double>(dst) - 0.5L + static_cast<long double>(P.delta)) * Kr)) + P.max_degree + 4;
 	}
 
 	// expected stream length and output size
 	double const mean_deg = std::min(static_cast<double>(dst) * p + 1.0, static_cast<double>(P.max_degree));
-	long long const ov    = round_up(P.max_degree + 2 + 2 * kBlk, kSeg);
+	long long const ov    = round_up(P.max_degree + 2 + (kWinBlocks + 2) * kBlk, kSeg);
 	long long ch          = chunk_draws > 0 ? chunk_draws : (1ll << 26);
 	{
 		double const est = static_cast<double>(src) * (mean_deg + 1.0) * 1.02 + 65536.0;
@@ -555,6 +801,11 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	}
 	ch                  = round_up(std::max<long long>(ch, kWarpSpan), kWarpSpan);
 	long long const len = round_up(ch + ov, kWarpSpan);
+	if (len >= (1ll << 30)) {
+		if (err)
+			*err = "fixed_probability: chunk too long for 30-bit positions";
+		return 3;
+	}
 	long long const segs = len / kSeg;
 	long long const groups = (segs + kGroupSegs - 1) / kGroupSegs;
 
@@ -565,30 +816,50 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	capacity               = std::max<long long>(capacity, 1);
 
 	double* y            = nullptr;
-	long long *blk_local = nullptr, *seg_sum = nullptr, *seg_base = nullptr, *row_start = nullptr, *degree = nullptr;
+	long long *blk_local = nullptr, *seg_sum = nullptr, *seg_base = nullptr, *row_start = nullptr, *degree = nullptr, *below = nullptr,
+	          *fix_list  = nullptr;
+	unsigned *next = nullptr, *hop_a = nullptr, *hop_b = nullptr, *anchor_pos = nullptr, *anchor_row = nullptr, *fix_count = nullptr;
+	int* row_flag        = nullptr;
 	ulonglong2* ckpt     = nullptr;
 	orbit_state* st      = nullptr;
 	int* error           = nullptr;
 	orbit_state* st_host = nullptr;
 	bool const filtered  = !(col_lo == 0 && col_hi == dst);
-	GEN_CUDA(cudaMalloc(&y, sizeof(double) * static_cast<size_t>(len)));
-	GEN_CUDA(cudaMalloc(&blk_local, sizeof(long long) * static_cast<size_t>(len / kBlk)));
-	GEN_CUDA(cudaMalloc(&seg_sum, sizeof(long long) * static_cast<size_t>(segs)));
-	GEN_CUDA(cudaMalloc(&seg_base, sizeof(long long) * static_cast<size_t>(segs)));
-	GEN_CUDA(cudaMalloc(&ckpt, sizeof(ulonglong2) * static_cast<size_t>(groups * kGroupSegs)));
-	GEN_CUDA(cudaMalloc(&row_start, sizeof(long long) * static_cast<size_t>(src + 1)));
-	GEN_CUDA(cudaMalloc(&st, sizeof(orbit_state)));
-	GEN_CUDA(cudaMalloc(&error, sizeof(int)));
+	long long const max_anchors = ch / kHop + 2;
+	GEN_CUDA(S.alloc(&y, static_cast<size_t>(len)));
+	GEN_CUDA(S.alloc(&blk_local, static_cast<size_t>(len / kBlk)));
+	GEN_CUDA(S.alloc(&seg_sum, static_cast<size_t>(segs)));
+	GEN_CUDA(S.alloc(&seg_base, static_cast<size_t>(segs)));
+	GEN_CUDA(S.alloc(&ckpt, static_cast<size_t>(groups * kGroupSegs)));
+	GEN_CUDA(S.alloc(&row_start, static_cast<size_t>(src + 1)));
+	GEN_CUDA(S.alloc(&next, static_cast<size_t>(ch)));
+	GEN_CUDA(S.alloc(&hop_a, static_cast<size_t>(ch)));
+	GEN_CUDA(S.alloc(&hop_b, static_cast<size_t>(ch)));
+	GEN_CUDA(S.alloc(&anchor_pos, static_cast<size_t>(max_anchors)));
+	GEN_CUDA(S.alloc(&anchor_row, static_cast<size_t>(max_anchors)));
+	GEN_CUDA(S.alloc(&row_flag, static_cast<size_t>(src)));
+	GEN_CUDA(S.alloc(&fix_list, static_cast<size_t>(2 * src))); // a row is listed at most twice (by two of its warps)
+	GEN_CUDA(S.alloc(&fix_count, 1));
+	GEN_CUDA(S.alloc(&st, 1));
+	GEN_CUDA(S.alloc(&error, 1));
 	GEN_CUDA(cudaMallocHost(&st_host, sizeof(orbit_state)));
+	S.host.push_back(st_host);
 	GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(capacity + 8))); // +8: the delivery kernel reads whole 16-byte groups
-	if (filtered)
-		GEN_CUDA(cudaMalloc(&degree, sizeof(long long) * static_cast<size_t>(src)));
+	if (filtered) {
+		GEN_CUDA(S.alloc(&degree, static_cast<size_t>(src)));
+		GEN_CUDA(S.alloc(&below, static_cast<size_t>(src)));
+		GEN_CUDA(cudaMemsetAsync(degree, 0, sizeof(long long) * static_cast<size_t>(src), stream));
+		GEN_CUDA(cudaMemsetAsync(below, 0, sizeof(long long) * static_cast<size_t>(src), stream));
+	}
 	GEN_CUDA(cudaMemsetAsync(st, 0, sizeof(orbit_state), stream));
 	GEN_CUDA(cudaMemsetAsync(error, 0, sizeof(int), stream));
+	GEN_CUDA(cudaMemsetAsync(row_flag, 0, sizeof(int) * static_cast<size_t>(src), stream));
 	GEN_CUDA(cudaMemsetAsync(row_start, 0, sizeof(long long), stream)); // row 0 starts at position 0
 
 	{
 		static bool uploaded[64] = {};
+		static std::mutex upload_mutex; // generations of one network run concurrently (runtime.cu build_pending)
+		std::lock_guard<std::mutex> lock(upload_mutex);
 		int dev = 0;
 		GEN_CUDA(cudaGetDevice(&dev));
 		if (dev >= 0 && dev < 64 && !uploaded[dev]) {
@@ -617,36 +888,57 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	float rows_ms = 0;
 	long long row = 0, base = 0;
 	int launches = 0;
+	prefix_view const V{y, blk_local, seg_base, len, P.fix};
+	// rows of ~100 entries and more: four warps to a row; shorter ones: one
+	int const warps_per_row = mean_deg >= 256 ? 4 : 1;
 
 	auto run_values = [&](long long chunk_base) -> int {
 		ca.base_poly = to_dev(util::jump::xpow(static_cast<UInt>(chunk_base)));
 		fp_checkpoints<<<static_cast<int>((groups + 127) / 128), 128, 0, stream>>>(ca);
 		values_args va{ckpt, y, blk_local, seg_sum, segs, P.fix};
 		fp_values<<<static_cast<int>((segs / 32 + 3) / 4), 128, 0, stream>>>(va);
-		launches += 2;
+		fp_segscan<<<1, 1024, 0, stream>>>(seg_sum, seg_base, segs);
+		launches += 3;
 		return static_cast<int>(cudaGetLastError());
 	};
 	auto run_rows = [&](long long chunk_base, long long rlo, long long rhi, int write) -> int {
 		if (rhi <= rlo)
 			return 0;
-		rows_args ra{P, y, chunk_base, row_start, rlo, rhi, degree, out->offsets, out->neighbors, capacity, error, write};
+		rows_args ra{P,        V,        chunk_base, row_start, rlo,   rhi,   degree,       filtered ? below : nullptr, out->offsets, out->neighbors,
+		             capacity, row_flag, fix_list,   fix_count, error, write, warps_per_row};
+		cudaMemsetAsync(fix_count, 0, sizeof(unsigned), stream);
 		cudaEventRecord(evr0, stream);
-		fp_rows<<<static_cast<int>((rhi - rlo + 127) / 128), 128, 0, stream>>>(ra);
+		int const rows_per_cta = 4 / warps_per_row;
+		fp_rows<<<static_cast<unsigned>((rhi - rlo + rows_per_cta - 1) / rows_per_cta), 128, 0, stream>>>(ra);
+		fp_rows_exact<<<128, 128, 0, stream>>>(ra); // rows with an entry (or an end) the bounds could not decide: strided over the list
 		cudaEventRecord(evr1, stream);
-		launches++;
+		launches += 2;
 		return static_cast<int>(cudaGetLastError());
 	};
 
 	while (row < src) {
 		GEN_CUDA(static_cast<cudaError_t>(run_values(base)));
-		fp_segscan<<<1, 1024, 0, stream>>>(seg_sum, seg_base, segs);
-		orbit_args oa{P, y, blk_local, seg_base, base, base + ch, len, row_start, st};
-		fp_orbit<<<1, 32, 0, stream>>>(oa);
-		launches += 2;
+		next_args na{P, V, ch, next};
+		fp_next<<<static_cast<unsigned>((ch / kSeg + 3) / 4), 128, 0, stream>>>(na);
+		unsigned const dgrid = static_cast<unsigned>((ch + 255) / 256);
+		unsigned const* from = next;
+		for (int k = 0; k < kHopLog; k++) {
+			unsigned* to = (k & 1) ? hop_b : hop_a;
+			fp_double<<<dgrid, 256, 0, stream>>>(from, to, ch);
+			from = to;
+		}
+		chase_args cha{P, y, next, from, base, ch, row_start, anchor_pos, anchor_row, row_flag, st};
+		fp_chase<<<1, 32, 0, stream>>>(cha);
+		launches += 2 + kHopLog;
 		GEN_CUDA(cudaGetLastError());
 		GEN_CUDA(cudaMemcpyAsync(st_host, st, sizeof(orbit_state), cudaMemcpyDeviceToHost, stream));
 		GEN_CUDA(cudaStreamSynchronize(stream));
 		long long const rhi = st_host->row;
+		if (st_host->anchors > 0) {
+			fp_fill<<<static_cast<unsigned>((st_host->anchors + 127) / 128), 128, 0, stream>>>(next, anchor_pos, anchor_row, st_host->anchors, row, base,
+			                                                                                   row_start);
+			launches++;
+		}
 		if (!filtered) {
 			// offsets are a closed form of the row starts, so rows can be written right away
 			fp_offsets_closed_form<<<static_cast<int>((rhi - row + 1 + 255) / 256), 256, 0, stream>>>(row_start, out->offsets, row, rhi);
@@ -695,21 +987,6 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	out->launches = launches;
 	out->rows_ms  = rows_ms;
 	cudaEventElapsedTime(&out->total_ms, ev0, ev1);
-
-	cudaFree(y);
-	cudaFree(blk_local);
-	cudaFree(seg_sum);
-	cudaFree(seg_base);
-	cudaFree(ckpt);
-	cudaFree(row_start);
-	cudaFree(st);
-	cudaFree(error);
-	cudaFree(degree);
-	cudaFreeHost(st_host);
-	cudaEventDestroy(ev0);
-	cudaEventDestroy(ev1);
-	cudaEventDestroy(evr0);
-	cudaEventDestroy(evr1);
 
 	if (herr & 1) {
 		if (err)

@@ -26,8 +26,9 @@ using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
 
 // Device function applying the `n` events of one step that a stateful connection addressed to
 // one neuron: `list` holds the edge indices (arrival order); it is sorted ascending — the
-// reference's (source, row) order (synapse_population.h:88,99) — and Syn::deliver(synapse, neuron)
-// is called for each, reading the synapse state word-SoA (word w of edge e at syn[w*stride + e]).
+// reference's (source, row) order (synapse_population.h:88,99) — unless from->unordered (fast mode),
+// and Syn::deliver(synapse, neuron) is called for each, reading the synapse state word-SoA
+// (word w of edge e at syn[w*stride + e]).
 //
 // Synapses whose deliver() also takes the SOURCE neuron (concepts.h DeliverFromTo;
 // synapse_population.h:125-131) find it through `from`: the source of edge e is the row that holds e
@@ -38,6 +39,8 @@ struct from_ctx {
 	std::int64_t stride;
 	std::int64_t const* offsets; // CSR row offsets of the connection
 	std::int64_t n_src;
+	std::int32_t unordered;      // SPICE_MODE_FAST: apply the events in arrival order (their list was filled with atomics)
+	                             // instead of sorting them into the reference's (source, row) order first
 };
 using apply_events_fn = void (*)(void const* functor, void* neuron, std::uint32_t const* syn, std::int64_t syn_stride,
                                  std::int32_t* list, unsigned n, from_ctx const* from);

@@ -124,13 +124,14 @@ __device__ void apply_events_impl(void const* functor, void* neuron, std::uint32
 	if constexpr (StatefulSynapse<Syn>) {
 		using N = typename DstNeur::neuron;
 		using S = typename Syn::synapse;
-		for (unsigned i = 1; i < n; i++) { // insertion sort: ascending edge index = (source, row) order
-			std::int32_t const key = list[i];
-			int j                  = static_cast<int>(i) - 1;
-			for (; j >= 0 && list[j] > key; j--)
-				list[j + 1] = list[j];
-			list[j + 1] = key;
-		}
+		if (!from->unordered)
+			for (unsigned i = 1; i < n; i++) { // insertion sort: ascending edge index = (source, row) order
+				std::int32_t const key = list[i];
+				int j                  = static_cast<int>(i) - 1;
+				for (; j >= 0 && list[j] > key; j--)
+					list[j + 1] = list[j];
+				list[j + 1] = key;
+			}
 		Syn const f = *static_cast<Syn const*>(functor);
 		N nn        = *static_cast<N*>(neuron);
 		for (unsigned i = 0; i < n; i++) {

@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,7 @@
 #include <deque>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "deliver.h"
@@ -441,6 +443,11 @@ struct connection {
 	std::int32_t* evt_list    = nullptr;
 	long long evt_cap         = 0;
 	apply_events_fn apply_events = nullptr;
+	// fixed_probability connections are generated when the network is finalized, all of them concurrently
+	bool pending_fp  = false;
+	double fp_p      = 0;
+	UInt128 fp_seed{0, 0};   // the graph's seed (synapse_population.h:31), drawn at connect() time
+	UInt128 init_seed{0, 0}; // the per-synapse init hook's (synapse_population.h:35), drawn right behind it
 };
 
 struct host_spikes {
@@ -482,6 +489,8 @@ struct spice_ctx {
 
 	// delivery
 	bool tiled                        = true;    // SPICE_DELIVER=atomic selects the one-atomic-per-event kernel
+	bool direct_segments              = false;   // several ranks: the delivery kernel reads the ring's per-rank segments itself
+	                                             // and waits for the peers' flags (no wait_window / flatten_window launches)
 	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
 	unsigned* d_work                  = nullptr;
 	int total_tiles = 0, tile_cap = 0, n_desc = 0;
@@ -569,10 +578,100 @@ struct peer_blob {
 	cudaIpcMemHandle_t handle;
 };
 
+int init_synapses(spice_ctx* ctx, connection* c);
+
+// SPICE_BUILD_TIMING=1: wall-clock of the build phases on stderr
+struct build_clock {
+	bool on = std::getenv("SPICE_BUILD_TIMING") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void lap(char const* what) {
+		if (!on)
+			return;
+		auto const t1 = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[spice build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+
+// Generate every pending fixed_probability connection: one host thread and one stream per connection, so the
+// sequential part of each generation (one thread chasing row starts, generator.cu) overlaps the parallel parts
+// of the others.
+int build_pending(spice_ctx* ctx) {
+	std::vector<int> todo;
+	for (size_t ci = 0; ci < ctx->conns.size(); ci++)
+		if (ctx->conns[ci].pending_fp)
+			todo.push_back(static_cast<int>(ci));
+	if (todo.empty())
+		return SPICE_OK;
+	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	struct job {
+		int rc = 0;
+		std::string err;
+		gen::result r;
+	};
+	std::vector<job> jobs(todo.size());
+	bool const serial = std::getenv("SPICE_SERIAL_BUILD") != nullptr;
+	auto run = [&](size_t j) {
+		connection& c         = ctx->conns[static_cast<size_t>(todo[j])];
+		population const& src = ctx->pops[c.src];
+		population const& dst = ctx->pops[c.dst];
+		cudaStream_t st       = nullptr;
+		if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+			jobs[j].rc  = SPICE_ERR_CUDA;
+			jobs[j].err = "cannot create a stream for synapse generation";
+			return;
+		}
+		jobs[j].rc = gen::generate_fixed_probability(st, src.size, dst.size, c.fp_p, c.fp_seed.lo, c.fp_seed.hi, dst.lo, dst.hi, 0, &jobs[j].r,
+		                                             &jobs[j].err);
+		cudaStreamDestroy(st);
+	};
+	if (serial || todo.size() == 1)
+		for (size_t j = 0; j < todo.size(); j++)
+			run(j);
+	else {
+		std::vector<std::thread> threads;
+		for (size_t j = 0; j < todo.size(); j++)
+			threads.emplace_back(run, j);
+		for (auto& t : threads)
+			t.join();
+	}
+	int rc = SPICE_OK;
+	for (size_t j = 0; j < todo.size(); j++) {
+		connection& c = ctx->conns[static_cast<size_t>(todo[j])];
+		c.pending_fp  = false;
+		if (jobs[j].rc != 0) {
+			cudaFree(jobs[j].r.offsets);
+			cudaFree(jobs[j].r.neighbors);
+			if (rc == SPICE_OK)
+				rc = fail(ctx, jobs[j].rc, jobs[j].err);
+			continue;
+		}
+		c.offsets   = jobs[j].r.offsets;
+		c.neighbors = jobs[j].r.neighbors;
+		c.edges     = jobs[j].r.edges;
+		ctx->launches += jobs[j].r.launches;
+	}
+	if (rc != SPICE_OK)
+		return rc;
+	for (int ci : todo) { // per-synapse state of the stateful ones (host hooks: one after the other)
+		rc = init_synapses(ctx, &ctx->conns[static_cast<size_t>(ci)]);
+		if (rc != SPICE_OK)
+			return rc;
+	}
+	return SPICE_OK;
+}
+
 int finalize(spice_ctx* ctx) {
 	if (ctx->finalized)
 		return SPICE_OK;
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	build_clock clock;
+	{
+		int const rc = build_pending(ctx);
+		if (rc != SPICE_OK)
+			return rc;
+	}
+	clock.lap("synapse generation");
 	// window = min delay over connections (any partition of the steps into windows no longer than
 	// the shortest delay is valid), bounded by kMaxWindow
 	long long dmin = kMaxWindow, dmax = 1;
@@ -596,6 +695,13 @@ int finalize(spice_ctx* ctx) {
 	// one window ahead (they cannot pass wait_window(w + 1) before this rank has published w + 1).
 	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay + (ctx->world > 1 ? ctx->window : 0), 2ll * ctx->window));
 	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
+	{
+		size_t stateless = 0;
+		for (auto const& c : ctx->conns)
+			stateless += c.stateful ? 0 : 1;
+		ctx->direct_segments = ctx->world > 1 && !std::getenv("SPICE_FLATTEN") &&
+		                       stateless * static_cast<size_t>(ctx->window) * static_cast<size_t>(ctx->world) <= static_cast<size_t>(deliver::kMaxCounts);
+	}
 	for (auto& p : ctx->pops)
 		if (p.host_update) {
 			size_t const cap = static_cast<size_t>(std::max<long long>(p.size, 1));
@@ -612,7 +718,7 @@ int finalize(spice_ctx* ctx) {
 		cudaFuncAttributes fa{};
 		CHECK_CUDA(ctx, cudaFuncGetAttributes(&fa, flatten_window));
 	}
-	if (ctx->world > 1) // flat copies of the spike lists for the delivery kernel (flatten_window)
+	if (ctx->world > 1 && !ctx->direct_segments) // flat copies of the spike lists for the delivery kernel (flatten_window)
 		for (auto& p : ctx->pops) {
 			size_t const cap = static_cast<size_t>(std::max<long long>(p.size, 1));
 			CHECK_CUDA(ctx, cudaMalloc(&p.flat_ids, sizeof(std::int32_t) * cap * ctx->ring));
@@ -701,39 +807,80 @@ int finalize(spice_ctx* ctx) {
 		// where each tile's share of a row starts; duplicate-free connections are then rewritten into
 		// the delivery kernel's own stream (bank-balanced counter addresses in whole 16-byte groups,
 		// deliver.h) and give their CSR entries back
-		for (int ci : order) {
-			connection& c         = ctx->conns[ci];
+		// (one host thread and one stream per connection: the passes of different connections overlap)
+		std::vector<int> pack_rc(order.size(), 0);
+		std::vector<int> pack_launches(order.size(), 0);
+		auto pack_one = [&](size_t j) {
+			connection& c         = ctx->conns[static_cast<size_t>(order[j])];
 			long long const n_src = ctx->pops[c.src].size;
-			CHECK_CUDA(ctx, cudaMalloc(&c.tile_ptr, sizeof(long long) * static_cast<size_t>(n_src) * static_cast<size_t>(c.tiles + 1)));
-			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::build_tile_ptr(ctx->stream, c.offsets, c.neighbors, n_src, c.tile, c.tiles, c.tile_ptr)));
-			ctx->launches++;
-			long long const n_runs = n_src * c.tiles;
-			if (c.duplicates || c.edges / 4 + n_runs >= (1ll << 32)) // multapses / more groups than 32-bit run pointers address
-				continue;
-			CHECK_CUDA(ctx, cudaMalloc(&c.run_ptr, sizeof(unsigned) * static_cast<size_t>(n_runs + 1)));
-			long long groups = 0;
-			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::count_groups(ctx->stream, c.tile_ptr, n_src, c.tiles, c.run_ptr, &groups)));
-			CHECK_CUDA(ctx, cudaMalloc(&c.packed, sizeof(std::int32_t) * 4 * static_cast<size_t>(std::max<long long>(groups, 1))));
-			CHECK_CUDA(ctx, static_cast<cudaError_t>(deliver::pack_runs(ctx->stream, c.neighbors, c.tile_ptr, c.run_ptr, n_src, c.tile, c.tiles,
-			                                                           ctx->tile_cap, c.packed)));
-			ctx->launches += 3;
-			CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			CHECK_CUDA(ctx, cudaFree(c.neighbors));
-			CHECK_CUDA(ctx, cudaFree(c.tile_ptr));
-			c.neighbors = nullptr;
-			c.tile_ptr  = nullptr;
-			c.arranged  = true;
+			cudaStream_t st       = nullptr;
+			auto check            = [&](cudaError_t e) {
+                if (e != cudaSuccess && pack_rc[j] == 0)
+                    pack_rc[j] = static_cast<int>(e);
+                return e == cudaSuccess;
+			};
+			if (!check(cudaSetDevice(ctx->device)) || !check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)))
+				return;
+			do {
+				if (!check(cudaMalloc(&c.tile_ptr, sizeof(long long) * static_cast<size_t>(n_src) * static_cast<size_t>(c.tiles + 1))))
+					break;
+				if (!check(static_cast<cudaError_t>(deliver::build_tile_ptr(st, c.offsets, c.neighbors, n_src, c.tile, c.tiles, c.tile_ptr))))
+					break;
+				pack_launches[j]++;
+				long long const n_runs = n_src * c.tiles;
+				if (c.duplicates || c.edges / 4 + n_runs >= (1ll << 32)) { // multapses / more groups than 32-bit run pointers address
+					check(cudaStreamSynchronize(st));
+					break;
+				}
+				if (!check(cudaMalloc(&c.run_ptr, sizeof(unsigned) * static_cast<size_t>(n_runs + 1))))
+					break;
+				long long groups = 0;
+				if (!check(static_cast<cudaError_t>(deliver::count_groups(st, c.tile_ptr, n_src, c.tiles, c.run_ptr, &groups))))
+					break;
+				if (!check(cudaMalloc(&c.packed, sizeof(std::int32_t) * 4 * static_cast<size_t>(std::max<long long>(groups, 1)))))
+					break;
+				if (!check(static_cast<cudaError_t>(deliver::pack_runs(st, c.neighbors, c.tile_ptr, c.run_ptr, n_src, c.tile, c.tiles, ctx->tile_cap, c.packed))))
+					break;
+				pack_launches[j] += 3;
+				if (!check(cudaStreamSynchronize(st)))
+					break;
+				check(cudaFree(c.neighbors));
+				check(cudaFree(c.tile_ptr));
+				c.neighbors = nullptr;
+				c.tile_ptr  = nullptr;
+				c.arranged  = true;
+			} while (false);
+			cudaStreamDestroy(st);
+		};
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (std::getenv("SPICE_SERIAL_BUILD") || order.size() <= 1)
+			for (size_t j = 0; j < order.size(); j++)
+				pack_one(j);
+		else {
+			std::vector<std::thread> threads;
+			for (size_t j = 0; j < order.size(); j++)
+				threads.emplace_back(pack_one, j);
+			for (auto& t : threads)
+				t.join();
 		}
+		for (size_t j = 0; j < order.size(); j++) {
+			ctx->launches += pack_launches[j];
+			CHECK_CUDA(ctx, static_cast<cudaError_t>(pack_rc[j]));
+		}
+		clock.lap("delivery stream (pack_runs)");
 		std::vector<deliver::conn_desc> descs;
 		for (int ci : order) {
 			connection const& c = ctx->conns[ci];
 			population const& src = ctx->pops[c.src];
 			population const& dst = ctx->pops[c.dst];
 			deliver::conn_desc d{};
-			d.ring_ids   = ctx->world > 1 ? src.flat_ids : xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
-			d.ring_cnt   = ctx->world > 1 ? src.flat_cnt : xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
+			bool const flat = ctx->world > 1 && !ctx->direct_segments;
+			d.ring_ids   = flat ? src.flat_ids : xptr<std::int32_t>(ctx->xbase, src.ring_ids_off);
+			d.ring_cnt   = flat ? src.flat_cnt : xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off);
 			d.ring_cap   = std::max<long long>(src.size, 1);
-			d.cnt_stride = 1;
+			d.cnt_stride = flat ? 1 : ctx->world;
+			for (int r = 0; r < ctx->world; r++)
+				d.seg_lo[r] = static_cast<std::int32_t>(src.size * r / ctx->world);
 			d.packed      = c.packed;
 			d.run_ptr     = c.run_ptr;
 			d.neighbors   = c.neighbors;
@@ -804,7 +951,7 @@ int finalize(spice_ctx* ctx) {
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_ring_cap, sizeof(long long) * std::max(np, 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_seg_lo, sizeof(long long) * std::max<size_t>(h_seg.size(), 1)));
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_peer_cnt, sizeof(void*) * std::max(np, 1) * ctx->world));
-	if (ctx->world > 1 && np) {
+	if (ctx->world > 1 && !ctx->direct_segments && np) {
 		std::vector<std::int32_t*> h_flat_ids;
 		std::vector<std::uint32_t*> h_flat_cnt;
 		for (auto const& p : ctx->pops) {
@@ -834,6 +981,7 @@ int finalize(spice_ctx* ctx) {
 	CHECK_CUDA(ctx, cudaMalloc(&ctx->d_error, sizeof(int)));
 	CHECK_CUDA(ctx, cudaMemset(ctx->d_error, 0, sizeof(int)));
 	ctx->spike_cache.assign(np, std::vector<host_spikes>(static_cast<size_t>(ctx->ring)));
+	clock.lap("tables");
 	ctx->finalized = true;
 	return SPICE_OK;
 }
@@ -856,7 +1004,7 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1,
 		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events,
 		                               from_ctx{c.src_snapshot, ctx->pops[c.src].stride, reinterpret_cast<std::int64_t const*>(c.offsets),
-		                                        ctx->pops[c.src].size}};
+		                                        ctx->pops[c.src].size, ctx->mode == SPICE_MODE_FAST ? 1 : 0}};
 	}
 }
 
@@ -1051,10 +1199,16 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		pb.nsteps = nsteps;
 		pb.seq    = ctx->seq;
 		publish_window<<<1, 256, 0, ctx->stream>>>(pb);
-		wait_args wa{xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off)), ctx->world, ctx->seq, ctx->d_error};
-		wait_window<<<1, 32, 0, ctx->stream>>>(wa);
-		ctx->launches += 2;
-		if (ctx->tiled && np > 0) { // one flat spike list per (step, population) for the delivery kernel
+		ctx->launches++;
+		// who waits for the peers: the tiled delivery launch itself when it reads the ring's segments directly and the
+		// window has nothing else to run behind the exchange (stateful deliveries, raster packing); else a wait kernel
+		bool const deliver_waits = ctx->direct_segments && ctx->tiled && ctx->n_desc > 0 && !ctx->any_stateful && !ctx->raster_on;
+		if (!deliver_waits) {
+			wait_args wa{xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off)), ctx->world, ctx->seq, ctx->d_error};
+			wait_window<<<1, 32, 0, ctx->stream>>>(wa);
+			ctx->launches++;
+		}
+		if (ctx->tiled && np > 0 && !ctx->direct_segments) { // one flat spike list per (step, population) for the delivery kernel
 			flatten_args fa{ctx->d_ring_ids, ctx->d_ring_cnt, ctx->d_ring_cap, ctx->d_seg_lo, ctx->d_flat_ids, ctx->d_flat_cnt,
 			                np,              ctx->ring,       ctx->world,      ctx->time};
 			flatten_window<<<nsteps * np, 256, 0, ctx->stream>>>(fa);
@@ -1140,6 +1294,11 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ta.stats       = ctx->d_stats;
 			ta.error       = ctx->d_error;
 			ta.tile_cap    = ctx->tile_cap;
+			ta.world       = ctx->world > 1 && !ctx->direct_segments ? 1 : ctx->world; // flat lists look like one rank's
+			if (ctx->direct_segments && !ctx->any_stateful && !ctx->raster_on) {
+				ta.flags = xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off));
+				ta.seq   = ctx->seq;
+			}
 			int launched   = 0;
 			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device, &launched);
 			if (e != 0)
@@ -1288,9 +1447,7 @@ int init_synapses(spice_ctx* ctx, connection* c) {
 	c->syn_stride         = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(c->edges, 1)), 32));
 	CHECK_CUDA(ctx, cudaMalloc(&c->syn, sizeof(std::uint32_t) * static_cast<size_t>(words) * static_cast<size_t>(c->syn_stride)));
 	if (c->ops->per_synapse_init) {
-		if (ctx->world != 1)
-			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
-		UInt128 const sd = (ctx->seed++).seed(); // the hook's own engine (synapse_population.h:35)
+		UInt128 const sd = c->init_seed; // the hook's own engine (synapse_population.h:35), drawn at connect() time
 		std::vector<long long> off(static_cast<size_t>(src.size) + 1);
 		std::vector<std::int32_t> nb(static_cast<size_t>(std::max<long long>(c->edges, 1)));
 		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1567,22 +1724,15 @@ int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops
 	int rc = add_connection_common(ctx, ops, src_pop, dst_pop, delay, functor, &c);
 	if (rc != SPICE_OK)
 		return rc;
-	// synapse_population ctor: _graph(c, seed++) (synapse_population.h:30-31)
-	UInt128 const sd      = (ctx->seed++).seed();
-	population const& src = ctx->pops[src_pop];
-	population const& dst = ctx->pops[dst_pop];
-	gen::result r;
-	std::string err;
-	rc = gen::generate_fixed_probability(ctx->stream, src.size, dst.size, p, sd.lo, sd.hi, dst.lo, dst.hi, 0, &r, &err);
-	if (rc != 0)
-		return fail(ctx, rc, err);
-	c.offsets   = r.offsets;
-	c.neighbors = r.neighbors;
-	c.edges     = r.edges;
-	ctx->launches += r.launches;
-	rc = init_synapses(ctx, &c);
-	if (rc != SPICE_OK)
-		return rc;
+	// synapse_population ctor: _graph(c, seed++) (synapse_population.h:30-31), then the init hook's engine (:35)
+	c.fp_seed = (ctx->seed++).seed();
+	if (c.stateful && ops->per_synapse_init) {
+		if (ctx->world != 1)
+			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
+		c.init_seed = (ctx->seed++).seed();
+	}
+	c.fp_p       = p;
+	c.pending_fp = true; // generated by finalize(), together with the network's other connections
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
 		*conn_out = static_cast<int>(ctx->conns.size()) - 1;
@@ -1628,6 +1778,11 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 	for (size_t i = 1; i < packed.size(); i++)
 		if (packed[i] == packed[i - 1])
 			c.duplicates = true; // a multapse: rows may repeat a target
+	if (c.stateful && ops->per_synapse_init) {
+		if (ctx->world != 1)
+			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
+		c.init_seed = (ctx->seed++).seed();
+	}
 	rc = init_synapses(ctx, &c);
 	if (rc != SPICE_OK)
 		return rc;
@@ -1640,6 +1795,11 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t* offsets_out, int32_t* neighbors_out) {
 	PRE(ctx, conn >= 0 && conn < static_cast<int>(ctx->conns.size()));
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	{
+		int const rc = finalize(ctx); // the adjacency exists once the network has been built
+		if (rc != SPICE_OK)
+			return rc;
+	}
 	connection const& c = ctx->conns[conn];
 	if (n_edges_out)
 		*n_edges_out = c.edges;
@@ -1669,6 +1829,11 @@ int spice_connection_csr(spice_ctx* ctx, int conn, int64_t* n_edges_out, int64_t
 
 int spice_connection_synapses(spice_ctx* ctx, int conn, void* out, int64_t bytes) {
 	PRE(ctx, conn >= 0 && conn < static_cast<int>(ctx->conns.size()));
+	{
+		int const rc = finalize(ctx);
+		if (rc != SPICE_OK)
+			return rc;
+	}
 	connection const& c = ctx->conns[conn];
 	if (!c.stateful)
 		return fail(ctx, SPICE_ERR_UNSUPPORTED, "stateless connection: no per-synapse state");

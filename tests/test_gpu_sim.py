@@ -268,6 +268,37 @@ def test_two_ranks_one_device_plastic(sp, orc):
         assert off[-1] == keep.sum()
 
 
+# north star: "the fast atomic mode must match membrane potentials within a stated float tolerance and per-population
+# firing rates within a stated tolerance".  SPICE_MODE_FAST applies a target's plastic events in arrival order (the
+# event lists are filled with atomics) instead of the reference's (source, row) order: float sums in another order.
+FAST_V_TOL = 1e-4        # volts, per neuron, on membrane potentials of ~1e-2 (threshold 0.02), for >= 99.5 % of the neurons
+FAST_RATE_TOL = 0.02     # relative, per population, over the run
+
+
+def test_fast_mode_tolerances(sp, orc):
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=3000, p=0.1, w_exc=np.float32(2.0 / 300), w_inh=np.float32(-10.0 / 300), seed=(5,), plastic=True)
+    net, pops = brunel(mode=sp.MODE_FAST, **kw)
+    onet, opops = brunel_oracle(orc, **kw)
+    steps = 300
+    net.raster_enable(True)
+    net.step(steps)
+    counts, _ids = net.raster_read(steps)
+    ocounts = np.zeros_like(counts)
+    for s in range(steps):
+        onet.step()
+        ocounts[s] = [len(onet.spikes(op, 0)) for op in opops]
+    got, want = counts.sum(0).astype(float), ocounts.sum(0).astype(float)
+    assert np.all(np.abs(got - want) <= FAST_RATE_TOL * want + 1), (got, want)
+    for pi in (1, 2):
+        g, w = pops[pi].get_neurons(), onet.neurons(pi)
+        close = np.abs(g["V"].astype(np.float64) - w["V"].astype(np.float64)) <= FAST_V_TOL
+        assert close.mean() >= 0.995, (pi, close.mean())
+    gs, ws = net.connection_synapses(2), onet.connection_synapses(2)
+    assert np.mean(np.abs(gs["W"].astype(np.float64) - ws["W"].astype(np.float64)) <= 1e-7) >= 0.995
+
+
 def test_brunel_plus_300_golden(sp, orc, golden):
     """samples/brunel+ (N = 20000, 300 steps): raster of the compiled reference (strict flavour)."""
     from spice2_b200.samples import brunel
