@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include <cub/device/device_scan.cuh>
 
@@ -53,6 +54,8 @@ constexpr int kStageBytes  = kRuns * kSlotBytes;
 constexpr int kQuarters    = 32 / kRuns; // stages per batch of 32 runs
 constexpr int kLookahead   = kStaticUnits - 1; // units beyond the one being counted whose tickets a warp may read
 constexpr unsigned kFull   = 0xffffffffu;
+// A stream entry is the ADDRESS of a counter in the CTA's shared-memory window (counter_base() + 4 x the word index):
+// red.shared takes it as it is, and it is never zero (see issue()).
 
 __device__ __forceinline__ unsigned smem_u32(void const* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -88,29 +91,36 @@ __device__ __forceinline__ int4 ldg_stream(void const* p) {
 	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
 	return v;
 }
-// count the 4 entries of a group: byte offsets of 4 u32 counters
-__device__ __forceinline__ void tally(unsigned cnt, int4 v) {
-	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.x) : "memory");
-	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.y) : "memory");
-	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.z) : "memory");
-	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt + v.w) : "memory");
+// count the 4 entries of a group: the shared-memory addresses of 4 u32 counters
+__device__ __forceinline__ void tally(int4 v) {
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.x) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.y) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.z) : "memory");
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.w) : "memory");
 }
 
-// static shared state of a CTA
+// what the unit path needs of a connection (a copy in shared memory; conn_desc stays in global memory)
+struct conn_hot {
+	char const* stream;
+	unsigned const* run_ptr;
+	std::uint32_t* counts;
+	std::int32_t const* ring_ids;
+	long long ring_cap, cstride, n_dst;
+	int tiles, tile, delay, cring, arranged, pad;
+};
+
+// shared state of a CTA (behind the counters: 2 CTAs of 8 warps fit an SM only while this stays below ~9 KB)
 template <int kW, int kStages>
-struct cta_state {
+struct alignas(16) cta_state {
 	unsigned long long bars[kW][kStages];
 	unsigned tickets[kTicketRing];       // the CTA's unit sequence: tickets[seq % kTicketRing]
 	unsigned cnts[kMaxCounts];           // spikes of (connection, step): world == 1 the total; else the inclusive prefix over ranks
 	int prefix[kMaxConns + 1];           // tile_prefix of the connections, + total_tiles
-	char const* stream[kMaxConns];       // the connections' packed streams ...
-	unsigned const* run_ptr[kMaxConns];  // ... run pointers ...
-	int tiles[kMaxConns];                // ... and tile counts
+	conn_hot conns[kMaxConns];           // the launch's connections: nothing on the unit path reads them from global memory
 };
 
 // A unit as a warp needs it (warp-uniform)
 struct unit_view {
-	conn_desc const* C;
 	int c, s, k;
 	int cs; // (connection, step) index
 	unsigned total;
@@ -160,14 +170,22 @@ __device__ __forceinline__ unsigned warp_batches(unsigned total, int warp) {
 template <int kW, int kStages, bool kBulk>
 __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_args a) {
 	static_assert(kStages == 2 || kStages == 4, "the stage slots and mbarrier phases below are static for 2 or 4 stages");
+	// dynamic shared memory only, the counters first: they start at the same address in every variant of this kernel,
+	// the address the stream entries were built for (counter_base(); checked below)
 	extern __shared__ uint4 smem4[];
-	__shared__ cta_state<kW, kStages> sh;
 	int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	unsigned const units  = static_cast<unsigned>(a.total_tiles) * a.nsteps;
 	unsigned const cnt    = smem_u32(smem4);                                  // counters: arrays A, B, dump
 	int const cnt_words   = 2 * a.tile_cap + 32;
-	unsigned const ring   = cnt + static_cast<unsigned>(cnt_words) * 4 + static_cast<unsigned>(warp) * (kStages * kStageBytes);
+	cta_state<kW, kStages>& sh = *reinterpret_cast<cta_state<kW, kStages>*>(reinterpret_cast<char*>(smem4) + static_cast<size_t>(cnt_words) * 4);
+	unsigned const ring   = cnt + static_cast<unsigned>(cnt_words) * 4 + static_cast<unsigned>(sizeof(cta_state<kW, kStages>)) +
+	                        static_cast<unsigned>(warp) * (kStages * kStageBytes);
 	unsigned const bar0   = smem_u32(&sh.bars[warp][0]);
+	if (cnt != a.cnt_base) { // the streams address another shared-memory layout: count nothing
+		if (tid == 0)
+			atomicOr(a.error, 1 << 16);
+		return;
+	}
 
 	// ---- CTA prologue -----------------------------------------------------------------------------------
 	int const world = a.world;
@@ -195,13 +213,12 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			sh.cnts[i * world + r] = run;
 		}
 	}
-	for (int i = tid; i <= a.nconns; i += kW * 32) {
+	for (int i = tid; i <= a.nconns; i += kW * 32)
 		sh.prefix[i] = i < a.nconns ? a.conns[i].tile_prefix : a.total_tiles;
-		if (i < a.nconns) {
-			sh.stream[i]  = reinterpret_cast<char const*>(a.conns[i].packed);
-			sh.run_ptr[i] = a.conns[i].run_ptr;
-			sh.tiles[i]   = a.conns[i].tiles;
-		}
+	for (int i = tid; i < a.nconns; i += kW * 32) {
+		conn_desc const& C = a.conns[i];
+		sh.conns[i] = conn_hot{reinterpret_cast<char const*>(C.packed), C.run_ptr, C.counts, C.ring_ids, C.ring_cap, C.cstride, C.n_dst,
+		                       C.tiles, C.tile, static_cast<int>(C.delay), C.cring, C.arranged, 0};
 	}
 	if (tid < kTicketRing)
 		sh.tickets[tid] = tid < kStaticUnits ? static_ticket(blockIdx.x, gridDim.x, tid) : 0xffffffffu;
@@ -222,7 +239,6 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		v.valid               = ticket < units;
 		if (v.valid) {
 			unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
-			v.C     = a.conns + p.c;
 			v.c     = p.c;
 			v.s     = p.s;
 			v.k     = p.k;
@@ -238,7 +254,6 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	unsigned cs_seq = 0, cs_b = 0, cs_total = 0, cs_nbatch = 0;
 	bool cs_known = false, cs_end = false;
 	std::int32_t const* cs_ids = nullptr;
-	std::int32_t const* cs_seg = nullptr; // several ranks: the source population's segment starts
 	int cs_cs = 0, cs_c = 0, cs_k = 0;
 	// spike ids requested (idn), run pointers requested (nxt), runs being fetched and counted (cur)
 	bool id_valid = false;
@@ -260,11 +275,11 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 					cs_end = true;
 					return false;
 				}
+				conn_hot const& C    = sh.conns[v.c];
 				long long const slot = (a.t0 + v.s) % a.ring;
 				cs_total  = v.total;
-				cs_nbatch = v.C->arranged ? warp_batches<kW>(v.total, warp) : 0; // plain units are walked at their merge
-				cs_ids    = v.C->ring_ids + slot * v.C->ring_cap;
-				cs_seg    = v.C->seg_lo;
+				cs_nbatch = C.arranged ? warp_batches<kW>(v.total, warp) : 0; // plain units are walked at their merge
+				cs_ids    = C.ring_ids + slot * C.ring_cap;
 				cs_cs     = v.cs;
 				cs_c      = v.c;
 				cs_k      = v.k;
@@ -280,52 +295,65 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			cs_known = false;
 		}
 	};
-	// move every prefetch stage forward as far as it goes: ids -> run pointers (nxt) -> cur.  Once per batch.
-	auto refill = [&]() {
-#pragma unroll
-		for (int pass = 0; pass < 3; pass++) {
-			if (!cur.valid && nxt.valid) {
-				cur       = nxt;
-				nxt.valid = false;
+	// move every prefetch stage forward by one: cur <- nxt <- (run pointers of the ids requested last time) <- (ids of the
+	// cursor's next batch).  Nothing here reads what it has just requested: the values are consumed one call later.
+	auto advance = [&]() {
+		if (!cur.valid && nxt.valid) {
+			cur       = nxt;
+			nxt.valid = false;
+		}
+		if (!nxt.valid && id_valid) {
+			nxt.valid  = true;
+			nxt.seq    = id_seq;
+			nxt.c      = id_c;
+			nxt.g0 = nxt.ng = 0;
+			if (id_src >= 0) {
+				unsigned const* p = sh.conns[id_c].run_ptr + (static_cast<long long>(id_src) * sh.conns[id_c].tiles + id_k);
+				nxt.g0            = p[0];
+				nxt.ng            = p[1]; // end of the run for now: issue() subtracts (the loads are still in flight)
 			}
-			if (!nxt.valid && id_valid) {
-				nxt.valid  = true;
-				nxt.seq    = id_seq;
-				nxt.c      = id_c;
-				nxt.g0 = nxt.ng = 0;
-				if (id_src >= 0) {
-					unsigned const* p = sh.run_ptr[id_c] + (static_cast<long long>(id_src) * sh.tiles[id_c] + id_k);
-					nxt.g0            = p[0];
-					nxt.ng            = p[1]; // end of the run for now: issue() and count_stage() subtract (the loads are still in flight)
-				}
-				id_valid = false;
-			}
-			if (!id_valid) {
-				unsigned seq, b;
-				if (cursor_next(seq, b)) {
-					unsigned const q = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
-					id_valid  = true;
-					id_seq    = seq;
-					id_src    = -1;
-					if (q < cs_total) {
-						if (world == 1)
-							id_src = cs_ids[q];
-						else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
-							unsigned const* pre = sh.cnts + cs_cs * world;
-							int r               = 0;
-							while (pre[r] <= q)
-								r++;
-							id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + cs_seg[r] + (q - (r ? pre[r - 1] : 0u)));
-						}
+			id_valid = false;
+		}
+		if (!id_valid) {
+			unsigned seq, b;
+			if (cursor_next(seq, b)) {
+				unsigned const q = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
+				id_valid  = true;
+				id_seq    = seq;
+				id_src    = -1;
+				if (q < cs_total) {
+					if (world == 1)
+						id_src = cs_ids[q];
+					else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
+						unsigned const* pre = sh.cnts + cs_cs * world;
+						int r               = 0;
+						while (pre[r] <= q)
+							r++;
+						id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + a.conns[cs_c].seg_lo[r] + (q - (r ? pre[r - 1] : 0u)));
 					}
-					id_c      = cs_c;
-					id_k      = cs_k;
 				}
+				id_c      = cs_c;
+				id_k      = cs_k;
+			}
+		}
+	};
+	// Once per batch.  In the steady state one step fills cur from values requested a whole batch ago; only an empty
+	// pipeline (the CTA's first unit, or a cursor that had run into the look-ahead limit) takes the dependent steps, behind
+	// a real branch: a predicated move of a value still in flight would wait for it whether it is needed or not.
+	auto refill = [&]() {
+		advance();
+		if (!cur.valid && (nxt.valid || id_valid)) {
+			asm volatile("" ::: "memory");
+			advance();
+			if (!cur.valid && (nxt.valid || id_valid)) {
+				asm volatile("" ::: "memory");
+				advance();
 			}
 		}
 	};
 	// issue the copies of quarter q of batch b into stage slot `st`
 	auto issue = [&](batch const& b, unsigned q, unsigned st) {
+		char const* stream = sh.conns[b.c].stream;
 		if constexpr (kBulk) {
 			unsigned const bar   = bar0 + st * 8;
 			bool const mine      = (static_cast<unsigned>(lane) / kRuns) == q;
@@ -335,53 +363,67 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				mbar_arrive_expect_tx(bar, tot);
 			__syncwarp();
 			if (bytes)
-				bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, sh.stream[b.c] + static_cast<unsigned long long>(b.g0) * 16, bytes, bar);
+				bulk_g2s(ring + st * kStageBytes + (lane % kRuns) * kSlotBytes, stream + static_cast<unsigned long long>(b.g0) * 16, bytes, bar);
 		} else {
+			// every lane copies its group of every run, or zero-fills its place in the run's slot (src-size 0: nothing is
+			// read): a stream entry is never zero (an address behind the window's reserved start), so the count tells the two apart without the run's length
 			unsigned const dst = ring + st * kStageBytes + lane * 16;
-			char const* src    = sh.stream[b.c] + lane * 16;
 #pragma unroll
 			for (int j = 0; j < kRuns; j++) {
 				unsigned const g0 = __shfl_sync(kFull, b.g0, q * kRuns + j);
 				unsigned const g1 = __shfl_sync(kFull, b.ng, q * kRuns + j);
-				if (static_cast<unsigned>(lane) < g1 - g0)
-					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * kSlotBytes), "l"(src + static_cast<unsigned long long>(g0) * 16) : "memory");
+				unsigned const sz = static_cast<unsigned>(lane) < g1 - g0 ? 16u : 0u;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + j * kSlotBytes),
+				             "l"(stream + static_cast<unsigned long long>(g0 + lane) * 16), "r"(sz)
+				             : "memory");
 			}
 			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 	};
 	// count quarter q of cur, landed in stage slot `st`
-	auto count_stage = [&](unsigned q, unsigned st, unsigned ph) {
-		if constexpr (kBulk)
-			mbar_wait(bar0 + st * 8, ph);
-		else // groups complete in order: all but the kStages - 1 youngest have landed (each lane reads back only what it copied)
-			asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+	auto count_stage = [&](unsigned q, unsigned st, unsigned ph, unsigned longer) {
 		unsigned const base = ring + st * kStageBytes + lane * 16;
-		unsigned const mine = cur.ng - cur.g0;
-		bool longer = false;
+		if constexpr (kBulk) {
+			mbar_wait(bar0 + st * 8, ph);
+			unsigned const mine = cur.ng - cur.g0;
 #pragma unroll
-		for (int h = 0; h < kRuns; h += 4) { // four runs at a time: their groups are read back, then counted
-			int4 v[4];
-			unsigned n[4];
+			for (int h = 0; h < kRuns; h += 4) { // four runs at a time: their groups are read back, then counted
+				int4 v[4];
+				unsigned n[4];
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				n[j] = __shfl_sync(kFull, mine, q * kRuns + h + j);
-				if (static_cast<unsigned>(lane) < n[j])
-					v[j] = lds128(base + (h + j) * kSlotBytes);
+				for (int j = 0; j < 4; j++) {
+					n[j] = __shfl_sync(kFull, mine, q * kRuns + h + j);
+					v[j] = lds128(base + (h + j) * kSlotBytes); // (a stale slot where this lane has no group: not counted)
+				}
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					if (static_cast<unsigned>(lane) < n[j])
+						tally(v[j]);
 			}
+		} else {
+			// groups complete in order: all but the kStages - 1 youngest have landed (each lane reads back only what it copied)
+			asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				if (static_cast<unsigned>(lane) < n[j])
-					tally(cnt, v[j]);
-				longer |= n[j] > 32;
+			for (int h = 0; h < kRuns; h += 4) {
+				int4 v[4];
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					v[j] = lds128(base + (h + j) * kSlotBytes);
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					if (v[j].x)
+						tally(v[j]);
 			}
 		}
-		if (longer) { // a run of more than 32 groups (rare: tiles are sized for ~25): the rest straight from global memory
+		if ((longer >> (q * kRuns)) & ((1u << kRuns) - 1)) { // a run of more than 32 groups in this quarter (rare: tiles are sized for ~25): the rest straight from global memory
+			char const* stream  = sh.conns[cur.c].stream;
+			unsigned const mine = cur.ng - cur.g0;
 #pragma unroll 1
 			for (int j = 0; j < kRuns; j++) {
 				unsigned const g0 = __shfl_sync(kFull, cur.g0, q * kRuns + j);
 				unsigned const nj = __shfl_sync(kFull, mine, q * kRuns + j);
 				for (unsigned off = 32 + lane; off < nj; off += 32)
-					tally(cnt, ldg_stream(sh.stream[cur.c] + static_cast<unsigned long long>(g0 + off) * 16));
+					tally(ldg_stream(stream + static_cast<unsigned long long>(g0 + off) * 16));
 			}
 		}
 		__syncwarp(); // every lane has read the stage's slots: they may be overwritten
@@ -389,7 +431,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	// end of unit `done`: all warps arrive; merge + zero the counters, store the tile's range; publish the next ticket
 	auto boundary = [&](unit_view const& U) {
 		__syncthreads();
-		conn_desc const& C = *U.C;
+		conn_hot const& C  = sh.conns[U.c];
 		int const lo       = U.k * C.tile;
 		int const width    = static_cast<int>(min(static_cast<long long>(C.tile), C.n_dst - lo));
 		long long const t  = a.t0 + U.s;
@@ -408,7 +450,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				unsigned before         = 0;
 				for (int r = 0; r < world; r++) { // one segment per rank (one rank: the whole list)
 					unsigned const upto = sh.cnts[U.cs * world + r];
-					ev += walk_plain<kW>(C, U.k, ids + (world > 1 ? C.seg_lo[r] : 0), upto - before, out, lo, lane, warp);
+					ev += walk_plain<kW>(a.conns[U.c], U.k, ids + (world > 1 ? a.conns[U.c].seg_lo[r] : 0), upto - before, out, lo, lane, warp);
 					before = upto;
 				}
 			}
@@ -459,11 +501,14 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			boundary(U);
 			continue;
 		}
-		for (; q_cur < static_cast<unsigned>(kStages); q_cur++) // after a pipeline bubble only
-			issue(cur, q_cur, q_cur);
+#pragma unroll
+		for (int q = 0; q < kStages; q++) // after a pipeline bubble only
+			if (q_cur <= static_cast<unsigned>(q))
+				issue(cur, q, q);
+		unsigned const longer = __ballot_sync(kFull, cur.ng - cur.g0 > 32u); // lanes whose run has more than 32 groups
 #pragma unroll
 		for (int q = 0; q < kQuarters; q++) {
-			count_stage(q, q % kStages, kStages == 2 ? (q >> 1) & 1 : parity);
+			count_stage(q, q % kStages, kStages == 2 ? (q >> 1) & 1 : parity, longer);
 			if (q + kStages < kQuarters)
 				issue(cur, q + kStages, q % kStages);
 			else if (nxt.valid)
@@ -506,7 +551,7 @@ __global__ void __launch_bounds__(256) run_groups_kernel(long long const* tile_p
 // position p of a chunk is counted by lane p >> 2 in instruction p & 3, together with the entries
 // at p +- 4, +- 8, ... — those must fall into different banks.
 __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long long const* tile_ptr, unsigned const* run_ptr,
-                                                   long long n_runs, int tiles, int tile, int cap, std::int32_t* packed) {
+                                                   long long n_runs, int tiles, int tile, int cap, int base, std::int32_t* packed) {
 	long long const id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (id >= n_runs)
 		return;
@@ -591,7 +636,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 					rem[best]--;
 					int const j  = order[first[b] + i];
 					int const tt = t[j];
-					out[next[best]] = 4 * ((bank[j] & 0x80) ? cap + rotw_fwd(tt) : tt);
+					out[next[best]] = base + 4 * ((bank[j] & 0x80) ? cap + rotw_fwd(tt) : tt);
 					next[best] += 4;
 				}
 			}
@@ -601,7 +646,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 				unsigned const free_banks = ~used_banks[c];
 				int const b               = free_banks ? __ffs(free_banks) - 1 : 0;
 				used_banks[c] |= 1u << b;
-				out[next[c]] = 4 * (2 * cap + b);
+				out[next[c]] = base + 4 * (2 * cap + b);
 			}
 	}
 }
@@ -609,7 +654,7 @@ __global__ void __launch_bounds__(128) pack_kernel(std::int32_t const* nb, long 
 // One thread per row: decode the counter addresses of the row's runs back to local columns and
 // emit them ascending (tiles in order, a bitmap per tile).
 __global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets,
-                                                     long long n_rows, int tiles, int tile, int cap, std::int32_t* out) {
+                                                     long long n_rows, int tiles, int tile, int cap, int base, std::int32_t* out) {
 	long long const row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (row >= n_rows)
 		return;
@@ -621,7 +666,7 @@ __global__ void __launch_bounds__(128) unpack_kernel(std::int32_t const* packed,
 			present[i] = 0;
 		long long const beg = static_cast<long long>(run_ptr[row * tiles + k]) * 4, end = static_cast<long long>(run_ptr[row * tiles + k + 1]) * 4;
 		for (long long e = beg; e < end; e++) {
-			int const v = packed[e] >> 2;
+			int const v = (packed[e] - base) >> 2;
 			if (v >= 2 * cap)
 				continue;
 			int const t = v < cap ? v : rotw_inv(v - cap);
@@ -697,20 +742,66 @@ int count_groups(void* stream, long long const* tile_ptr, long long src_count, i
 	return static_cast<int>(e);
 }
 
+namespace {
+// where a kernel without static shared memory finds its dynamic shared memory (the window's reserved start lies before it)
+__global__ void smem_base_kernel(unsigned* out) {
+	extern __shared__ uint4 probe4[];
+	*out = smem_u32(probe4);
+}
+}
+
+int counter_base(void* stream, int* base_out) {
+	static std::mutex m;
+	static int cached[64] = {};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess || dev < 0 || dev >= 64)
+		return static_cast<int>(e != cudaSuccess ? e : cudaErrorInvalidDevice);
+	std::lock_guard<std::mutex> lock(m);
+	if (!cached[dev]) {
+		auto st       = static_cast<cudaStream_t>(stream);
+		unsigned* d   = nullptr;
+		unsigned base = 0;
+		e = cudaMalloc(&d, sizeof(unsigned));
+		if (e != cudaSuccess)
+			return static_cast<int>(e);
+		smem_base_kernel<<<1, 1, 16, st>>>(d);
+		e = cudaGetLastError();
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(&base, d, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(st);
+		cudaFree(d);
+		if (e != cudaSuccess)
+			return static_cast<int>(e);
+		if (base == 0 || base > 0x10000)
+			return static_cast<int>(cudaErrorUnknown);
+		cached[dev] = static_cast<int>(base);
+	}
+	*base_out = cached[dev];
+	return 0;
+}
+
 int pack_runs(void* stream, std::int32_t const* neighbors, long long const* tile_ptr, unsigned const* run_ptr, long long src_count,
               int tile, int tiles, int cap, std::int32_t* packed) {
 	long long const n = src_count * tiles;
+	int base          = 0;
+	if (int const e = counter_base(stream, &base))
+		return e;
 	if (n > 0)
 		pack_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(neighbors, tile_ptr, run_ptr, n,
-		                                                                                                 tiles, tile, cap, packed);
+		                                                                                                 tiles, tile, cap, base, packed);
 	return static_cast<int>(cudaGetLastError());
 }
 
 int unpack_rows(void* stream, std::int32_t const* packed, unsigned const* run_ptr, long long const* offsets, long long src_count,
                 int tile, int tiles, int cap, std::int32_t* out) {
+	int base = 0;
+	if (int const e = counter_base(stream, &base))
+		return e;
 	if (src_count > 0)
 		unpack_kernel<<<static_cast<unsigned>((src_count + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-		    packed, run_ptr, offsets, src_count, tiles, tile, cap, out);
+		    packed, run_ptr, offsets, src_count, tiles, tile, cap, base, out);
 	return static_cast<int>(cudaGetLastError());
 }
 
@@ -722,7 +813,8 @@ static int env_int(char const* name, int dflt) {
 
 namespace {
 size_t cta_smem(int tile_cap, int warps, int stages) {
-	return static_cast<size_t>(2 * tile_cap + 32) * 4 + static_cast<size_t>(warps) * stages * kStageBytes;
+	size_t const state = warps == 8 ? sizeof(cta_state<8, 2>) : sizeof(cta_state<16, 2>);
+	return static_cast<size_t>(2 * tile_cap + 32) * 4 + state + static_cast<size_t>(warps) * stages * kStageBytes;
 }
 using kernel_t = void (*)(tiles_args);
 struct shape {
@@ -737,7 +829,7 @@ shape const kShapes[4] = {{deliver_units<8, 2, true>, 8, 2}, {deliver_units<16, 
 
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
-	                 path_env = env_int("SPICE_DELIVER_PATH", 0); // 0: cp.async.bulk, 1: cp.async (experiment)
+	                 path_env = env_int("SPICE_DELIVER_PATH", 0); // 0: cp.async.bulk + mbarrier (measured faster: 0.658 vs 0.625 of the roofline), 1: cp.async with zero fill
 	static int blocks_per_sm[64][4] = {};
 	static int sms[64]              = {};
 	static int smem_set[64]         = {};
@@ -778,7 +870,12 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 		grid = std::clamp(grid_env, 1, grid);
 	if (launches)
 		*launches = 1;
-	S.kernel<<<grid, S.warps * 32, cta_smem(a.tile_cap, S.warps, S.stages), static_cast<cudaStream_t>(stream)>>>(a);
+	tiles_args b = a;
+	int base     = 0;
+	if (int const e = counter_base(stream, &base))
+		return e;
+	b.cnt_base = static_cast<unsigned>(base);
+	S.kernel<<<grid, S.warps * 32, cta_smem(a.tile_cap, S.warps, S.stages), static_cast<cudaStream_t>(stream)>>>(b);
 	return static_cast<int>(cudaGetLastError());
 }
 

@@ -52,10 +52,11 @@ struct tiles_args {
 	// several ranks: the launch itself waits until every peer has published window `seq` (runtime.cu publish_window)
 	unsigned long long const* flags; // this rank's flag array [world], or null
 	unsigned long long seq;
+	unsigned cnt_base;               // filled in by launch_tiles: where the CTA's counters start in its shared-memory window
 };
 
 constexpr int kMaxConns  = 32;   // connections per launch
-constexpr int kMaxCounts = 1536; // nconns * nsteps * world spike counts staged in shared memory per launch
+constexpr int kMaxCounts = 768;  // nconns * nsteps * world spike counts staged in shared memory per launch
 
 // tile_ptr[row * (tiles + 1) + k] = first position in row `row` whose target is >= k * tile
 // (k = tiles: the row end).  Returns a cudaError_t as int.

@@ -34,8 +34,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -288,7 +290,7 @@ struct next_args {
 	unsigned* next;     // [ch]: (end of the row that starts at s) + 1, | kAmbig
 };
 
-constexpr int kWinBlocks = 5; // window of Z values a warp searches at a time: 160 positions
+constexpr int kWinBlocks = 8; // window of Z values a warp searches at a time: 256 positions, kept as a ring of blocks
 
 __global__ void __launch_bounds__(128) fp_next(next_args a) {
 	__shared__ long long win_s[4][kWinBlocks * kBlk];
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(128) fp_next(next_args a) {
 		blk_lo += static_cast<long long>(j) * st; // the last probed block start that is not an end
 		span = st;
 	}
-	long long anchor = blk_lo; // block index
+	long long anchor = blk_lo; // first block of the window
+	long long filled = blk_lo; // blocks [anchor, filled) of the window hold their Z values (ring slot = block % kWinBlocks)
 
 	for (int i = 0; i < kSeg / kBlk; i++) {
 		long long const s   = s0 + i * kBlk + lane;
@@ -333,21 +336,23 @@ __global__ void __launch_bounds__(128) fp_next(next_args a) {
 		long long e         = -1;
 		bool certain        = false;
 		for (;;) {
-			// Z of the window's positions
-#pragma unroll
-			for (int b = 0; b < kWinBlocks; b++) {
+			// Z of the window's positions: the ends move on by about a block per batch of starts, so most of the window is
+			// still there from the batch before
+			if (filled < anchor)
+				filled = anchor;
+			for (; filled < anchor + kWinBlocks; filled++) {
 				long long o2;
-				long long const p1 = block_prefix(a.V, anchor + b, lane, o2);
-				win[b * kBlk + lane] = zval((anchor + b) * kBlk + lane, P.K, p1);
+				long long const p1 = block_prefix(a.V, filled, lane, o2);
+				win[(filled % kWinBlocks) * kBlk + lane] = zval(filled * kBlk + lane, P.K, p1);
 			}
 			__syncwarp();
 			long long const w0 = anchor * kBlk;
 			if (e < 0) {
-				// first j with win[j] - zp >= c_hi (wrap-safe: differences of nearby prefixes are small)
+				// first j with Z(w0 + j) - zp >= c_hi (wrap-safe: differences of nearby prefixes are small)
 				int lo = 0, hi = kWinBlocks * kBlk; // answer in [lo, hi]; hi = not in this window
 				while (lo < hi) {
 					int const mid = (lo + hi) >> 1;
-					if ((w0 + mid >= a.V.len) | (zdiff(win[mid], zp) >= P.c_hi)) // (nothing is looked for behind the chunk's draws)
+					if ((w0 + mid >= a.V.len) | (zdiff(win[(w0 + mid) % (kWinBlocks * kBlk)], zp) >= P.c_hi)) // (nothing is looked for behind the chunk's draws)
 						hi = mid;
 					else
 						lo = mid + 1;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(128) fp_next(next_args a) {
 				long long const t = w0 + lo;
 				if (lo < kWinBlocks * kBlk && t <= cap) {
 					e       = t;
-					certain = (zdiff(win[lo], zp) >= P.c_lo) | (t == cap);
+					certain = (zdiff(win[t % (kWinBlocks * kBlk)], zp) >= P.c_lo) | (t == cap);
 				} else if (cap < w0 + kWinBlocks * kBlk) {
 					e       = cap;
 					certain = true;
@@ -566,65 +571,92 @@ __global__ void __launch_bounds__(128) fp_rows(rows_args a) {
 	}
 }
 
-// One thread per listed row replays the reference's exact float recurrence, writes (or counts) the row and checks that
-// it ends exactly where the orbit said the next row starts.
+// One WARP per listed row replays the reference's exact float recurrence, writes (or counts) the row and checks that
+// it ends exactly where the orbit said the next row starts.  The recurrence is sequential (lane 0 runs it, one DFMA of
+// latency per draw), its inputs and outputs are not: the warp stages the draws tile by tile in shared memory, one tile
+// ahead of the chain, and classifies / stores the tile's targets with all lanes.
+constexpr int kExactTile = 256;
+
 __global__ void __launch_bounds__(128) fp_rows_exact(rows_args a) {
+	__shared__ double ybuf[4][kExactTile];
+	__shared__ int dbuf[4][kExactTile];
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned const nfix = *a.fix_count;
-	for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < nfix; f += gridDim.x * blockDim.x) {
+	params const& P     = a.P;
+	double const* y     = a.V.y;
+	for (unsigned f = blockIdx.x * 4 + warp; f < nfix; f += gridDim.x * 4) {
 		long long const r  = a.fix_list[f];
-		params const& P    = a.P;
 		long long const s  = a.row_start[r] - a.base;
 		long long const en = a.row_start[r + 1] - a.base - 1; // where the orbit says the terminating draw is
-		long long out      = a.write ? a.offsets[r] : 0;
-		long long kept = 0, left = 0;
-		double noise       = 0;
-		int index = 0, dst = 0;
-		long long t        = s;
-		double const* y    = a.V.y;
-		// The recurrence is sequential, its inputs are not: the draws are fetched 16 at a time, one batch ahead.
-		// Reads past the row's end stay inside the chunk's overlap margin.
-		constexpr int kAhead = 16;
-		double cur[kAhead], nxt[kAhead];
+		long long const out0 = a.write ? a.offsets[r] : 0;
+		long long kept = 0, left = 0; // warp-uniform totals
+		double noise = 0;             // lane 0's chain
+		int index    = 0;
+		long long t  = s;
+		bool bad     = false;
+		double reg[kExactTile / 32];
 #pragma unroll
-		for (int i = 0; i < kAhead; i++)
-			cur[i] = y[t + i];
+		for (int j = 0; j < kExactTile / 32; j++) {
+			long long const pos = t + j * 32 + lane;
+			reg[j]              = pos < a.V.len ? y[pos] : 0.0;
+		}
 		for (bool done = false; !done;) {
 #pragma unroll
-			for (int i = 0; i < kAhead; i++)
-				nxt[i] = y[t + kAhead + i];
+			for (int j = 0; j < kExactTile / 32; j++)
+				ybuf[warp][j * 32 + lane] = reg[j];
+			__syncwarp();
 #pragma unroll
-			for (int i = 0; i < kAhead; i++) {
-				if (done)
-					continue;
-				if (row_step(cur[i], P, noise, index, dst)) {
-					done = true;
-					continue;
-				}
-				if (dst < P.col_lo)
-					left++;
-				else if (dst < P.col_hi) {
-					if (a.write) {
-						if (out < a.capacity)
-							a.neighbors[out] = dst - static_cast<int>(P.col_lo);
-						out++;
-					}
-					kept++;
-				}
-				index++;
-				t++;
-				if (t > en) // would run past the orbit's row end: the check below reports it
-					done = true;
+			for (int j = 0; j < kExactTile / 32; j++) { // the next tile's draws are on their way while the chain runs
+				long long const pos = t + kExactTile + j * 32 + lane;
+				reg[j]              = pos < a.V.len ? y[pos] : 0.0;
 			}
-#pragma unroll
-			for (int i = 0; i < kAhead; i++)
-				cur[i] = nxt[i];
+			int cnt = kExactTile, state = 0; // state: 1 = the row ended inside this tile, 2 = it ran past the orbit's end
+			if (lane == 0) {
+				for (int i = 0; i < kExactTile; i++) {
+					if (t + i > en) { // would run past the orbit's row end: reported below
+						cnt   = i;
+						state = 2;
+						break;
+					}
+					int dst;
+					if (row_step(ybuf[warp][i], P, noise, index, dst)) {
+						cnt   = i;
+						state = (t + i == en) ? 1 : 2;
+						break;
+					}
+					dbuf[warp][i] = dst;
+					index++;
+				}
+			}
+			cnt   = __shfl_sync(0xffffffffu, cnt, 0);
+			state = __shfl_sync(0xffffffffu, state, 0);
+			__syncwarp();
+			// the tile's entries: targets ascend along a row, so the ones left of col_lo come first, then the kept ones
+			for (int i0 = 0; i0 < cnt; i0 += 32) {
+				int const i        = i0 + lane;
+				int const d        = i < cnt ? dbuf[warp][i] : 0x7fffffff;
+				bool const is_left = i < cnt && d < P.col_lo;
+				bool const is_kept = i < cnt && d >= P.col_lo && d < P.col_hi;
+				unsigned const ml  = __ballot_sync(0xffffffffu, is_left);
+				unsigned const mk  = __ballot_sync(0xffffffffu, is_kept);
+				left += __popc(ml);
+				if (a.write && is_kept) {
+					long long const o = out0 + kept + __popc(mk & ((1u << lane) - 1));
+					if (o < a.capacity)
+						a.neighbors[o] = d - static_cast<int>(P.col_lo);
+					else
+						bad = true;
+				}
+				kept += __popc(mk);
+			}
+			__syncwarp();
+			t += cnt;
+			bad |= state == 2;
+			done = state != 0;
 		}
-		if (t != en)
-			atomicOr(a.error, 1);
-		if (a.write) {
-			if (out > a.capacity)
-				atomicOr(a.error, 2);
-		} else {
+		if (__any_sync(0xffffffffu, bad) && lane == 0)
+			atomicOr(a.error, bad && a.write && out0 + kept > a.capacity ? 3 : 1);
+		if (lane == 0 && !a.write) {
 			a.degree[r] = kept;
 			if (a.below)
 				a.below[r] = left;
@@ -720,6 +752,17 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
                                result* out, std::string* err) {
 	auto stream = static_cast<cudaStream_t>(stream_);
 	*out        = result{};
+	// SPICE_GEN_TIMING=1: host wall-clock of the phases on stderr (synchronises at every lap)
+	bool const timing = std::getenv("SPICE_GEN_TIMING") != nullptr;
+	auto t_last       = std::chrono::steady_clock::now();
+	auto lap          = [&](char const* what) {
+        if (!timing)
+            return;
+        cudaStreamSynchronize(stream);
+        auto const now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[spice gen %lld x %lld] %-24s %8.2f ms\n", src, dst, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+	};
 	scratch S; // frees the scratch buffers and events on every return below; the result's arrays belong to the caller
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
 	GEN_CUDA(S.event(&ev0));
@@ -855,6 +898,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	GEN_CUDA(cudaMemsetAsync(error, 0, sizeof(int), stream));
 	GEN_CUDA(cudaMemsetAsync(row_flag, 0, sizeof(int) * static_cast<size_t>(src), stream));
 	GEN_CUDA(cudaMemsetAsync(row_start, 0, sizeof(long long), stream)); // row 0 starts at position 0
+	lap("allocations");
 
 	{
 		static bool uploaded[64] = {};
@@ -916,8 +960,10 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 		return static_cast<int>(cudaGetLastError());
 	};
 
+	lap("jump polynomials");
 	while (row < src) {
 		GEN_CUDA(static_cast<cudaError_t>(run_values(base)));
+		lap("values");
 		next_args na{P, V, ch, next};
 		fp_next<<<static_cast<unsigned>((ch / kSeg + 3) / 4), 128, 0, stream>>>(na);
 		unsigned const dgrid = static_cast<unsigned>((ch + 255) / 256);
@@ -933,6 +979,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 		GEN_CUDA(cudaGetLastError());
 		GEN_CUDA(cudaMemcpyAsync(st_host, st, sizeof(orbit_state), cudaMemcpyDeviceToHost, stream));
 		GEN_CUDA(cudaStreamSynchronize(stream));
+		lap("next + doubling + chase");
 		long long const rhi = st_host->row;
 		if (st_host->anchors > 0) {
 			fp_fill<<<static_cast<unsigned>((st_host->anchors + 127) / 128), 128, 0, stream>>>(next, anchor_pos, anchor_row, st_host->anchors, row, base,
@@ -952,6 +999,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 			GEN_CUDA(static_cast<cudaError_t>(run_rows(base, row, rhi, 0)));
 			chunks.push_back({base, row, rhi});
 		}
+		lap("rows");
 		if (rhi == row && st_host->pos < base + ch) {
 			if (err)
 				*err = "fixed_probability: orbit made no progress";
@@ -983,6 +1031,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 	GEN_CUDA(cudaMemcpyAsync(&herr, error, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	GEN_CUDA(cudaEventRecord(ev1, stream));
 	GEN_CUDA(cudaStreamSynchronize(stream));
+	lap("tail");
 	out->edges    = edges;
 	out->launches = launches;
 	out->rows_ms  = rows_ms;

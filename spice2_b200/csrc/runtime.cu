@@ -680,6 +680,14 @@ int finalize(spice_ctx* ctx) {
 		dmax = std::max(dmax, c.delay);
 	}
 	ctx->window = static_cast<int>(std::max<long long>(1, std::min<long long>(dmin, kMaxWindow)));
+	{
+		// the delivery kernel stages the spike counts of (connection, step) in shared memory (deliver::kMaxCounts)
+		long long stateless = 0;
+		for (auto const& c : ctx->conns)
+			stateless += c.stateful ? 0 : 1;
+		if (stateless > 0)
+			ctx->window = static_cast<int>(std::max<long long>(1, std::min<long long>(ctx->window, deliver::kMaxCounts / stateless)));
+	}
 	for (auto const& c : ctx->conns)
 		if (c.stateful) {
 			// a stateful synapse's delivery at step t depends on its target's spikes up to step t
