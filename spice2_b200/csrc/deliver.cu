@@ -99,6 +99,8 @@ __device__ __forceinline__ void tally(int4 v) {
 	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.w) : "memory");
 }
 
+__device__ unsigned g_zero_pair[2]; // an empty run, for lanes without a spike
+
 // what the unit path needs of a connection (a copy in shared memory; conn_desc stays in global memory)
 struct conn_hot {
 	char const* stream;
@@ -258,7 +260,8 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	// spike ids requested (idn), run pointers requested (nxt), runs being fetched and counted (cur)
 	bool id_valid = false;
 	unsigned id_seq = 0;
-	std::int32_t id_src = -1;
+	std::int32_t id_src = 0;
+	bool id_ok = false; // this lane's share of the batch is a spike (else: behind the end of the list)
 	int id_c = 0, id_k = 0;
 	batch nxt{0, 0, 0, 0, false}, cur{0, 0, 0, 0, false};
 	unsigned q_cur = 0;        // quarters of cur whose copies have been issued (kStages in the steady state)
@@ -303,52 +306,47 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			nxt.valid = false;
 		}
 		if (!nxt.valid && id_valid) {
-			nxt.valid  = true;
-			nxt.seq    = id_seq;
-			nxt.c      = id_c;
-			nxt.g0 = nxt.ng = 0;
-			if (id_src >= 0) {
-				unsigned const* p = sh.conns[id_c].run_ptr + (static_cast<long long>(id_src) * sh.conns[id_c].tiles + id_k);
-				nxt.g0            = p[0];
-				nxt.ng            = p[1]; // end of the run for now: issue() subtracts (the loads are still in flight)
-			}
-			id_valid = false;
+			nxt.valid = true;
+			nxt.seq   = id_seq;
+			nxt.c     = id_c;
+			// always a load, never a merge with a constant: the two words land in nxt's own registers and nobody waits
+			// for them before issue() (a lane without a spike reads a pair of zeros: an empty run)
+			unsigned const* p = id_ok ? sh.conns[id_c].run_ptr + (static_cast<long long>(id_src) * sh.conns[id_c].tiles + id_k) : g_zero_pair;
+			nxt.g0            = p[0];
+			nxt.ng            = p[1]; // end of the run for now: issue() subtracts (the loads are still in flight)
+			id_valid          = false;
 		}
 		if (!id_valid) {
 			unsigned seq, b;
 			if (cursor_next(seq, b)) {
-				unsigned const q = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
-				id_valid  = true;
-				id_seq    = seq;
-				id_src    = -1;
-				if (q < cs_total) {
-					if (world == 1)
-						id_src = cs_ids[q];
-					else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
-						unsigned const* pre = sh.cnts + cs_cs * world;
-						int r               = 0;
-						while (pre[r] <= q)
-							r++;
-						id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + a.conns[cs_c].seg_lo[r] + (q - (r ? pre[r - 1] : 0u)));
-					}
+				unsigned const q  = kRuns * (warp + kW * (kQuarters * b + lane / kRuns)) + lane % kRuns;
+				unsigned const qc = min(q, cs_total - 1); // (a cursor batch exists only in units with spikes)
+				id_valid = true;
+				id_seq   = seq;
+				id_ok    = q < cs_total;
+				if (world == 1)
+					id_src = cs_ids[qc];
+				else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
+					unsigned const* pre = sh.cnts + cs_cs * world;
+					int r               = 0;
+					while (pre[r] <= qc)
+						r++;
+					id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + a.conns[cs_c].seg_lo[r] + (qc - (r ? pre[r - 1] : 0u)));
 				}
-				id_c      = cs_c;
-				id_k      = cs_k;
+				id_c = cs_c;
+				id_k = cs_k;
 			}
 		}
 	};
 	// Once per batch.  In the steady state one step fills cur from values requested a whole batch ago; only an empty
 	// pipeline (the CTA's first unit, or a cursor that had run into the look-ahead limit) takes the dependent steps, behind
-	// a real branch: a predicated move of a value still in flight would wait for it whether it is needed or not.
+	// a real branch: a move of a value still in flight would wait for it whether it is needed or not.
 	auto refill = [&]() {
-		advance();
-		if (!cur.valid && (nxt.valid || id_valid)) {
-			asm volatile("" ::: "memory");
+#pragma unroll 1
+		for (int pass = 0; pass < 3; pass++) { // ONE copy of the code: the state keeps its registers, nothing is moved (and waited for) at a join
 			advance();
-			if (!cur.valid && (nxt.valid || id_valid)) {
-				asm volatile("" ::: "memory");
-				advance();
-			}
+			if (cur.valid || !(nxt.valid || id_valid))
+				break;
 		}
 	};
 	// issue the copies of quarter q of batch b into stage slot `st`
