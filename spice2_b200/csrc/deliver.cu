@@ -115,7 +115,7 @@ struct conn_hot {
 template <int kW, int kStages>
 struct alignas(16) cta_state {
 	unsigned long long bars[kW][kStages];
-	unsigned tickets[kTicketRing];       // the CTA's unit sequence: tickets[seq % kTicketRing]
+	int4 units[kTicketRing];             // the CTA's unit sequence, located: units[seq % kTicketRing] = {connection, step, tile, spikes}; x < 0: no unit
 	unsigned cnts[kMaxCounts];           // spikes of (connection, step): world == 1 the total; else the inclusive prefix over ranks
 	int prefix[kMaxConns + 1];           // tile_prefix of the connections, + total_tiles
 	conn_hot conns[kMaxConns];           // the launch's connections: nothing on the unit path reads them from global memory
@@ -222,8 +222,6 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		sh.conns[i] = conn_hot{reinterpret_cast<char const*>(C.packed), C.run_ptr, C.counts, C.ring_ids, C.ring_cap, C.cstride, C.n_dst,
 		                       C.tiles, C.tile, static_cast<int>(C.delay), C.cring, C.arranged, 0};
 	}
-	if (tid < kTicketRing)
-		sh.tickets[tid] = tid < kStaticUnits ? static_ticket(blockIdx.x, gridDim.x, tid) : 0xffffffffu;
 	for (int i = tid; i < (cnt_words + 3) / 4; i += kW * 32)
 		smem4[i] = make_uint4(0, 0, 0, 0);
 	if (lane < kStages)
@@ -234,19 +232,26 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	if (tid == 0)
 		pending = atomicAdd(a.work, 1u);
 	__syncthreads();
+	// a ticket is located once, by the thread that publishes it: {connection, step, tile, spikes of the step}
+	auto locate = [&](unsigned ticket) {
+		if (ticket >= units)
+			return make_int4(-1, 0, 0, 0);
+		unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
+		return make_int4(p.c, p.s, p.k, static_cast<int>(sh.cnts[(p.c * a.nsteps + p.s) * world + world - 1]));
+	};
+	if (tid < kTicketRing)
+		sh.units[tid] = tid < kStaticUnits ? locate(static_ticket(blockIdx.x, gridDim.x, tid)) : make_int4(-1, 0, 0, 0);
+	__syncthreads();
 
 	auto view = [&](unsigned seq) {
+		int4 const r = sh.units[seq % kTicketRing];
 		unit_view v{};
-		unsigned const ticket = sh.tickets[seq % kTicketRing];
-		v.valid               = ticket < units;
-		if (v.valid) {
-			unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
-			v.c     = p.c;
-			v.s     = p.s;
-			v.k     = p.k;
-			v.total = sh.cnts[(p.c * a.nsteps + p.s) * world + world - 1];
-			v.cs    = p.c * a.nsteps + p.s;
-		}
+		v.valid = r.x >= 0;
+		v.c     = r.x;
+		v.s     = r.y;
+		v.k     = r.z;
+		v.total = static_cast<unsigned>(r.w);
+		v.cs    = r.x * a.nsteps + r.y;
 		return v;
 	};
 
@@ -257,13 +262,14 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	bool cs_known = false, cs_end = false;
 	std::int32_t const* cs_ids = nullptr;
 	int cs_cs = 0, cs_c = 0, cs_k = 0;
-	// spike ids requested (idn), run pointers requested (nxt), runs being fetched and counted (cur)
+	// spike ids requested (id_*), run pointers requested (nx2), run pointers landed (nxt: its first quarters are issued while
+	// cur is counted), runs being fetched and counted (cur)
 	bool id_valid = false;
 	unsigned id_seq = 0;
 	std::int32_t id_src = 0;
 	bool id_ok = false; // this lane's share of the batch is a spike (else: behind the end of the list)
 	int id_c = 0, id_k = 0;
-	batch nxt{0, 0, 0, 0, false}, cur{0, 0, 0, 0, false};
+	batch nx2{0, 0, 0, 0, false}, nxt{0, 0, 0, 0, false}, cur{0, 0, 0, 0, false};
 	unsigned q_cur = 0;        // quarters of cur whose copies have been issued (kStages in the steady state)
 	unsigned parity = 0;       // kStages == 4: the mbarriers' phase of the batch being counted
 	unsigned long long ev = 0; // Syn::deliver invocations this thread has merged
@@ -298,22 +304,26 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			cs_known = false;
 		}
 	};
-	// move every prefetch stage forward by one: cur <- nxt <- (run pointers of the ids requested last time) <- (ids of the
-	// cursor's next batch).  Nothing here reads what it has just requested: the values are consumed one call later.
+	// move every prefetch stage forward by one: cur <- nxt <- nx2 <- (run pointers of the ids requested last time) <- (ids
+	// of the cursor's next batch).  Nothing here reads what it has just requested: the values are consumed one call later.
 	auto advance = [&]() {
 		if (!cur.valid && nxt.valid) {
 			cur       = nxt;
 			nxt.valid = false;
 		}
-		if (!nxt.valid && id_valid) {
-			nxt.valid = true;
-			nxt.seq   = id_seq;
-			nxt.c     = id_c;
-			// always a load, never a merge with a constant: the two words land in nxt's own registers and nobody waits
-			// for them before issue() (a lane without a spike reads a pair of zeros: an empty run)
+		if (!nxt.valid && nx2.valid) {
+			nxt       = nx2;
+			nx2.valid = false;
+		}
+		if (!nx2.valid && id_valid) {
+			nx2.valid = true;
+			nx2.seq   = id_seq;
+			nx2.c     = id_c;
+			// always a load, never a merge with a constant: the two words land in nx2's own registers and nobody waits
+			// for them before the next call (a lane without a spike reads a pair of zeros: an empty run)
 			unsigned const* p = id_ok ? sh.conns[id_c].run_ptr + (static_cast<long long>(id_src) * sh.conns[id_c].tiles + id_k) : g_zero_pair;
-			nxt.g0            = p[0];
-			nxt.ng            = p[1]; // end of the run for now: issue() subtracts (the loads are still in flight)
+			nx2.g0            = p[0];
+			nx2.ng            = p[1]; // the END of the run: issue() subtracts
 			id_valid          = false;
 		}
 		if (!id_valid) {
@@ -343,9 +353,9 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	// a real branch: a move of a value still in flight would wait for it whether it is needed or not.
 	auto refill = [&]() {
 #pragma unroll 1
-		for (int pass = 0; pass < 3; pass++) { // ONE copy of the code: the state keeps its registers, nothing is moved (and waited for) at a join
+		for (int pass = 0; pass < 4; pass++) { // ONE copy of the code: the state keeps its registers, nothing is moved (and waited for) at a join
 			advance();
-			if (cur.valid || !(nxt.valid || id_valid))
+			if (cur.valid || !(nxt.valid || nx2.valid || id_valid))
 				break;
 		}
 	};
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 			}
 		}
 		if (tid == 0) { // the ticket claimed while this unit ran becomes unit done + kStaticUnits; claim the one after it
-			sh.tickets[(done + kStaticUnits) % kTicketRing] = dynamic_ticket(gridDim.x, pending);
+			sh.units[(done + kStaticUnits) % kTicketRing] = locate(dynamic_ticket(gridDim.x, pending));
 			pending                                         = atomicAdd(a.work, 1u);
 		}
 		__syncthreads();
