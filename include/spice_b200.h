@@ -197,6 +197,8 @@ SPICE_API int64_t spice_adjacency_edges(spice_adjacency const* a);
 SPICE_API void* spice_adjacency_offsets_dev(spice_adjacency const* a);   /* int64[src_count+1] */
 SPICE_API void* spice_adjacency_neighbors_dev(spice_adjacency const* a); /* int32[edges] */
 SPICE_API int spice_adjacency_copy(spice_adjacency const* a, int64_t* offsets_host, int32_t* neighbors_host);
+/* entries [edge_lo, edge_hi) of the neighbors array (a block of rows of an adjacency too large to copy whole) */
+SPICE_API int spice_adjacency_copy_range(spice_adjacency const* a, int64_t edge_lo, int64_t edge_hi, int32_t* neighbors_host);
 /* device-side timings of the last generation, milliseconds: total and the row-writing kernel */
 SPICE_API int spice_adjacency_timing(spice_adjacency const* a, float* total_ms, float* rows_kernel_ms, int64_t* draws);
 SPICE_API int spice_adjacency_destroy(spice_adjacency* a);

@@ -155,6 +155,41 @@ void orc_xoroshiro_state_at(orc_u128 seed, int64_t k, uint64_t state[2]) {
 	state[1] = r.s1;
 }
 
+/* Engine state after k draws without walking them.  The state update of xoroshiro128+ (random.h:222-234) is linear over
+ * GF(2): one step is a 128 x 128 bit matrix T, k steps are T^k, built from T^(2^i) by repeated squaring.  For streams no
+ * CPU can walk in a test (bench/connectivity at 1e6 x 1e6 draws 1e11 values); checked against the walk in tests. */
+typedef struct {
+	uint64_t lo, hi;
+} bits128;
+static bits128 mat_vec(bits128 const m[128], bits128 v) {
+	bits128 r = {0, 0};
+	for (int j = 0; j < 128; j++)
+		if ((j < 64 ? v.lo >> j : v.hi >> (j - 64)) & 1u) {
+			r.lo ^= m[j].lo;
+			r.hi ^= m[j].hi;
+		}
+	return r;
+}
+void orc_xoroshiro_jump(orc_u128 seed, uint64_t k, uint64_t state[2]) {
+	bits128 m[128], sq[128];
+	for (int j = 0; j < 128; j++) { /* column j of T: one step from the basis state e_j */
+		xoro r = {j < 64 ? 1ull << j : 0, j < 64 ? 0 : 1ull << (j - 64)};
+		(void)xoro_next(&r);
+		m[j].lo = r.s0;
+		m[j].hi = r.s1;
+	}
+	bits128 v = {seed.lo, seed.hi};
+	for (; k; k >>= 1) {
+		if (k & 1)
+			v = mat_vec(m, v);
+		for (int j = 0; j < 128; j++)
+			sq[j] = mat_vec(m, m[j]);
+		memcpy(m, sq, sizeof m);
+	}
+	state[0] = v.lo;
+	state[1] = v.hi;
+}
+
 /* generate_canonical<float,false> on a 64-bit engine (random.h:236-247): top 24 bits / 2^24 */
 static inline float canonical_float(xoro* r) { return (float)(xoro_next(r) >> 40) / 16777216.0f; }
 /* generate_canonical<double,true>: ((r >> 11) + 1) / 2^53, in (0,1] */
@@ -262,6 +297,44 @@ int64_t orc_fixed_probability_generate(int64_t src, int64_t dst, double p, orc_u
 		offsets[src] = count;
 	if (draws_out)
 		*draws_out = draws;
+	return count;
+}
+
+/* `rows` consecutive rows of the same loop (topology.cpp:89-110), started from the engine state at the first row's first
+ * draw: for matrices whose stream is entered by orc_xoroshiro_jump.  Only targets in [col_lo, col_hi) are kept, as local
+ * columns (a rank's share of a sharded adjacency); kept_degree / full_degree receive one entry per row.  Returns the
+ * number of kept entries (those beyond `cap` are counted, not written). */
+int64_t orc_fixed_probability_rows_from(uint64_t const state[2], int64_t rows, int64_t dst, double p, int64_t col_lo,
+                                        int64_t col_hi, int64_t* kept_degree, int64_t* full_degree, int32_t* neighbors,
+                                        int64_t cap) {
+	xoro rng                 = {state[0], state[1]};
+	double const c           = 1.0 - 1.0 / p;
+	int64_t const max_degree = orc_fixed_probability_max_degree(dst, p);
+	int64_t count            = 0;
+	for (int64_t s = 0; s < rows; s++) {
+		int32_t index = 0;
+		int64_t kept  = 0;
+		double noise  = 0;
+		for (;;) {
+			double const u    = (double)((xoro_next(&rng) >> 11) + 1) * 0x1p-53;
+			noise             = fma(log(u), c, noise);
+			int32_t const d32 = (int32_t)((uint32_t)index +
+			                              (uint32_t)cvttsd2si32(noise + copysign(0x1.fffffffffffffp-2, noise)));
+			if (((int64_t)d32 >= dst) | (index >= max_degree))
+				break;
+			if (d32 >= col_lo && d32 < col_hi) {
+				if (neighbors && count < cap)
+					neighbors[count] = (int32_t)(d32 - col_lo);
+				count++;
+				kept++;
+			}
+			index++;
+		}
+		if (kept_degree)
+			kept_degree[s] = kept;
+		if (full_degree)
+			full_degree[s] = index;
+	}
 	return count;
 }
 

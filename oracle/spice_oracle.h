@@ -31,6 +31,8 @@ orc_u128 orc_seed_next(orc_u128 s);                   /* random.h:163-167 (seed+
 orc_u128 orc_seed_stream(orc_u128 s, uint64_t id);    /* random.h:169 */
 void orc_xoroshiro(orc_u128 seed, int64_t count, uint64_t* out); /* random.h:222-234 */
 void orc_xoroshiro_state_at(orc_u128 seed, int64_t k, uint64_t state[2]);
+/* the same by GF(2) matrix powers, for positions no test can walk to (1e11 draws at 1e6 x 1e6) */
+void orc_xoroshiro_jump(orc_u128 seed, uint64_t k, uint64_t state[2]);
 void orc_kahan_dt(float dt, int64_t steps, float* out);          /* numeric.h:9-15, snn.cpp:8-10 */
 uint64_t orc_fnv1a64(void const* data, int64_t bytes);
 
@@ -43,6 +45,11 @@ int64_t orc_fixed_probability_size(int64_t src, int64_t dst, double p);
 int64_t orc_fixed_probability_generate(int64_t src, int64_t dst, double p, orc_u128 seed,
                                        int64_t* offsets, int32_t* neighbors, uint64_t* row_hash,
                                        int64_t* draws_out);
+
+/* rows of the same loop from the engine state at a row's first draw; targets in [col_lo, col_hi) kept as local columns */
+int64_t orc_fixed_probability_rows_from(uint64_t const state[2], int64_t rows, int64_t dst, double p, int64_t col_lo,
+                                        int64_t col_hi, int64_t* kept_degree, int64_t* full_degree, int32_t* neighbors,
+                                        int64_t cap);
 
 /* ---- networks ---------------------------------------------------------------------------- */
 enum { ORC_POISSON = 0, ORC_LIF_BRUNEL = 1, ORC_LIF_VOGELS = 2 };

@@ -18,7 +18,7 @@ import numpy as np
 
 from .build import build as _build
 
-__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "seed_seq", "fnv1a64",
+__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "Adjacency", "seed_seq", "fnv1a64",
            "MODE_DETERMINISTIC", "MODE_FAST"]
 
 MODE_DETERMINISTIC, MODE_FAST = 0, 1
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
             "spice_adjacency_offsets_dev": (vp, [vp]),
             "spice_adjacency_neighbors_dev": (vp, [vp]),
             "spice_adjacency_copy": (i32, [vp, vp, vp]),
+            "spice_adjacency_copy_range": (i32, [vp, i64, i64, vp]),
             "spice_adjacency_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i64)]),
             "spice_adjacency_destroy": (i32, [vp]),
             "spice_seed_seq": (None, [vp, i32, vp]),
@@ -369,6 +370,54 @@ def fnv1a64(a) -> str:
     """FNV-1a (64 bit) of an array's bytes as 16 hex digits — the digest the golden fixtures use."""
     a = np.ascontiguousarray(a)
     return f"{int(lib().spice_fnv1a64(_ptr(a), a.nbytes)):016x}"
+
+
+class Adjacency:
+    """A generated adjacency that stays on the device (bench/connectivity sizes whose arrays do not fit the host):
+    offsets() and rows(lo, hi) copy what is asked for."""
+
+    def __init__(self, src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None):
+        L = lib()
+        lo, hi = seed_seq(seed, increments)
+        self.src, self.dst = src, dst
+        self.col_lo, self.col_hi = col_lo, dst if col_hi is None else col_hi
+        self.h = C.c_void_p()
+        rc = L.spice_fixed_probability_generate(device, src, dst, p, lo, hi, self.col_lo, self.col_hi, C.byref(self.h))
+        if rc != 0:
+            raise SpiceError(rc, L.spice_last_error(None).decode())
+        self.edges = int(L.spice_adjacency_edges(self.h))
+        total, rows = C.c_float(), C.c_float()
+        draws = C.c_int64()
+        L.spice_adjacency_timing(self.h, C.byref(total), C.byref(rows), C.byref(draws))
+        self.total_ms, self.rows_ms, self.draws = total.value, rows.value, draws.value
+        self._off = None
+
+    def offsets(self):
+        if self._off is None:
+            off = np.zeros(self.src + 1, np.int64)
+            if lib().spice_adjacency_copy(self.h, _ptr(off), None) != 0:
+                raise SpiceError(2, "adjacency copy failed")
+            self._off = off
+        return self._off
+
+    def rows(self, lo, hi):
+        """neighbors of rows [lo, hi) (local columns), one flat array."""
+        off = self.offsets()
+        out = np.zeros(max(int(off[hi] - off[lo]), 1), np.int32)
+        if lib().spice_adjacency_copy_range(self.h, int(off[lo]), int(off[hi]), _ptr(out)) != 0:
+            raise SpiceError(2, "adjacency copy failed")
+        return out[: int(off[hi] - off[lo])]
+
+    def close(self):
+        if self.h:
+            lib().spice_adjacency_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True):

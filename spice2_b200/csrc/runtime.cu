@@ -2240,6 +2240,16 @@ int spice_adjacency_copy(spice_adjacency const* a, int64_t* offsets_host, int32_
 	return SPICE_OK;
 }
 
+int spice_adjacency_copy_range(spice_adjacency const* a, int64_t edge_lo, int64_t edge_hi, int32_t* neighbors_host) {
+	if (!a || edge_lo < 0 || edge_hi < edge_lo || edge_hi > a->r.edges || (!neighbors_host && edge_hi > edge_lo))
+		return SPICE_ERR_PRECONDITION;
+	cudaSetDevice(a->device);
+	if (edge_hi > edge_lo && cudaMemcpy(neighbors_host, a->r.neighbors + edge_lo, sizeof(std::int32_t) * static_cast<size_t>(edge_hi - edge_lo),
+	                                   cudaMemcpyDeviceToHost) != cudaSuccess)
+		return SPICE_ERR_CUDA;
+	return SPICE_OK;
+}
+
 int spice_adjacency_timing(spice_adjacency const* a, float* total_ms, float* rows_kernel_ms, int64_t* draws) {
 	if (total_ms)
 		*total_ms = a->r.total_ms;

@@ -57,6 +57,10 @@ class Oracle:
         L.orc_seed_stream.argtypes = [U128, C.c_uint64]
         L.orc_xoroshiro.argtypes = [U128, C.c_int64, C.c_void_p]
         L.orc_xoroshiro_state_at.argtypes = [U128, C.c_int64, C.c_void_p]
+        L.orc_xoroshiro_jump.argtypes = [U128, C.c_uint64, C.c_void_p]
+        L.orc_fixed_probability_rows_from.restype = C.c_int64
+        L.orc_fixed_probability_rows_from.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_int64]
         L.orc_kahan_dt.argtypes = [C.c_float, C.c_int64, C.c_void_p]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fnv1a64.argtypes = [C.c_void_p, C.c_int64]
@@ -117,6 +121,12 @@ class Oracle:
         self.L.orc_xoroshiro_state_at(seed, k, _ptr(out))
         return int(out[0]), int(out[1])
 
+    def jump(self, seed: U128, k):
+        """Engine state after k draws by GF(2) matrix powers (no walk)."""
+        out = np.zeros(2, np.uint64)
+        self.L.orc_xoroshiro_jump(seed, C.c_uint64(k), _ptr(out))
+        return int(out[0]), int(out[1])
+
     def kahan_dt(self, dt, steps):
         out = np.zeros(steps, np.float32)
         self.L.orc_kahan_dt(dt, steps, _ptr(out))
@@ -140,6 +150,19 @@ class Oracle:
                                                       C.byref(draws)))
         return dict(edges=e, offsets=offsets, neighbors=None if nb is None else nb[:e], row_hash=rh,
                     draws=int(draws.value), capacity=cap)
+
+    def fixed_probability_rows(self, state, rows, dst, p, col_lo=0, col_hi=None, want_neighbors=True):
+        """`rows` consecutive rows from the engine state at the first row's first draw; targets in [col_lo, col_hi) kept
+        as local columns -> dict(kept_degree, full_degree, neighbors)."""
+        col_hi = dst if col_hi is None else col_hi
+        st = np.asarray(state, np.uint64)
+        kd, fd = np.zeros(rows, np.int64), np.zeros(rows, np.int64)
+        cap = int(rows * min(self.max_degree(dst, p), col_hi - col_lo)) if want_neighbors else 0
+        nb = np.zeros(max(cap, 1), np.int32) if want_neighbors else None
+        self.L.orc_fixed_probability_rows_from.restype = C.c_int64
+        n = int(self.L.orc_fixed_probability_rows_from(_ptr(st), C.c_int64(rows), C.c_int64(dst), C.c_double(p), C.c_int64(col_lo),
+                                                       C.c_int64(col_hi), _ptr(kd), _ptr(fd), _ptr(nb), C.c_int64(cap)))
+        return dict(kept=n, kept_degree=kd, full_degree=fd, neighbors=None if nb is None else nb[:n])
 
     # -- networks ---------------------------------------------------------------------------
     def net(self, dt, max_delay, seed_il=(1337,), flavour=STRICT, rank=0, world=1):
