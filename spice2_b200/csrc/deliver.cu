@@ -115,7 +115,8 @@ struct conn_hot {
 template <int kW, int kStages>
 struct alignas(16) cta_state {
 	unsigned long long bars[kW][kStages];
-	int4 units[kTicketRing];             // the CTA's unit sequence, located: units[seq % kTicketRing] = {connection, step, tile, spikes}; x < 0: no unit
+	int4 units[kTicketRing];             // the CTA's unit sequence, located: units[seq % kTicketRing] = {connection | step << 8 | round << 16, tile,
+	                                     // first spike, spikes}; x < 0: no unit
 	unsigned cnts[kMaxCounts];           // spikes of (connection, step): world == 1 the total; else the inclusive prefix over ranks
 	int prefix[kMaxConns + 1];           // tile_prefix of the connections, + total_tiles
 	conn_hot conns[kMaxConns];           // the launch's connections: nothing on the unit path reads them from global memory
@@ -124,6 +125,8 @@ struct alignas(16) cta_state {
 // A unit as a warp needs it (warp-uniform)
 struct unit_view {
 	int c, s, k;
+	int r;          // round: launches with few, long units hand every unit out in tiles_args::rounds parts of its spike list
+	unsigned base;  // first spike of the round in the step's list
 	int cs; // (connection, step) index
 	unsigned total;
 	bool valid;
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	// the address the stream entries were built for (counter_base(); checked below)
 	extern __shared__ uint4 smem4[];
 	int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	unsigned const units  = static_cast<unsigned>(a.total_tiles) * a.nsteps;
+	unsigned const rounds = static_cast<unsigned>(a.rounds);
+	unsigned const units  = static_cast<unsigned>(a.total_tiles) * a.nsteps * rounds; // work items: (connection, step, tile, round)
 	unsigned const cnt    = smem_u32(smem4);                                  // counters: arrays A, B, dump
 	int const cnt_words   = 2 * a.tile_cap + 32;
 	cta_state<kW, kStages>& sh = *reinterpret_cast<cta_state<kW, kStages>*>(reinterpret_cast<char*>(smem4) + static_cast<size_t>(cnt_words) * 4);
@@ -236,8 +240,13 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	auto locate = [&](unsigned ticket) {
 		if (ticket >= units)
 			return make_int4(-1, 0, 0, 0);
-		unit_pos const p = locate_unit(ticket, sh.prefix, a.nconns, a.nsteps);
-		return make_int4(p.c, p.s, p.k, static_cast<int>(sh.cnts[(p.c * a.nsteps + p.s) * world + world - 1]));
+		unit_pos const p   = locate_unit(ticket / rounds, sh.prefix, a.nconns, a.nsteps);
+		unsigned const r   = ticket % rounds;
+		unsigned const tot = sh.cnts[(p.c * a.nsteps + p.s) * world + world - 1];
+		// round r of a unit: spikes [tot r / rounds, tot (r + 1) / rounds) of the step's list, cut at multiples of a quarter
+		unsigned const lo = r == 0 ? 0u : (static_cast<unsigned>(static_cast<unsigned long long>(tot) * r / rounds) & ~(kRuns - 1u));
+		unsigned const hi = r + 1 == rounds ? tot : (static_cast<unsigned>(static_cast<unsigned long long>(tot) * (r + 1) / rounds) & ~(kRuns - 1u));
+		return make_int4(p.c | (p.s << 8) | (static_cast<int>(r) << 16), p.k, static_cast<int>(lo), static_cast<int>(hi - lo));
 	};
 	if (tid < kTicketRing)
 		sh.units[tid] = tid < kStaticUnits ? locate(static_ticket(blockIdx.x, gridDim.x, tid)) : make_int4(-1, 0, 0, 0);
@@ -247,18 +256,20 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		int4 const r = sh.units[seq % kTicketRing];
 		unit_view v{};
 		v.valid = r.x >= 0;
-		v.c     = r.x;
-		v.s     = r.y;
-		v.k     = r.z;
+		v.c     = r.x & 0xff;
+		v.s     = (r.x >> 8) & 0xff;
+		v.r     = r.x >> 16;
+		v.k     = r.y;
+		v.base  = static_cast<unsigned>(r.z);
 		v.total = static_cast<unsigned>(r.w);
-		v.cs    = r.x * a.nsteps + r.y;
+		v.cs    = v.c * a.nsteps + v.s;
 		return v;
 	};
 
 	// ---- per-warp pipeline state -------------------------------------------------------------------------
 	unsigned done = 0; // units of this CTA merged so far = the unit being counted
 	// cursor: the next batch of this warp whose spike ids have not been requested yet
-	unsigned cs_seq = 0, cs_b = 0, cs_total = 0, cs_nbatch = 0;
+	unsigned cs_seq = 0, cs_b = 0, cs_total = 0, cs_nbatch = 0, cs_base = 0;
 	bool cs_known = false, cs_end = false;
 	std::int32_t const* cs_ids = nullptr;
 	int cs_cs = 0, cs_c = 0, cs_k = 0;
@@ -287,6 +298,7 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				conn_hot const& C    = sh.conns[v.c];
 				long long const slot = (a.t0 + v.s) % a.ring;
 				cs_total  = v.total;
+				cs_base   = v.base;
 				cs_nbatch = C.arranged ? warp_batches<kW>(v.total, warp) : 0; // plain units are walked at their merge
 				cs_ids    = C.ring_ids + slot * C.ring_cap;
 				cs_cs     = v.cs;
@@ -334,14 +346,15 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				id_valid = true;
 				id_seq   = seq;
 				id_ok    = q < cs_total;
+				unsigned const g  = cs_base + qc; // its place in the step's list
 				if (world == 1)
-					id_src = cs_ids[qc];
-				else { // spike q of the step: the (q - spikes of the ranks before r)-th of rank r's segment
+					id_src = cs_ids[g];
+				else { // spike g of the step: the (g - spikes of the ranks before r)-th of rank r's segment
 					unsigned const* pre = sh.cnts + cs_cs * world;
 					int r               = 0;
-					while (pre[r] <= qc)
+					while (pre[r] <= g)
 						r++;
-					id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + a.conns[cs_c].seg_lo[r] + (qc - (r ? pre[r - 1] : 0u)));
+					id_src = *reinterpret_cast<volatile std::int32_t const*>(cs_ids + a.conns[cs_c].seg_lo[r] + (g - (r ? pre[r - 1] : 0u)));
 				}
 				id_c = cs_c;
 				id_k = cs_k;
@@ -446,14 +459,18 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 		std::uint32_t* out = C.counts + ((t + C.delay) % C.cring) * C.cstride + lo;
 		int const quads    = (width + 3) / 4;
 		uint4* o           = reinterpret_cast<uint4*>(out);
-		if (tid == 0 && U.k == 0 && U.total)
+		if (tid == 0 && U.k == 0 && U.total) // (every round adds its own share of the step's spikes)
 			atomicAdd(a.stats + 1, static_cast<unsigned long long>(U.total));
 		if (!C.arranged) {
-			for (int i = tid; i < quads; i += kW * 32)
-				o[i] = make_uint4(0, 0, 0, 0);
-			__threadfence_block();
-			__syncthreads();
-			if (U.total) {
+			// plain columns: the whole unit in its round 0 (the rare path is not split)
+			if (!a.prezeroed) {
+				for (int i = tid; i < quads; i += kW * 32)
+					o[i] = make_uint4(0, 0, 0, 0);
+				__threadfence_block();
+				__syncthreads();
+			}
+			unsigned const tot = sh.cnts[U.cs * world + world - 1];
+			if (tot && U.r == 0) {
 				std::int32_t const* ids = C.ring_ids + ((a.t0 + U.s) % a.ring) * C.ring_cap;
 				unsigned before         = 0;
 				for (int r = 0; r < world; r++) { // one segment per rank (one rank: the whole list)
@@ -463,8 +480,9 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				}
 			}
 		} else if (U.total == 0) {
-			for (int i = tid; i < quads; i += kW * 32)
-				o[i] = make_uint4(0, 0, 0, 0);
+			if (!a.prezeroed) // (pre-zeroed counters: the consumer clears what it has read, nothing to store)
+				for (int i = tid; i < quads; i += kW * 32)
+					o[i] = make_uint4(0, 0, 0, 0);
 		} else {
 			unsigned const cap4 = static_cast<unsigned>(a.tile_cap) * 4;
 			for (int i = tid; i < quads; i += kW * 32) {
@@ -483,7 +501,19 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 				}
 				uint4 const c = make_uint4(ca.x + cb[0], ca.y + cb[1], ca.z + cb[2], ca.w + cb[3]);
 				ev += c.x + c.y + c.z + c.w;
-				o[i] = c;
+				if (rounds == 1)
+					o[i] = c; // the only writer of this range in this window
+				else { // one of several rounds: added to counters the consumer left at zero (integer sums: any order, same bits)
+					std::uint32_t* at = out + t0;
+					if (c.x)
+						asm volatile("red.global.add.u32 [%0], %1;" ::"l"(at), "r"(c.x) : "memory");
+					if (c.y)
+						asm volatile("red.global.add.u32 [%0], %1;" ::"l"(at + 1), "r"(c.y) : "memory");
+					if (c.z)
+						asm volatile("red.global.add.u32 [%0], %1;" ::"l"(at + 2), "r"(c.z) : "memory");
+					if (c.w)
+						asm volatile("red.global.add.u32 [%0], %1;" ::"l"(at + 3), "r"(c.w) : "memory");
+				}
 			}
 		}
 		if (tid == 0) { // the ticket claimed while this unit ran becomes unit done + kStaticUnits; claim the one after it
@@ -836,7 +866,7 @@ shape const kShapes[4] = {{deliver_units<8, 2, true>, 8, 2}, {deliver_units<16, 
 }
 
 int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
-	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0),
+	static int const warps_env = env_int("SPICE_DELIVER_WARPS", 0), grid_env = env_int("SPICE_DELIVER_GRID", 0), rounds_env = env_int("SPICE_DELIVER_ROUNDS", 0),
 	                 path_env = env_int("SPICE_DELIVER_PATH", 0); // 0: cp.async.bulk + mbarrier (measured faster: 0.658 vs 0.625 of the roofline), 1: cp.async with zero fill
 	static int blocks_per_sm[64][4] = {};
 	static int sms[64]              = {};
@@ -863,11 +893,19 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 		cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);
 		smem_set[device] = a.tile_cap;
 	}
-	long long const units = static_cast<long long>(a.total_tiles) * a.nsteps;
+	long long units = static_cast<long long>(a.total_tiles) * a.nsteps;
 	if (units <= 0)
 		return 0;
-	// fewer than ~6 units per 8-warp CTA: the tail of the window would run on a few CTAs; put 16 warps on a unit
-	int which = units < 6ll * sms[device] * blocks_per_sm[device][0] ? 1 : 0;
+	// Few, long units (a rank of a multi-GPU run sees every source but only its share of the targets): measured on the
+	// 8-rank shape (tools/rank_shape_probe.py 8 300 0.5, profiles/probe_r02_rank_shapes.txt) two CTAs of 8 warps on whole
+	// units deliver in 190 us per window, one CTA of 16 warps in 207 us, units handed out in 2 / 3 / 4 rounds that add to
+	// pre-zeroed counters in 211 / 209 / 215 us: whole units on the 8-warp shape it is.  The other two stay reachable for
+	// experiments (SPICE_DELIVER_WARPS=16; SPICE_PREZEROED=1 SPICE_DELIVER_ROUNDS=n).
+	int rounds = 1;
+	int which  = 0;
+	if (rounds_env > 0 && a.prezeroed)
+		rounds = std::clamp(rounds_env, 1, 8);
+	units *= rounds;
 	if (warps_env == 8 || warps_env == 16)
 		which = warps_env == 16;
 	which += path_env == 1 ? 2 : 0;
@@ -883,6 +921,7 @@ int launch_tiles(void* stream, tiles_args const& a, int device, int* launches) {
 	if (int const e = counter_base(stream, &base))
 		return e;
 	b.cnt_base = static_cast<unsigned>(base);
+	b.rounds   = rounds;
 	S.kernel<<<grid, S.warps * 32, cta_smem(a.tile_cap, S.warps, S.stages), static_cast<cudaStream_t>(stream)>>>(b);
 	return static_cast<int>(cudaGetLastError());
 }

@@ -53,6 +53,9 @@ struct tiles_args {
 	unsigned long long const* flags; // this rank's flag array [world], or null
 	unsigned long long seq;
 	unsigned cnt_base;               // filled in by launch_tiles: where the CTA's counters start in its shared-memory window
+	int rounds;                      // filled in by launch_tiles: parts of a unit's spike list handed out separately (1: whole units)
+	int prezeroed;                   // the counters' consumer (the update kernel) clears what it has read: nothing is stored for a unit
+	                                 // without spikes, and units may be counted in rounds that ADD to the counters
 };
 
 constexpr int kMaxConns  = 32;   // connections per launch

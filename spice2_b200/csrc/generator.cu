@@ -410,6 +410,7 @@ struct chase_args {
 	unsigned const* hop;   // kHop rows ahead
 	long long base;        // global position of the chunk's first draw
 	long long ch;
+	long long len;         // draws held in y
 	long long* row_start;  // [src + 1], global positions
 	unsigned* anchor_pos;  // chunk-frame position of every kHop-th row start the chase passed ...
 	unsigned* anchor_row;  // ... and its row, relative to the chunk's first row
@@ -442,9 +443,33 @@ __global__ void __launch_bounds__(32) fp_chase(chase_args a) {
 			double noise = 0;
 			int index = 0, dst = 0;
 			long long t = s;
-			while (!row_step(a.y[t], P, noise, index, dst)) {
-				index++;
-				t++;
+			// the recurrence is sequential, its inputs are not: the draws are fetched 16 at a time, one batch ahead (rows
+			// of 1e5 draws at 1e6 x 1e6 would otherwise pay a memory round trip per draw); reads behind the row's end stay
+			// inside the chunk's overlap margin or are clamped to its last draw
+			constexpr int kAhead = 16;
+			long long const last = a.len - 1;
+			double cur[kAhead], nxt[kAhead];
+#pragma unroll
+			for (int i = 0; i < kAhead; i++)
+				cur[i] = a.y[min(t + i, last)];
+			for (bool done = false; !done;) {
+#pragma unroll
+				for (int i = 0; i < kAhead; i++)
+					nxt[i] = a.y[min(t + kAhead + i, last)];
+#pragma unroll
+				for (int i = 0; i < kAhead; i++) {
+					if (done)
+						continue;
+					if (row_step(cur[i], P, noise, index, dst))
+						done = true;
+					else {
+						index++;
+						t++;
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < kAhead; i++)
+					cur[i] = nxt[i];
 			}
 			nx = t + 1;
 			nexact++;
@@ -954,7 +979,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 		cudaEventRecord(evr0, stream);
 		int const rows_per_cta = 4 / warps_per_row;
 		fp_rows<<<static_cast<unsigned>((rhi - rlo + rows_per_cta - 1) / rows_per_cta), 128, 0, stream>>>(ra);
-		fp_rows_exact<<<128, 128, 0, stream>>>(ra); // rows with an entry (or an end) the bounds could not decide: strided over the list
+		fp_rows_exact<<<296, 128, 0, stream>>>(ra); // rows with an entry (or an end) the bounds could not decide: strided over the list
 		cudaEventRecord(evr1, stream);
 		launches += 2;
 		return static_cast<int>(cudaGetLastError());
@@ -973,7 +998,7 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 			fp_double<<<dgrid, 256, 0, stream>>>(from, to, ch);
 			from = to;
 		}
-		chase_args cha{P, y, next, from, base, ch, row_start, anchor_pos, anchor_row, row_flag, st};
+		chase_args cha{P, y, next, from, base, ch, len, row_start, anchor_pos, anchor_row, row_flag, st};
 		fp_chase<<<1, 32, 0, stream>>>(cha);
 		launches += 2 + kHopLog;
 		GEN_CUDA(cudaGetLastError());

@@ -341,9 +341,8 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 		for (int c = 0; c < C; c++) {
 			if (c < NIN && kk[c]) {
 				incoming const& in = a.in[c];
-				if constexpr (Generic)
-					if (in.zero_after_read)
-						in.counts[cslot * in.cstride + ii] = 0;
+				if (in.zero_after_read) // the producer adds to these counters (atomic delivery, or tiled delivery in rounds)
+					in.counts[cslot * in.cstride + ii] = 0;
 				if constexpr (std::is_void_v<FSyn>)
 					in.apply(in.functor, &n, kk[c]);
 				else
@@ -510,7 +509,7 @@ struct neuron_ops_builder {
 			if (a->n_local > 0) {
 				bool fast = a->n_in <= 4;
 				for (int c = 0; c < a->n_in; c++)
-					fast = fast && !a->in[c].evt_cnt && !a->in[c].zero_after_read;
+					fast = fast && !a->in[c].evt_cnt;
 				int const grid = grid_for(a->n_local, 128);
 				if (!fast)
 					update_stateful_kernel<Neur, kMaxIncoming, true><<<grid, 128, 0, stream>>>(*a);

@@ -489,6 +489,8 @@ struct spice_ctx {
 
 	// delivery
 	bool tiled                        = true;    // SPICE_DELIVER=atomic selects the one-atomic-per-event kernel
+	bool prezeroed                    = false;   // the update kernels clear the event counters they have read, so the tiled delivery may
+	                                             // count a unit in several rounds that add to them (windows with few, long units)
 	bool direct_segments              = false;   // several ranks: the delivery kernel reads the ring's per-rank segments itself
 	                                             // and waits for the peers' flags (no wait_window / flatten_window launches)
 	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
@@ -707,6 +709,10 @@ int finalize(spice_ctx* ctx) {
 		size_t stateless = 0;
 		for (auto const& c : ctx->conns)
 			stateless += c.stateful ? 0 : 1;
+		// SPICE_PREZEROED=1 (experiments): the update kernels clear the counters they read and the delivery may count a unit
+		// in SPICE_DELIVER_ROUNDS rounds; measured slower than whole units at every rank shape (deliver.cu launch_tiles)
+		if (char const* e = std::getenv("SPICE_PREZEROED"))
+			ctx->prezeroed = *e == '1';
 		ctx->direct_segments = ctx->world > 1 && !std::getenv("SPICE_FLATTEN") &&
 		                       stateless * static_cast<size_t>(ctx->window) * static_cast<size_t>(ctx->world) <= static_cast<size_t>(deliver::kMaxCounts);
 	}
@@ -1009,7 +1015,7 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	*n_in = static_cast<int>(p.incoming.size());
 	for (int k = 0; k < *n_in; k++) {
 		connection const& c = ctx->conns[p.incoming[k]];
-		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, ctx->tiled ? 0 : 1,
+		in[k]               = incoming{c.counts, c.cstride, c.apply, c.functor_dev, ctx->cring, (ctx->tiled && !ctx->prezeroed) ? 0 : 1,
 		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events,
 		                               from_ctx{c.src_snapshot, ctx->pops[c.src].stride, reinterpret_cast<std::int64_t const*>(c.offsets),
 		                                        ctx->pops[c.src].size, ctx->mode == SPICE_MODE_FAST ? 1 : 0}};
@@ -1175,7 +1181,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 						fused = nullptr;
 				}
 				for (int c = 0; c < ua.n_in; c++)
-					if (ua.in[c].evt_cnt || ua.in[c].zero_after_read)
+					if (ua.in[c].evt_cnt)
 						fused = nullptr;
 			}
 			int const e = fused ? fused(&ua) : p.ops->launch_update(&ua);
@@ -1302,6 +1308,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ta.stats       = ctx->d_stats;
 			ta.error       = ctx->d_error;
 			ta.tile_cap    = ctx->tile_cap;
+			ta.prezeroed   = ctx->prezeroed ? 1 : 0;
 			ta.world       = ctx->world > 1 && !ctx->direct_segments ? 1 : ctx->world; // flat lists look like one rank's
 			if (ctx->direct_segments && !ctx->any_stateful && !ctx->raster_on) {
 				ta.flags = xptr<unsigned long long>(ctx->xbase, static_cast<long long>(ctx->flags_off));
