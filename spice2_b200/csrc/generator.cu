@@ -116,13 +116,6 @@ __device__ __forceinline__ int cvttsd2si32(double x) {
 	return (x > -2147483649.0 && x < 2147483648.0) ? __double2int_rz(x) : static_cast<int>(0x80000000u);
 }
 
-// one step of the reference's row recurrence; returns true when the row ends at this draw
-__device__ __forceinline__ bool row_step(double y, params const& P, double& noise, int& index, int& dst) {
-	noise = __fma_rn(y, P.c, noise);
-	dst   = index + cvttsd2si32(__dadd_rn(noise, copysign(kHalfLo, noise)));
-	return (static_cast<long long>(dst) >= P.dst) | (index >= P.max_degree);
-}
-
 __device__ __forceinline__ long long quantize(double y, double fix) { return __double2ll_rn(__dmul_rn(y, fix)); }
 
 // ---- kernel J: RNG checkpoints -------------------------------------------------------------------
@@ -456,17 +449,26 @@ __global__ void __launch_bounds__(32) fp_chase(chase_args a) {
 #pragma unroll
 				for (int i = 0; i < kAhead; i++)
 					nxt[i] = a.y[min(t + kAhead + i, last)];
+				// only the additions to `noise` depend on each other; the end tests of the batch do not
+				double nz[kAhead];
+				double run = noise;
 #pragma unroll
 				for (int i = 0; i < kAhead; i++) {
-					if (done)
-						continue;
-					if (row_step(cur[i], P, noise, index, dst))
-						done = true;
-					else {
-						index++;
-						t++;
-					}
+					run   = __fma_rn(cur[i], P.c, run);
+					nz[i] = run;
 				}
+				int first = kAhead; // the first draw of the batch that ends the row
+#pragma unroll
+				for (int i = kAhead - 1; i >= 0; i--) {
+					int const idx = index + i;
+					dst           = idx + cvttsd2si32(__dadd_rn(nz[i], copysign(kHalfLo, nz[i])));
+					if ((static_cast<long long>(dst) >= P.dst) | (idx >= P.max_degree))
+						first = i;
+				}
+				done = first < kAhead;
+				t += first;
+				index += first;
+				noise = nz[kAhead - 1];
 #pragma unroll
 				for (int i = 0; i < kAhead; i++)
 					cur[i] = nxt[i];
@@ -616,7 +618,6 @@ __global__ void __launch_bounds__(128) fp_rows_exact(rows_args a) {
 		long long const out0 = a.write ? a.offsets[r] : 0;
 		long long kept = 0, left = 0; // warp-uniform totals
 		double noise = 0;             // lane 0's chain
-		int index    = 0;
 		long long t  = s;
 		bool bad     = false;
 		double reg[kExactTile / 32];
@@ -635,26 +636,36 @@ __global__ void __launch_bounds__(128) fp_rows_exact(rows_args a) {
 				long long const pos = t + kExactTile + j * 32 + lane;
 				reg[j]              = pos < a.V.len ? y[pos] : 0.0;
 			}
-			int cnt = kExactTile, state = 0; // state: 1 = the row ended inside this tile, 2 = it ran past the orbit's end
+			// lane 0 runs nothing but the chain: noise_i = fma(y_i, c, noise_(i-1)), written over the draw it consumed
 			if (lane == 0) {
+				double run = noise;
+#pragma unroll 8
 				for (int i = 0; i < kExactTile; i++) {
-					if (t + i > en) { // would run past the orbit's row end: reported below
-						cnt   = i;
-						state = 2;
-						break;
-					}
-					int dst;
-					if (row_step(ybuf[warp][i], P, noise, index, dst)) {
-						cnt   = i;
-						state = (t + i == en) ? 1 : 2;
-						break;
-					}
-					dbuf[warp][i] = dst;
-					index++;
+					run            = __fma_rn(ybuf[warp][i], P.c, run);
+					ybuf[warp][i]  = run;
 				}
+				noise = run;
 			}
-			cnt   = __shfl_sync(0xffffffffu, cnt, 0);
-			state = __shfl_sync(0xffffffffu, state, 0);
+			__syncwarp();
+			// the roundings, the targets and the end tests of the tile's draws are independent: all lanes
+			int cnt = kExactTile, state = 0; // state: 1 = the row ended inside this tile, 2 = it did not end where the orbit says
+			for (int i0 = 0; i0 < kExactTile && state == 0; i0 += 32) {
+				int const i        = i0 + lane;
+				long long const ix = (t - s) + i; // the entry's index in its row
+				double const nz    = ybuf[warp][i];
+				int const d        = static_cast<int>(ix) + cvttsd2si32(__dadd_rn(nz, copysign(kHalfLo, nz)));
+				bool const past    = t + i > en; // would run past the orbit's row end: reported below
+				bool const stop    = (static_cast<long long>(d) >= P.dst) | (ix >= P.max_degree);
+				unsigned const m   = __ballot_sync(0xffffffffu, past | stop);
+				if (m) {
+					int const first = __ffs(m) - 1;
+					bool const p1   = __shfl_sync(0xffffffffu, past, first);
+					cnt             = i0 + first;
+					state           = (!p1 && t + cnt == en) ? 1 : 2;
+				}
+				if (i < cnt)
+					dbuf[warp][i] = d;
+			}
 			__syncwarp();
 			// the tile's entries: targets ascend along a row, so the ones left of col_lo come first, then the kept ones
 			for (int i0 = 0; i0 < cnt; i0 += 32) {
@@ -856,6 +867,13 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 		P.K    = static_cast<long long>(llroundl(Kr));
 		P.c_hi = static_cast<long long>(floorl((static_cast<long double>(dst) - 0.5L - static_cast<long double>(P.delta)) * Kr)) - P.max_degree - 4;
 		P.c_lo = static_cast<long long>(ceill((static_cast<long double>(dst) - 0.5L + static_cast<long double>(P.delta)) * Kr)) + P.max_degree + 4;
+	}
+
+	// SPICE_GEN_FORCE_EXACT=1 (tests): pretend the bounds decide nothing — every row end is found by the chase's exact
+	// replay and every row is written by fp_rows_exact, the paths that otherwise see one row in 1e8 / one in 100
+	if (std::getenv("SPICE_GEN_FORCE_EXACT")) {
+		P.delta = 0.1249;
+		P.c_lo  = (1ll << 62);
 	}
 
 	// expected stream length and output size

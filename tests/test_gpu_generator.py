@@ -85,3 +85,25 @@ def test_generate_multi_chunk(sp, orc):
     assert r["edges"] == o2["edges"] and np.array_equal(r["neighbors"], o2["neighbors"])
     r1 = sp.generate_fixed_probability(s, d, p, (5,))
     assert np.array_equal(r1["neighbors"], o["neighbors"])
+
+
+def test_generate_with_every_decision_left_to_the_exact_replays(sp, orc, monkeypatch):
+    """SPICE_GEN_FORCE_EXACT=1 disables the interval bounds: every row end is found by the chase's exact replay and every
+    row written by fp_rows_exact — the paths that otherwise decide one row end in 1e8 and one row in 100 (and every row
+    of a 1e6 x 1e6 matrix, where the bounds are too wide).  Same adjacency, bit for bit; also on column slices."""
+    monkeypatch.setenv("SPICE_GEN_FORCE_EXACT", "1")
+    rng = np.random.default_rng(5)
+    for (s, d, p) in [(300, 4000, 0.1), (50, 30000, 0.33), (1000, 700, 0.02), (40, 3000, 1.0), (20000, 900, 0.1)]:
+        inc = int(rng.integers(0, 4))
+        r = sp.generate_fixed_probability(s, d, p, (3,), inc)
+        o = orc.fixed_probability(s, d, p, orc.seed_seq([3], inc))
+        assert r["edges"] == o["edges"], (s, d, p)
+        assert np.array_equal(r["offsets"], o["offsets"]) and np.array_equal(r["neighbors"], o["neighbors"]), (s, d, p)
+    s, d, p = 200, 9000, 0.1
+    o = orc.fixed_probability(s, d, p, orc.seed_seq([1337]))
+    part = sp.generate_fixed_probability(s, d, p, (1337,), 0, col_lo=3000, col_hi=5500)
+    want = []
+    for i in range(s):
+        row = o["neighbors"][o["offsets"][i]: o["offsets"][i + 1]]
+        want.append(row[(row >= 3000) & (row < 5500)] - 3000)
+    assert np.array_equal(part["neighbors"], np.concatenate(want))
