@@ -193,6 +193,11 @@ SPICE_API int64_t spice_fixed_probability_max_degree(int64_t dst_count, double p
 typedef struct spice_adjacency spice_adjacency;
 SPICE_API int spice_fixed_probability_generate(int device, int64_t src_count, int64_t dst_count, double p, uint64_t seed_lo,
                                      uint64_t seed_hi, int64_t col_lo, int64_t col_hi, spice_adjacency** out);
+/* adj_list::generate(offsets, neighbors, seed)                        (topology.cpp:56-71; bench/connectivity.cpp:8-22)
+ * on the GPU: the (src, dst) pairs adj_list::connect collected (host arrays) are sorted by (src, dst) and streamed into
+ * CSR.  Same handle, same accessors as above.  An index out of range is a violated precondition (topology.cpp:16-18). */
+SPICE_API int spice_adj_list_generate(int device, int32_t const* edges_src, int32_t const* edges_dst, int64_t n_edges, int64_t src_count,
+                            int64_t dst_count, int64_t col_lo, int64_t col_hi, spice_adjacency** out);
 SPICE_API int64_t spice_adjacency_edges(spice_adjacency const* a);
 SPICE_API void* spice_adjacency_offsets_dev(spice_adjacency const* a);   /* int64[src_count+1] */
 SPICE_API void* spice_adjacency_neighbors_dev(spice_adjacency const* a); /* int32[edges] */

@@ -18,7 +18,7 @@ import numpy as np
 
 from .build import build as _build
 
-__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "Adjacency", "seed_seq", "fnv1a64",
+__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "generate_adj_list", "Adjacency", "seed_seq", "fnv1a64",
            "MODE_DETERMINISTIC", "MODE_FAST"]
 
 MODE_DETERMINISTIC, MODE_FAST = 0, 1
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
             "spice_adjacency_neighbors_dev": (vp, [vp]),
             "spice_adjacency_copy": (i32, [vp, vp, vp]),
             "spice_adjacency_copy_range": (i32, [vp, i64, i64, vp]),
+            "spice_adj_list_generate": (i32, [i32, vp, vp, i64, i64, i64, i64, i64, C.POINTER(vp)]),
             "spice_adjacency_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i64)]),
             "spice_adjacency_destroy": (i32, [vp]),
             "spice_seed_seq": (None, [vp, i32, vp]),
@@ -418,6 +419,34 @@ class Adjacency:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def generate_adj_list(edges_src, edges_dst, src_count, dst_count, device=0, col_lo=0, col_hi=None, copy=True):
+    """adj_list::generate on the GPU (spice/src/topology.cpp:56-71): (src, dst) pairs -> CSR sorted by (src, dst) -> dict."""
+    L = lib()
+    es = np.ascontiguousarray(edges_src, np.int32)
+    ed = np.ascontiguousarray(edges_dst, np.int32)
+    assert es.shape == ed.shape and es.ndim == 1
+    col_hi = dst_count if col_hi is None else col_hi
+    h = C.c_void_p()
+    rc = L.spice_adj_list_generate(device, _ptr(es), _ptr(ed), es.size, src_count, dst_count, col_lo, col_hi, C.byref(h))
+    if rc != 0:
+        raise SpiceError(rc, L.spice_last_error(None).decode())
+    try:
+        e = int(L.spice_adjacency_edges(h))
+        total, rows = C.c_float(), C.c_float()
+        draws = C.c_int64()
+        L.spice_adjacency_timing(h, C.byref(total), C.byref(rows), C.byref(draws))
+        out = dict(edges=e, total_ms=total.value)
+        if copy:
+            off = np.zeros(src_count + 1, np.int64)
+            nb = np.zeros(max(e, 1), np.int32)
+            if L.spice_adjacency_copy(h, _ptr(off), _ptr(nb)) != 0:
+                raise SpiceError(2, "adjacency copy failed")
+            out.update(offsets=off, neighbors=nb[:e])
+        return out
+    finally:
+        L.spice_adjacency_destroy(h)
 
 
 def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True):

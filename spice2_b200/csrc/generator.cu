@@ -42,6 +42,9 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "generator.h"
 #include "spice/detail/glibc_log.h"
 #include "spice/util/random.h"
@@ -1090,6 +1093,139 @@ int generate_fixed_probability(void* stream_, long long src, long long dst, doub
 			*err = "fixed_probability: neighbor capacity exceeded";
 		return 4;
 	}
+	return 0;
+}
+
+// ---- adj_list ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) adj_pack(int const* es, int const* ed, long long n, long long src, long long dst,
+                                                unsigned long long* keys, int* flags) {
+	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	int const s = es[i], d = ed[i];
+	if (s < 0 || s >= src || d < 0 || d >= dst) {
+		atomicOr(flags, 1); // out of range
+		keys[i] = ~0ull;
+		return;
+	}
+	keys[i] = (static_cast<unsigned long long>(static_cast<unsigned>(s)) << 32) | static_cast<unsigned>(d);
+}
+// sorted keys -> per-row counts of kept targets, multapse flag
+__global__ void __launch_bounds__(256) adj_count(unsigned long long const* keys, long long n, long long col_lo, long long col_hi,
+                                                 unsigned long long* degree, int* flags) {
+	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	unsigned long long const k = keys[i];
+	if (i > 0 && keys[i - 1] == k)
+		atomicOr(flags, 2);
+	long long const d = static_cast<long long>(k & 0xffffffffull);
+	if (d >= col_lo && d < col_hi)
+		atomicAdd(degree + (k >> 32), 1ull);
+}
+// kept targets in key order: entry i goes to offsets[src] + (its rank among the kept keys of its row); keys are sorted,
+// so that rank is (number of kept keys before i) - offsets[src] = kept_before[i] - offsets[src]
+__global__ void __launch_bounds__(256) adj_write(unsigned long long const* keys, long long const* kept_before, long long n,
+                                                 long long col_lo, long long col_hi, int* neighbors) {
+	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	long long const d = static_cast<long long>(keys[i] & 0xffffffffull);
+	if (d >= col_lo && d < col_hi)
+		neighbors[kept_before[i]] = static_cast<int>(d - col_lo);
+}
+__global__ void __launch_bounds__(256) adj_keep_flags(unsigned long long const* keys, long long n, long long col_lo, long long col_hi,
+                                                      long long* keep) {
+	long long const i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	long long const d = static_cast<long long>(keys[i] & 0xffffffffull);
+	keep[i]           = (d >= col_lo && d < col_hi) ? 1 : 0;
+}
+}
+
+int generate_adj_list(void* stream_, int const* edges_src, int const* edges_dst, long long n, long long src, long long dst, long long col_lo,
+                      long long col_hi, result* out, bool* duplicates, std::string* err) {
+	auto stream = static_cast<cudaStream_t>(stream_);
+	*out        = result{};
+	if (duplicates)
+		*duplicates = false;
+	scratch S;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	GEN_CUDA(S.event(&ev0));
+	GEN_CUDA(S.event(&ev1));
+	GEN_CUDA(cudaEventRecord(ev0, stream));
+	GEN_CUDA(cudaMalloc(&out->offsets, sizeof(long long) * static_cast<size_t>(src + 1)));
+	GEN_CUDA(cudaMemsetAsync(out->offsets, 0, sizeof(long long) * static_cast<size_t>(src + 1), stream));
+	if (n <= 0 || src <= 0) {
+		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * 8));
+		GEN_CUDA(cudaStreamSynchronize(stream));
+		return 0;
+	}
+	int *es = nullptr, *ed = nullptr, *flags = nullptr;
+	unsigned long long *keys = nullptr, *keys2 = nullptr, *degree = nullptr;
+	long long* kept = nullptr;
+	void* tmp       = nullptr;
+	GEN_CUDA(S.alloc(&es, static_cast<size_t>(n)));
+	GEN_CUDA(S.alloc(&ed, static_cast<size_t>(n)));
+	GEN_CUDA(S.alloc(&keys, static_cast<size_t>(n)));
+	GEN_CUDA(S.alloc(&keys2, static_cast<size_t>(n)));
+	GEN_CUDA(S.alloc(&kept, static_cast<size_t>(n)));
+	GEN_CUDA(S.alloc(&degree, static_cast<size_t>(src + 1)));
+	GEN_CUDA(S.alloc(&flags, 1));
+	GEN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), stream));
+	GEN_CUDA(cudaMemsetAsync(degree, 0, sizeof(unsigned long long) * static_cast<size_t>(src + 1), stream));
+	GEN_CUDA(cudaMemcpyAsync(es, edges_src, sizeof(int) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+	GEN_CUDA(cudaMemcpyAsync(ed, edges_dst, sizeof(int) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+	unsigned const grid = static_cast<unsigned>((n + 255) / 256);
+	adj_pack<<<grid, 256, 0, stream>>>(es, ed, n, src, dst, keys, flags);
+	// the key's significant bits: 32 of the target, those of the largest source above them
+	int src_bits = 1;
+	while ((1ll << src_bits) < src)
+		src_bits++;
+	int dst_bits = 1;
+	while ((1ll << dst_bits) < dst)
+		dst_bits++;
+	size_t bytes = 0, bytes2 = 0;
+	cub::DoubleBuffer<unsigned long long> db(keys, keys2);
+	GEN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, static_cast<long long>(n), 0, 32 + src_bits, stream));
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes2, kept, kept, static_cast<long long>(n), stream));
+	bytes = std::max(bytes, bytes2);
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes2, reinterpret_cast<long long*>(degree), out->offsets, static_cast<long long>(src + 1), stream));
+	bytes = std::max(bytes, bytes2);
+	GEN_CUDA(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+	S.dev.push_back(tmp);
+	if (dst_bits < 32) { // two passes: the low 32 bits hold a target below 2^dst_bits, the bits in between are zero
+		GEN_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, db, static_cast<long long>(n), 0, dst_bits, stream));
+		GEN_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, db, static_cast<long long>(n), 32, 32 + src_bits, stream));
+	} else
+		GEN_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, db, static_cast<long long>(n), 0, 32 + src_bits, stream));
+	unsigned long long const* sorted = db.Current();
+	adj_count<<<grid, 256, 0, stream>>>(sorted, n, col_lo, col_hi, degree, flags);
+	adj_keep_flags<<<grid, 256, 0, stream>>>(sorted, n, col_lo, col_hi, kept);
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, kept, kept, static_cast<long long>(n), stream));
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, reinterpret_cast<long long*>(degree), out->offsets, static_cast<long long>(src + 1), stream));
+	long long edges = 0;
+	int hflags      = 0;
+	GEN_CUDA(cudaMemcpyAsync(&edges, out->offsets + src, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+	GEN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	GEN_CUDA(cudaStreamSynchronize(stream));
+	if (hflags & 1) {
+		if (err)
+			*err = "adj_list: a source or target index is out of range";
+		return 1;
+	}
+	GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(edges + 8))); // +8: the delivery kernel reads whole 16-byte groups
+	adj_write<<<grid, 256, 0, stream>>>(sorted, kept, n, col_lo, col_hi, out->neighbors);
+	GEN_CUDA(cudaGetLastError());
+	GEN_CUDA(cudaEventRecord(ev1, stream));
+	GEN_CUDA(cudaStreamSynchronize(stream));
+	out->edges    = edges;
+	out->launches = 12;
+	cudaEventElapsedTime(&out->total_ms, ev0, ev1);
+	if (duplicates)
+		*duplicates = (hflags & 2) != 0;
 	return 0;
 }
 }

@@ -19,6 +19,14 @@ struct result {
 long long max_degree(long long dst, double p);
 
 // Returns 0 or a SPICE_ERR_* code (message in *err).  chunk_draws <= 0 picks the default.
+// adj_list::generate on the GPU (topology.cpp:56-71: sort the packed (src << 32 | dst) connections, stream them into
+// CSR): radix sort of the packed keys, rows by a histogram + scan.  edges_src / edges_dst are HOST arrays of n_edges
+// entries (what adj_list::connect collected); targets in [col_lo, col_hi) are kept as local columns.  *duplicates = a
+// (src, dst) pair occurs more than once (a multapse).  Returns 0, SPICE_ERR_PRECONDITION (1: an index out of range,
+// the reference's SPICE_PRE in edge_stream) or a CUDA error code as generate_fixed_probability does.
+int generate_adj_list(void* cuda_stream, int const* edges_src, int const* edges_dst, long long n_edges, long long src, long long dst,
+                      long long col_lo, long long col_hi, result* out, bool* duplicates, std::string* err);
+
 int generate_fixed_probability(void* cuda_stream, long long src, long long dst, double p, unsigned long long seed_lo,
                                unsigned long long seed_hi, long long col_lo, long long col_hi, long long chunk_draws,
                                result* out, std::string* err);

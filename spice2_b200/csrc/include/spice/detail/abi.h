@@ -144,6 +144,12 @@ struct import_args {
 	std::uint32_t* state;
 	std::int64_t n_local, stride;
 	void const* in_aos;
+	// what export_args folds into the copy it hands out is pending no more once that copy comes back: the events of
+	// step t_next are cleared, so a get / modify / set round trip applies them once (neuron_population.h:142-145 hands
+	// out the live state, where they have been applied already)
+	std::int64_t t_next;
+	std::int32_t n_in;
+	incoming in[kMaxIncoming];
 };
 }
 

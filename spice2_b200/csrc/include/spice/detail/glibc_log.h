@@ -12,7 +12,7 @@
 // Domain: finite x > 0, normal (the generator only calls it with u in [2^-53, 1]).  Zero,
 // negative, subnormal, inf and NaN inputs are outside the contract.
 //
-// Pinned by tests/test_glibc_log.py (host build vs this host's libm on 10^7 inputs, and the
+// Pinned by tests/test_host.py::test_glibc_log_restatement_matches_golden_pins (host build vs this host's libm on 10^7 inputs, and the
 // golden vectors in tests/golden/libm_pins.npz) and on the device by tests/test_gpu_generator.py.
 #pragma once
 

@@ -475,6 +475,13 @@ __global__ void __launch_bounds__(256) import_kernel(import_args a) {
 	if (i >= a.n_local)
 		return;
 	store_soa<N>(a.state, a.stride, i, static_cast<N const*>(a.in_aos)[i]);
+	for (int c = 0; c < a.n_in; c++) { // the imported state already holds the events export_kernel folded in
+		incoming const& in = a.in[c];
+		if (in.evt_cnt)
+			in.evt_cnt[i] = 0;
+		else
+			in.counts[(a.t_next % in.ring) * in.cstride + i] = 0;
+	}
 }
 
 inline int grid_for(std::int64_t threads, int block = 256) {
@@ -593,10 +600,28 @@ int launch_update_fused(update_args const* a) {
 	}
 }
 
+// A STATELESS synapse whose deliver() reads the source neuron (concepts.h:76-99, synapse_population.h:125-131): its events
+// differ from source to source, so they cannot be counted; they take the event-list path of the stateful synapses
+// (per target, in the reference's (source, row) order) with one unused word of state per edge.
+template <class Syn, class SrcNeur, class DstNeur>
+struct carried_from_to : Syn {
+	struct synapse {
+		std::int32_t unused = 0;
+	};
+	SPICE_HD void deliver(synapse const&, typename SrcNeur::neuron const& from, typename DstNeur::neuron& to) const {
+		Syn::deliver(from, to);
+	}
+};
+
 template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
 requires Synapse<Syn, SrcNeur, DstNeur>
 spice_synapse_ops const* synapse_ops(char const* name = "user") {
 	static_assert(std::is_trivially_copyable_v<Syn>, "synapse functors are copied to the device byte-wise");
+	if constexpr (!StatefulSynapse<Syn> && detail::deliver_from_to_v<Syn, SrcNeur, DstNeur>) {
+		using carried = carried_from_to<Syn, SrcNeur, DstNeur>;
+		static_assert(sizeof(carried) == sizeof(Syn) && Synapse<carried, SrcNeur, DstNeur>);
+		return synapse_ops<carried, SrcNeur, DstNeur>(name);
+	} else {
 	struct B {
 		static int get_apply(apply_fn* out) {
 			return static_cast<int>(cudaMemcpyFromSymbol(out, apply_ptr<Syn, DstNeur>, sizeof(apply_fn)));
@@ -661,5 +686,6 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 	                                   &B::launch_stateful,
 	                                   (!StatefulSynapse<Syn> && DeliverTo<Syn, DstNeur>) ? &launch_update_fused<Syn, DstNeur> : nullptr};
 	return &ops;
+	}
 }
 }

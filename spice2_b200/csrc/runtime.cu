@@ -1429,8 +1429,8 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	PRE(ctx, d >= 1 && "The delay must be at least 1dt.");                 // snn.h:35
 	PRE(ctx, d <= ctx->max_delay && "The delay of a synapse population may not exceed the maximum delay of the network."); // snn.h:36-38
 	if (ops->deliver_from_to && (ops->synapse_bytes == 0 || ctx->world > 1))
-		return fail(ctx, SPICE_ERR_UNSUPPORTED,
-		            "synapses whose deliver() reads the source neuron: only stateful synapses on a single rank are on the GPU path yet");
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, // (stateless ones arrive here with one carried word of state: model_ops.cuh carried_from_to)
+		            "synapses whose deliver() reads the source neuron are on the GPU path on a single rank only");
 	PRE(ctx, ops->synapse_bytes % 4 == 0);
 	c->stateful = ops->synapse_bytes != 0;
 	c->from_to  = ops->deliver_from_to != 0;
@@ -1764,35 +1764,28 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 	(void)(ctx->seed++); // the graph still consumes its seed (synapse_population.h:31)
 	population const& src = ctx->pops[src_pop];
 	population const& dst = ctx->pops[dst_pop];
-	// adj_list::generate: sort packed (src << 32 | dst) and stream into CSR (topology.cpp:63-71)
-	std::vector<std::uint64_t> packed(static_cast<size_t>(n_edges));
-	for (int64_t i = 0; i < n_edges; i++) {
-		PRE(ctx, edges_src[i] >= 0 && edges_src[i] < src.size);
-		PRE(ctx, edges_dst[i] >= 0 && edges_dst[i] < dst.size);
-		packed[static_cast<size_t>(i)] = (static_cast<std::uint64_t>(edges_src[i]) << 32) | static_cast<std::uint32_t>(edges_dst[i]);
-	}
-	std::sort(packed.begin(), packed.end());
-	std::vector<long long> offsets(static_cast<size_t>(src.size) + 1, 0);
-	std::vector<std::int32_t> nb;
-	nb.reserve(packed.size());
-	size_t k = 0;
-	for (long long s = 0; s < src.size; s++) {
-		offsets[static_cast<size_t>(s)] = static_cast<long long>(nb.size());
-		for (; k < packed.size() && static_cast<long long>(packed[k] >> 32) == s; k++) {
-			long long const d = static_cast<long long>(packed[k] & 0xffffffffu);
-			if (d >= dst.lo && d < dst.hi)
-				nb.push_back(static_cast<std::int32_t>(d - dst.lo));
+	// adj_list::generate: sort packed (src << 32 | dst) and stream into CSR (topology.cpp:63-71) — on the device (radix
+	// sort of the packed keys, rows by histogram + scan: generator.cu generate_adj_list)
+	{
+		gen::result r;
+		std::string err;
+		bool dup = false;
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		int const grc = gen::generate_adj_list(ctx->stream, edges_src, edges_dst, n_edges, src.size, dst.size, dst.lo, dst.hi, &r, &dup, &err);
+		if (grc != 0) {
+			cudaFree(r.offsets);
+			cudaFree(r.neighbors);
+			if (grc == 1) // the reference's SPICE_PRE on every streamed edge (topology.cpp:16-18)
+				return fail(ctx, SPICE_ERR_PRECONDITION, std::string("Assertion failed (") + __FILE__ + ":" + std::to_string(__LINE__) +
+				                                            "): 0 <= src && src < src_count && 0 <= dst && dst < dst_count");
+			return fail(ctx, grc, err);
 		}
+		c.offsets    = r.offsets;
+		c.neighbors  = r.neighbors;
+		c.edges      = r.edges;
+		c.duplicates = dup; // a multapse: rows may repeat a target
+		ctx->launches += r.launches;
 	}
-	offsets[static_cast<size_t>(src.size)] = static_cast<long long>(nb.size());
-	c.edges = static_cast<long long>(nb.size());
-	CHECK_CUDA(ctx, cudaMalloc(&c.offsets, sizeof(long long) * offsets.size()));
-	CHECK_CUDA(ctx, cudaMemcpy(c.offsets, offsets.data(), sizeof(long long) * offsets.size(), cudaMemcpyHostToDevice));
-	CHECK_CUDA(ctx, cudaMalloc(&c.neighbors, sizeof(std::int32_t) * (nb.size() + 8))); // +8: the delivery kernel reads whole 16-byte groups
-	CHECK_CUDA(ctx, cudaMemcpy(c.neighbors, nb.data(), sizeof(std::int32_t) * nb.size(), cudaMemcpyHostToDevice));
-	for (size_t i = 1; i < packed.size(); i++)
-		if (packed[i] == packed[i - 1])
-			c.duplicates = true; // a multapse: rows may repeat a target
 	if (c.stateful && ops->per_synapse_init) {
 		if (ctx->world != 1)
 			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
@@ -2032,7 +2025,16 @@ int spice_set_neurons(spice_ctx* ctx, int pop, void const* in, int64_t bytes) {
 	void* dev = nullptr;
 	CHECK_CUDA(ctx, cudaMalloc(&dev, static_cast<size_t>(bytes)));
 	cudaError_t ce = cudaMemcpyAsync(dev, in, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, ctx->stream);
-	import_args ia{ctx->stream, p.state, n, p.stride, dev};
+	import_args ia{};
+	ia.stream  = ctx->stream;
+	ia.state   = p.state;
+	ia.n_local = n;
+	ia.stride  = p.stride;
+	ia.in_aos  = dev;
+	ia.t_next  = ctx->time;
+	ia.n_in    = 0;
+	if (ctx->finalized)
+		fill_incoming(ctx, p, ia.in, &ia.n_in);
 	if (ce == cudaSuccess)
 		ce = static_cast<cudaError_t>(p.ops->launch_import(&ia));
 	ctx->launches++;
@@ -2228,6 +2230,35 @@ int spice_fixed_probability_generate(int device, int64_t src_count, int64_t dst_
 		cudaFree(a->r.neighbors);
 		g_create_error = err;
 		return rc;
+	}
+	*out = a.release();
+	return SPICE_OK;
+}
+
+int spice_adj_list_generate(int device, int32_t const* edges_src, int32_t const* edges_dst, int64_t n_edges, int64_t src_count, int64_t dst_count,
+                            int64_t col_lo, int64_t col_hi, spice_adjacency** out) {
+	*out = nullptr;
+	if (n_edges < 0 || src_count < 0 || dst_count < 0 || src_count >= 2147483647 || dst_count >= 2147483647 || col_lo < 0 ||
+	    col_hi > dst_count || col_lo > col_hi || (n_edges > 0 && (!edges_src || !edges_dst))) {
+		g_create_error = "spice_adj_list_generate: invalid argument";
+		return SPICE_ERR_PRECONDITION;
+	}
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) {
+		g_create_error = "no CUDA device — this backend has no CPU fallback";
+		return SPICE_ERR_NO_DEVICE;
+	}
+	cudaSetDevice(device);
+	auto a    = std::make_unique<spice_adjacency>();
+	a->device = device;
+	a->src    = src_count;
+	std::string err;
+	int const rc = gen::generate_adj_list(nullptr, edges_src, edges_dst, n_edges, src_count, dst_count, col_lo, col_hi, &a->r, nullptr, &err);
+	if (rc != 0) {
+		cudaFree(a->r.offsets);
+		cudaFree(a->r.neighbors);
+		g_create_error = rc == 1 ? "Assertion failed (adj_list): 0 <= src && src < src_count && 0 <= dst && dst < dst_count" : err;
+		return rc == 1 ? SPICE_ERR_PRECONDITION : rc;
 	}
 	*out = a.release();
 	return SPICE_OK;

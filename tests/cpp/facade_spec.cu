@@ -70,6 +70,26 @@ struct plastic_synapse { // synapse_population.cpp:83-93: counts how many steps 
 };
 static_assert(PlasticSynapse<plastic_synapse>);
 
+// concepts.h:76-99 DeliverFromTo without synapse state (synapse_population.h:125-131): a source that fires once and
+// carries a value its synapses read
+struct tagged_source {
+	struct neuron {
+		int tag   = 0;
+		int fired = 0;
+	};
+	SPICE_HD void init(neuron& n, Int id, auto&) const { n.tag = 10 * (static_cast<int>(id) + 1); }
+	SPICE_HD bool update(neuron& n, float, auto&) const {
+		if (n.fired)
+			return false;
+		n.fired = 1;
+		return true;
+	}
+};
+struct from_to_stateless {
+	SPICE_HD void deliver(tagged_source::neuron const& from, stateful_neuron::neuron& to) const { to.received_count += from.tag; }
+};
+static_assert(Synapse<from_to_stateless, tagged_source, stateful_neuron> && !StatefulSynapse<from_to_stateless>);
+
 adj_list graph() { // synapse_population.cpp:33-40
 	adj_list adj;
 	adj.connect(0, 0);
@@ -128,6 +148,21 @@ int main() {
 		EXPECT_EQ(n[2], 0);
 		EXPECT_EQ(n[3], 4);
 		EXPECT_EQ(n[4], 0);
+	}
+	{ // a stateless synapse that reads its source (no reference test; semantics of synapse_population.h:125-131)
+		snn net(1, 1, {1337});
+		auto src = net.add_population<tagged_source>(3);
+		auto dst = net.add_population<stateful_neuron>(5);
+		auto adj = graph();
+		net.connect<from_to_stateless>(src, dst, adj, 1);
+		net.step();
+		net.step(); // nobody fires twice
+		auto const n = dst->get_neurons();
+		EXPECT_EQ(n[0].received_count, 10);
+		EXPECT_EQ(n[1].received_count, 10);
+		EXPECT_EQ(n[2].received_count, 0);
+		EXPECT_EQ(n[3].received_count, 30);
+		EXPECT_EQ(n[4].received_count, 30);
 	}
 	// SynapsePopulation.DeliverPlastic (synapse_population.cpp:96-168): the lazy bookkeeping (`_ages`, the flush of
 	// snn.cpp:17-19 at step 0).  A synapse delivered at step T has been brought forward over steps 0..T exactly

@@ -107,3 +107,30 @@ def test_generate_with_every_decision_left_to_the_exact_replays(sp, orc, monkeyp
         row = o["neighbors"][o["offsets"][i]: o["offsets"][i + 1]]
         want.append(row[(row >= 3000) & (row < 5500)] - 3000)
     assert np.array_equal(part["neighbors"], np.concatenate(want))
+
+
+def _adj_list_reference(es, ed, src_count, col_lo, col_hi):
+    """adj_list::generate (topology.cpp:63-71): sort the packed (src << 32 | dst) keys, stream them into CSR."""
+    keys = np.sort((es.astype(np.int64) << 32) | ed.astype(np.int64))
+    s, d = keys >> 32, keys & 0xFFFFFFFF
+    keep = (d >= col_lo) & (d < col_hi)
+    off = np.zeros(src_count + 1, np.int64)
+    np.cumsum(np.bincount(s[keep], minlength=src_count), out=off[1:])
+    return off, (d[keep] - col_lo).astype(np.int32)
+
+
+def test_adj_list_generate_matches_sorted_keys(sp):
+    """adj_list on the GPU (radix sort + histogram) against the reference's algorithm restated with numpy: random graphs
+    with multapses, empty rows, wide target ranges (the bench's dst = i < 2^31), column slices, the empty list."""
+    rng = np.random.default_rng(3)
+    for (n, src, dst, lo, hi) in [(0, 5, 7, 0, 7), (1, 1, 1, 0, 1), (5000, 37, 91, 0, 91), (200000, 1000, 1 << 30, 0, 1 << 30),
+                                  (100000, 5000, 3000, 700, 2100), (50000, 3, 2147483646, 0, 2147483646)]:
+        es = rng.integers(0, src, n).astype(np.int32)
+        ed = rng.integers(0, dst, n).astype(np.int32)
+        if n > 10:
+            es[:5], ed[:5] = es[5:10], ed[5:10]  # multapses
+        r = sp.generate_adj_list(es, ed, src, dst, col_lo=lo, col_hi=hi)
+        off, nb = _adj_list_reference(es, ed, src, lo, hi)
+        assert r["edges"] == nb.size and np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (n, src, dst)
+    with pytest.raises(sp.SpiceError):
+        sp.generate_adj_list(np.array([0, 9], np.int32), np.array([0, 1], np.int32), 5, 5)

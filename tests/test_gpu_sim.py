@@ -473,3 +473,27 @@ def test_delivery_cta_shapes(sp, orc, golden, tmp_path, split):
     for _ in range(8 + 7):  # see test_synaptic_event_count
         onet.step()
     assert int(got["dense_events"][0]) == onet.events()
+
+
+@pytest.mark.parametrize("plastic", [False, True])
+def test_get_set_neurons_round_trip_changes_nothing(sp, plastic):
+    """get_neurons() hands out the state with the pending deliveries of the next step applied (the reference's live
+    state, neuron_population.h:142-145); writing the same values back must not apply them a second time."""
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=3000, p=0.1, w_exc=np.float32(2.0 / 300), w_inh=np.float32(-10.0 / 300), seed=(9,), plastic=plastic)
+    rasters = []
+    for round_trip in (False, True):
+        net, pops = brunel(**kw)
+        net.raster_enable(True)
+        net.step(130)
+        if round_trip:
+            for pi in (1, 2):
+                pops[pi].set_neurons(pops[pi].get_neurons())
+        net.step(130)
+        counts, ids = net.raster_read(260)
+        rasters.append((counts, ids, pops[1].get_neurons(), pops[2].get_neurons()))
+        net.close()
+    for a, b in zip(*rasters):
+        assert np.array_equal(a, b)
+    assert rasters[0][0][131:, 1:].sum() > 0  # the populations that were read and written did fire afterwards
