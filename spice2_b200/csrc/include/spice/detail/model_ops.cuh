@@ -124,14 +124,30 @@ __device__ void apply_events_impl(void const* functor, void* neuron, std::uint32
 	if constexpr (StatefulSynapse<Syn>) {
 		using N = typename DstNeur::neuron;
 		using S = typename Syn::synapse;
-		if (!from->unordered)
-			for (unsigned i = 1; i < n; i++) { // insertion sort: ascending edge index = (source, row) order
-				std::int32_t const key = list[i];
-				int j                  = static_cast<int>(i) - 1;
-				for (; j >= 0 && list[j] > key; j--)
-					list[j + 1] = list[j];
-				list[j + 1] = key;
+		// the step's events of this target, sorted: ascending edge index = (source, row) order.  Lists of up to kLocal
+		// events are sorted in a thread-local copy, not in global memory; Shell sort (Ciura's gaps): a target of
+		// samples/brunel+ receives ~20 events in a quiet step and a few hundred in a population burst, where an insertion
+		// sort's n^2 / 4 moves made this the longest kernel of the step
+		constexpr unsigned kLocal = 256;
+		std::int32_t local[kLocal];
+		if (n <= kLocal) {
+			for (unsigned i = 0; i < n; i++)
+				local[i] = list[i];
+			list = local;
+		}
+		if (!from->unordered) {
+			constexpr unsigned gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+			for (unsigned gi = 0; gi < 8; gi++) {
+				unsigned const gap = gaps[gi];
+				for (unsigned i = gap; i < n; i++) {
+					std::int32_t const key = list[i];
+					unsigned j             = i;
+					for (; j >= gap && list[j - gap] > key; j -= gap)
+						list[j] = list[j - gap];
+					list[j] = key;
+				}
 			}
+		}
 		Syn const f = *static_cast<Syn const*>(functor);
 		N nn        = *static_cast<N*>(neuron);
 		for (unsigned i = 0; i < n; i++) {
@@ -182,9 +198,9 @@ __device__ __forceinline__ void catch_up(Syn const& f, typename Syn::synapse& sy
 	f.skip(sy, dt, static_cast<Int>(64 - p));
 }
 
-// One warp per visited source: Deliver = true walks the spikes of the delivered step (catch the row's
-// synapses up, count one event per edge for its target), Deliver = false (the 64-step flush,
-// snn.cpp:17-19) walks every source and only catches up.
+// Deliver = true walks the spikes of the delivered step (catch the row's synapses up, count one event per edge for its
+// target), several warps to a source; Deliver = false (the 64-step flush, snn.cpp:17-19) walks every source, one warp
+// each, and only catches up.
 template <class Syn, bool Deliver>
 __global__ void __launch_bounds__(256) stateful_visit_kernel(stateful_args a) {
 	using S              = typename Syn::synapse;
@@ -198,18 +214,26 @@ __global__ void __launch_bounds__(256) stateful_visit_kernel(stateful_args a) {
 	int const nseg = Deliver ? a.world : 1;
 	for (int r = 0; r < nseg; r++) {
 		std::int64_t const n = Deliver ? a.ring_cnt[r] : a.n_src;
-		for (std::int64_t j = w; j < n; j += W) {
+		if (n == 0)
+			continue;
+		// Deliver: the step's spiking sources are few (tens to hundreds) and their rows long, so G warps share a source,
+		// each taking every G-th group of 32 edges; the source's age is then written by the reserve kernel, after every warp
+		// has read it.  The flush walks every source with one warp each and writes the age itself.
+		std::int64_t const G      = Deliver ? (W / n > 1 ? W / n : 1) : 1;
+		std::int64_t const groups = W / G;
+		std::int64_t const g      = w % G;
+		for (std::int64_t j = w / G; j < n; j += groups) {
 			std::int64_t const src = Deliver ? a.ring_ids[a.seg_lo[r] + j] : j;
 			std::int64_t const beg = a.offsets[src], end = a.offsets[src + 1];
 			bool pre = false, outdated = false;
 			std::int64_t age = a.time + 1;
 			if constexpr (PlasticSynapse<Syn>) {
-				std::uint64_t const g = a.ages[src];
-				pre                   = (g >> 63) != 0;
-				age                   = static_cast<std::int64_t>(g & ~(std::uint64_t(1) << 63));
-				outdated              = a.time >= age;
+				std::uint64_t const ag = a.ages[src];
+				pre                    = (ag >> 63) != 0;
+				age                    = static_cast<std::int64_t>(ag & ~(std::uint64_t(1) << 63));
+				outdated               = a.time >= age;
 			}
-			for (std::int64_t e = beg + lane; e < end; e += 32) {
+			for (std::int64_t e = beg + g * 32 + lane; e < end; e += 32 * G) {
 				std::int32_t const dst = a.neighbors[e];
 				if constexpr (PlasticSynapse<Syn>) {
 					if (outdated) {
@@ -221,13 +245,15 @@ __global__ void __launch_bounds__(256) stateful_visit_kernel(stateful_args a) {
 				if constexpr (Deliver)
 					atomicAdd(a.evt_cnt + dst, 1u);
 			}
-			if constexpr (PlasticSynapse<Syn>) {
+			if constexpr (PlasticSynapse<Syn> && !Deliver) {
 				__syncwarp();
 				if (lane == 0)
-					a.ages[src] = static_cast<std::uint64_t>(a.time + 1) | (std::uint64_t(Deliver ? 1 : 0) << 63);
+					a.ages[src] = static_cast<std::uint64_t>(a.time + 1);
 			}
-			ev += static_cast<unsigned long long>(end - beg);
-			sp++;
+			if (g == 0) {
+				ev += static_cast<unsigned long long>(end - beg);
+				sp++;
+			}
 		}
 	}
 	if (Deliver && lane == 0 && sp) {
@@ -239,6 +265,12 @@ __global__ void __launch_bounds__(256) stateful_visit_kernel(stateful_args a) {
 // every target with events reserves its part of the event list
 __global__ void __launch_bounds__(256) stateful_reserve_kernel(stateful_args a) {
 	std::int64_t const i = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (a.ages) { // plastic: the sources delivered in this step were brought up to it (synapse_population.h:137-138)
+		std::int64_t const T = static_cast<std::int64_t>(gridDim.x) * blockDim.x;
+		for (int r = 0; r < a.world; r++)
+			for (std::int64_t j = i; j < a.ring_cnt[r]; j += T)
+				a.ages[a.ring_ids[a.seg_lo[r] + j]] = static_cast<std::uint64_t>(a.time + 1) | (std::uint64_t(1) << 63);
+	}
 	if (i >= a.n_dst)
 		return;
 	unsigned const c = a.evt_cnt[i];
@@ -259,10 +291,15 @@ __global__ void __launch_bounds__(256) stateful_fill_kernel(stateful_args a) {
 	std::int64_t const W = (static_cast<std::int64_t>(gridDim.x) * blockDim.x) >> 5;
 	for (int r = 0; r < a.world; r++) {
 		std::int64_t const n = a.ring_cnt[r];
-		for (std::int64_t j = w; j < n; j += W) {
+		if (n == 0)
+			continue;
+		std::int64_t const G      = W / n > 1 ? W / n : 1; // warps per source, as in the visit
+		std::int64_t const groups = W / G;
+		std::int64_t const g      = w % G;
+		for (std::int64_t j = w / G; j < n; j += groups) {
 			std::int64_t const src = a.ring_ids[a.seg_lo[r] + j];
 			std::int64_t const beg = a.offsets[src], end = a.offsets[src + 1];
-			for (std::int64_t e = beg + lane; e < end; e += 32) {
+			for (std::int64_t e = beg + g * 32 + lane; e < end; e += 32 * G) {
 				std::int32_t const dst = a.neighbors[e];
 				if (a.evt_cnt[dst]) {
 					unsigned const k                   = atomicAdd(a.evt_fill + dst, 1u);
@@ -652,8 +689,8 @@ spice_synapse_ops const* synapse_ops(char const* name = "user") {
 				switch (a->phase) {
 				case 0: stateful_visit_kernel<Syn, true><<<148 * 4, 256, 0, stream>>>(*a); break;
 				case 1:
-					if (a->n_dst > 0)
-						stateful_reserve_kernel<<<grid_for(a->n_dst), 256, 0, stream>>>(*a);
+					if (a->n_dst > 0 || a->ages)
+						stateful_reserve_kernel<<<grid_for(a->n_dst > 0 ? a->n_dst : 1), 256, 0, stream>>>(*a);
 					break;
 				case 2: stateful_fill_kernel<<<148 * 4, 256, 0, stream>>>(*a); break;
 				case 3:
