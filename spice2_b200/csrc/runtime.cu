@@ -491,6 +491,15 @@ struct spice_ctx {
 	bool tiled                        = true;    // SPICE_DELIVER=atomic selects the one-atomic-per-event kernel
 	bool prezeroed                    = false;   // the update kernels clear the event counters they have read, so the tiled delivery may
 	                                             // count a unit in several rounds that add to them (windows with few, long units)
+	// Pipelined delivery: windows of at most half the shortest delay, so that the counters window w's delivery writes are
+	// first read by the updates of window w + 2: delivery w runs on its own stream beside the updates of window w + 1
+	// (and, with several ranks, the wait for the peers' spikes of window w is off the updates' path)
+	bool pipelined                    = false;
+	cudaStream_t dstream              = nullptr;
+	cudaEvent_t ev_upd                = nullptr;
+	cudaEvent_t ev_del[2]             = {nullptr, nullptr};
+	bool del_pending[2]               = {false, false};
+	long long windows_run             = 0;
 	bool direct_segments              = false;   // several ranks: the delivery kernel reads the ring's per-rank segments itself
 	                                             // and waits for the peers' flags (no wait_window / flatten_window launches)
 	deliver::conn_desc* d_conn_desc   = nullptr; // schedule order
@@ -697,13 +706,23 @@ int finalize(spice_ctx* ctx) {
 			ctx->window       = 1;
 			ctx->any_stateful = true;
 		}
+	{
+		// SPICE_PIPELINE=1 (experiment; parity-tested, measured slower on one GPU: 2.82 against 2.70 ms per 150 steps — the
+		// update kernels and the persistent delivery kernel each want whole SMs (61 K of 64 K registers, 225 of 228 KB shared
+		// memory go to two delivery CTAs), so they do not run side by side, and half-length windows cost the delivery 15 %)
+		char const* e  = std::getenv("SPICE_PIPELINE");
+		ctx->pipelined = ctx->tiled && !ctx->any_stateful && !ctx->conns.empty() && dmin >= 2 && e && *e == '1';
+		if (ctx->pipelined)
+			ctx->window = static_cast<int>(std::max<long long>(1, std::min<long long>(ctx->window, dmin / 2)));
+	}
 	// Spike ring: a slot is read until max_delay - 1 steps after it was written (stateful delivery of a
 	// connection with delay == max_delay, spikes(max_delay - 1)), and the delivery of a window reads the
 	// slots that window's updates wrote.  With several ranks a peer that has passed wait_window(w) already
 	// stores the spikes of window w + 1 into this rank's ring while this rank may still be reading, so the
 	// ring keeps one whole window of slack behind the oldest slot anyone reads: peers are never more than
 	// one window ahead (they cannot pass wait_window(w + 1) before this rank has published w + 1).
-	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay + (ctx->world > 1 ? ctx->window : 0), 2ll * ctx->window));
+	// (pipelined: a peer may be three windows ahead of the delivery this rank is still running)
+	ctx->ring   = static_cast<int>(std::max<long long>(ctx->max_delay + (ctx->world > 1 ? (ctx->pipelined ? 3 : 1) * ctx->window : 0), 2ll * ctx->window));
 	ctx->cring  = static_cast<int>(std::max<long long>(dmax, 1));
 	{
 		size_t stateless = 0;
@@ -916,8 +935,8 @@ int finalize(spice_ctx* ctx) {
 			CHECK_CUDA(ctx, cudaMemcpy(ctx->d_conn_desc, descs.data(), sizeof(deliver::conn_desc) * descs.size(), cudaMemcpyHostToDevice));
 		}
 		ctx->n_desc = static_cast<int>(descs.size());
-		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_work, sizeof(unsigned)));
-		CHECK_CUDA(ctx, cudaMemset(ctx->d_work, 0, sizeof(unsigned)));
+		CHECK_CUDA(ctx, cudaMalloc(&ctx->d_work, 2 * sizeof(unsigned))); // one per window parity (pipelined delivery)
+		CHECK_CUDA(ctx, cudaMemset(ctx->d_work, 0, 2 * sizeof(unsigned)));
 		if (ctx->n_desc > deliver::kMaxConns)
 			return fail(ctx, SPICE_ERR_UNSUPPORTED, "more than 32 stateless connections in one network");
 		if (ctx->n_desc > 0)
@@ -1022,14 +1041,14 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 	}
 }
 
-cudaEvent_t prof_mark(spice_ctx* ctx) {
+cudaEvent_t prof_mark(spice_ctx* ctx, cudaStream_t on = nullptr) {
 	if (ctx->prof_used == ctx->prof_events.size()) {
 		cudaEvent_t e = nullptr;
 		cudaEventCreate(&e);
 		ctx->prof_events.push_back(e);
 	}
 	cudaEvent_t e = ctx->prof_events[ctx->prof_used++];
-	cudaEventRecord(e, ctx->stream);
+	cudaEventRecord(e, on ? on : ctx->stream);
 	return e;
 }
 
@@ -1037,6 +1056,8 @@ int prof_collect(spice_ctx* ctx) {
 	if (ctx->prof_used == 0)
 		return SPICE_OK;
 	CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->dstream)
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->dstream));
 	for (size_t i = 0; i + 3 < ctx->prof_used; i += 4) {
 		float a = 0, b = 0, c = 0;
 		cudaEventElapsedTime(&a, ctx->prof_events[i], ctx->prof_events[i + 1]);
@@ -1079,7 +1100,20 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	pa.rank     = ctx->rank;
 	pa.t0       = ctx->time;
 	pa.nsteps   = nsteps;
-	pa.work     = ctx->d_work;
+	int const parity = static_cast<int>(ctx->windows_run & 1);
+	if (ctx->pipelined) {
+		if (!ctx->dstream) {
+			CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->dstream, cudaStreamNonBlocking));
+			CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upd, cudaEventDisableTiming));
+			for (auto& e : ctx->ev_del)
+				CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		}
+		// this window's updates read the counters delivery w - 2 wrote (and reuse its work counter); delivery w - 1 may
+		// still be running: its counters are first read by the next window
+		if (ctx->del_pending[parity])
+			CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_del[parity], 0));
+	}
+	pa.work     = ctx->d_work + (ctx->pipelined ? parity : 0);
 	window_prologue<<<nsteps, 512, 0, ctx->stream>>>(pa);
 	ctx->launches++;
 
@@ -1315,10 +1349,25 @@ int run_window(spice_ctx* ctx, int nsteps) {
 				ta.seq   = ctx->seq;
 			}
 			int launched   = 0;
-			int const e    = deliver::launch_tiles(ctx->stream, ta, ctx->device, &launched);
+			cudaStream_t on = ctx->stream;
+			if (ctx->pipelined) { // beside the next window's updates: after this window's updates (and publish), before the updates of w + 2
+				on      = ctx->dstream;
+				ta.work = ctx->d_work + parity;
+				CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_upd, ctx->stream));
+				CHECK_CUDA(ctx, cudaStreamWaitEvent(on, ctx->ev_upd, 0));
+				if (ctx->profile) {
+					ctx->prof_used--; // the mark behind the exchange goes where the delivery starts
+					prof_mark(ctx, on);
+				}
+			}
+			int const e    = deliver::launch_tiles(on, ta, ctx->device, &launched);
 			if (e != 0)
 				return fail(ctx, SPICE_ERR_CUDA, std::string("delivery launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
 			ctx->launches += launched;
+			if (ctx->pipelined) {
+				CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_del[parity], on));
+				ctx->del_pending[parity] = true;
+			}
 		}
 	} else
 		for (auto& c : ctx->conns) {
@@ -1351,7 +1400,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		}
 
 	if (ctx->profile)
-		prof_mark(ctx);
+		prof_mark(ctx, ctx->pipelined && ctx->tiled && ctx->n_desc > 0 ? ctx->dstream : nullptr);
 	if (ctx->raster_on && np > 0) {
 		sink_args sa{};
 		sa.ring_ids    = ctx->d_ring_ids;
@@ -1398,6 +1447,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	if (e != cudaSuccess)
 		return fail(ctx, SPICE_ERR_CUDA, std::string("window launch: ") + cudaGetErrorString(e));
 	ctx->time += nsteps;
+	ctx->windows_run++;
 	return SPICE_OK;
 }
 
@@ -1612,6 +1662,13 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_nib);
 	cudaFree(ctx->d_conn_desc);
 	cudaFree(ctx->d_work);
+	if (ctx->dstream) {
+		cudaStreamSynchronize(ctx->dstream);
+		cudaStreamDestroy(ctx->dstream);
+		cudaEventDestroy(ctx->ev_upd);
+		for (auto e : ctx->ev_del)
+			cudaEventDestroy(e);
+	}
 	cudaFree(ctx->d_stats);
 	cudaFree(ctx->d_error);
 	cudaFree(ctx->d_pop_size);
@@ -1925,6 +1982,10 @@ int spice_run(spice_ctx* ctx, int64_t n_steps) {
 			return rc;
 		n_steps -= n;
 	}
+	if (ctx->pipelined) // whatever follows on the context's stream (readouts, the next run) sees every delivery of this one
+		for (int p = 0; p < 2; p++)
+			if (ctx->del_pending[p])
+				CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_del[p], 0));
 	return SPICE_OK;
 }
 
