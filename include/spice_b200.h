@@ -110,6 +110,12 @@ SPICE_API int spice_population_range(spice_ctx const* ctx, int pop, int64_t* lo,
  * PRE 0 <= p <= 1 (topology.cpp:73); PRE 1 <= round(delay/dt) <= max_delay (snn.h:35-38). */
 SPICE_API int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop,
                                     double p, float delay, void const* functor, int* conn_out);
+/* The same connection drawn by this backend's counter-based generator (spice_fixed_probability_generate_fast below):
+ * independent Bernoulli(p) per (source, target) pair, rows generated in parallel at write bandwidth.  NOT the reference's
+ * matrix for the same seed (its stream is sequential): for networks whose results are compared statistically.  The
+ * connection consumes the same seed increment, so everything else of the network keeps its streams. */
+SPICE_API int spice_connect_fixed_probability_fast(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop,
+                                         double p, float delay, void const* functor, int* conn_out);
 /* snn::connect<Syn>(source, target, adj_list, delay, syn)            (snn.h:29-56, topology.h:37-46)
  * edges: n_edges (src, dst) pairs; sorted by (src,dst) into CSR as adj_list::generate does
  * (topology.cpp:63-71). */
@@ -193,6 +199,11 @@ SPICE_API int64_t spice_fixed_probability_max_degree(int64_t dst_count, double p
 typedef struct spice_adjacency spice_adjacency;
 SPICE_API int spice_fixed_probability_generate(int device, int64_t src_count, int64_t dst_count, double p, uint64_t seed_lo,
                                      uint64_t seed_hi, int64_t col_lo, int64_t col_hi, spice_adjacency** out);
+/* Not in the reference: the generator its sampler becomes when every row may use its own engine (seed_seq::stream(id),
+ * random.h:169, which the reference defines and never uses): engine (row * 32 + lane), geometric skips between connected
+ * targets, 32 per warp iteration, coalesced stores.  Same accessors; rows ascending, no duplicates, degree ~ Binomial(dst, p). */
+SPICE_API int spice_fixed_probability_generate_fast(int device, int64_t src_count, int64_t dst_count, double p, uint64_t seed_lo,
+                                          uint64_t seed_hi, int64_t col_lo, int64_t col_hi, spice_adjacency** out);
 /* adj_list::generate(offsets, neighbors, seed)                        (topology.cpp:56-71; bench/connectivity.cpp:8-22)
  * on the GPU: the (src, dst) pairs adj_list::connect collected (host arrays) are sorted by (src, dst) and streamed into
  * CSR.  Same handle, same accessors as above.  An index out of range is a violated precondition (topology.cpp:16-18). */

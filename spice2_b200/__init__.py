@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
             "spice_population_size": (i64, [vp, i32]),
             "spice_population_range": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
             "spice_connect_fixed_probability": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
+            "spice_connect_fixed_probability_fast": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
             "spice_connect_adj_list": (i32, [vp, vp, i32, i32, vp, vp, i64, C.c_float, vp, C.POINTER(i32)]),
             "spice_connection_csr": (i32, [vp, i32, C.POINTER(i64), vp, vp]),
             "spice_connection_synapses": (i32, [vp, i32, vp, i64]),
@@ -85,6 +86,7 @@ def lib() -> C.CDLL:
             "spice_adjacency_copy": (i32, [vp, vp, vp]),
             "spice_adjacency_copy_range": (i32, [vp, i64, i64, vp]),
             "spice_adj_list_generate": (i32, [i32, vp, vp, i64, i64, i64, i64, i64, C.POINTER(vp)]),
+            "spice_fixed_probability_generate_fast": (i32, [i32, i64, i64, C.c_double, C.c_uint64, C.c_uint64, i64, i64, C.POINTER(vp)]),
             "spice_adjacency_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i64)]),
             "spice_adjacency_destroy": (i32, [vp]),
             "spice_seed_seq": (None, [vp, i32, vp]),
@@ -130,8 +132,9 @@ SYNAPSE_STATE = {
 class fixed_probability:
     """spice::fixed_probability (spice/include/spice/topology.h:48-58)."""
 
-    def __init__(self, p: float):
+    def __init__(self, p: float, fast: bool = False):
         self.p = float(p)
+        self.fast = bool(fast)  # this backend's counter-based generator: not the reference's matrix for the same seed
 
 
 class adj_list:
@@ -272,8 +275,8 @@ class snn:
         functor = SYNAPSE_MODELS[synapse](**params)
         idx = C.c_int()
         if isinstance(topology, fixed_probability):
-            self._check(lib().spice_connect_fixed_probability(self._h, ops, source.index, target.index, topology.p,
-                                                              np.float32(delay), functor, C.byref(idx)))
+            fn = lib().spice_connect_fixed_probability_fast if topology.fast else lib().spice_connect_fixed_probability
+            self._check(fn(self._h, ops, source.index, target.index, topology.p, np.float32(delay), functor, C.byref(idx)))
         elif isinstance(topology, adj_list):
             s = np.asarray(topology.src, np.int32)
             d = np.asarray(topology.dst, np.int32)
@@ -449,13 +452,15 @@ def generate_adj_list(edges_src, edges_dst, src_count, dst_count, device=0, col_
         L.spice_adjacency_destroy(h)
 
 
-def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True):
-    """fixed_probability::generate on the GPU (spice/src/topology.cpp:80-112) -> dict."""
+def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True, fast=False):
+    """fixed_probability::generate on the GPU (spice/src/topology.cpp:80-112) -> dict.  fast=True: the counter-based
+    generator (spice_fixed_probability_generate_fast), not the reference's matrix."""
     L = lib()
     lo, hi = seed_seq(seed, increments)
     col_hi = dst if col_hi is None else col_hi
     h = C.c_void_p()
-    rc = L.spice_fixed_probability_generate(device, src, dst, p, lo, hi, col_lo, col_hi, C.byref(h))
+    gen = L.spice_fixed_probability_generate_fast if fast else L.spice_fixed_probability_generate
+    rc = gen(device, src, dst, p, lo, hi, col_lo, col_hi, C.byref(h))
     if rc != 0:
         raise SpiceError(rc, L.spice_last_error(None).decode())
     try:

@@ -1228,4 +1228,120 @@ int generate_adj_list(void* stream_, int const* edges_src, int const* edges_dst,
 		*duplicates = (hflags & 2) != 0;
 	return 0;
 }
+
+// ---- fixed_probability, counter-based ------------------------------------------------------------------------------------
+// The generator the north star describes ("counter-based RNG and geometric skip sampling ... bounded by write bandwidth"),
+// NOT the reference's stream: every (row, lane) has its own engine, seed_seq::stream(row * 32 + lane) (random.h:169, unused
+// by the reference), so rows are independent.  A warp generates a row 32 gaps at a time: gap = 1 + floor(log(u) / log(1 - p))
+// (the distance to the next connected target under independent Bernoulli(p) trials), an inclusive scan turns the gaps into
+// targets, the stores are coalesced.  Same distribution family as the reference's sampler (which rounds an exponential
+// and truncates rows at mean + 3 sigma), not the same matrix: no bit-exactness claim, tests are statistical.
+namespace {
+struct fast_args {
+	long long src, dst, col_lo, col_hi;
+	unsigned long long seed_lo, seed_hi;
+	double inv_log1mp;         // 1 / log(1 - p)   (-0.0 for p == 1: every gap is 1)
+	long long* degree;         // [src + 1] kept targets per row (count pass writes)
+	long long const* offsets;  // [src + 1] (write pass reads)
+	int* neighbors;
+};
+
+template <bool kWrite>
+__global__ void __launch_bounds__(256) fp_fast_rows(fast_args a) {
+	__shared__ std::uint64_t tab[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		tab[i] = g_log_tab[i];
+	__syncthreads();
+	int const lane       = threadIdx.x & 31;
+	long long const w    = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	long long const W    = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+	util::seed_seq const seed(UInt128{a.seed_lo, a.seed_hi});
+	for (long long r = w; r < a.src; r += W) {
+		UInt128 const st = seed.stream(static_cast<UInt>(r) * 32 + static_cast<UInt>(lane)).seed();
+		unsigned long long s0 = st.lo, s1 = st.hi;
+		long long base = -1; // the last target taken so far
+		long long kept = 0;
+		long long const out0 = kWrite ? a.offsets[r] : 0;
+		while (base < a.dst - 1) {
+			unsigned long long const x = s0 + s1;
+			xoro_advance(s0, s1);
+			double const u = __dmul_rn(__ull2double_rn((x >> 11) + 1), 0x1p-53); // (0, 1]
+			double const g = __dmul_rn(spice::detail::glibc::log_with_table(u, tab), a.inv_log1mp);
+			long long gap  = 1 + (g < 4.0e9 ? static_cast<long long>(g) : 4000000000ll);
+			long long scan = gap; // inclusive scan over the lanes
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				long long const o = __shfl_up_sync(0xffffffffu, scan, off);
+				if (lane >= off)
+					scan += o;
+			}
+			long long const t  = base + scan;
+			bool const keep    = t < a.dst && t >= a.col_lo && t < a.col_hi;
+			unsigned const m   = __ballot_sync(0xffffffffu, keep);
+			if (kWrite && keep)
+				a.neighbors[out0 + kept + __popc(m & ((1u << lane) - 1))] = static_cast<int>(t - a.col_lo);
+			kept += __popc(m);
+			base += __shfl_sync(0xffffffffu, scan, 31);
+		}
+		if (!kWrite && lane == 0)
+			a.degree[r] = kept;
+	}
+}
+}
+
+int generate_fixed_probability_fast(void* stream_, long long src, long long dst, double p, unsigned long long seed_lo, unsigned long long seed_hi,
+                                    long long col_lo, long long col_hi, result* out, std::string* err) {
+	auto stream = static_cast<cudaStream_t>(stream_);
+	*out        = result{};
+	scratch S;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	GEN_CUDA(S.event(&ev0));
+	GEN_CUDA(S.event(&ev1));
+	GEN_CUDA(cudaEventRecord(ev0, stream));
+	GEN_CUDA(cudaMalloc(&out->offsets, sizeof(long long) * static_cast<size_t>(src + 1)));
+	GEN_CUDA(cudaMemsetAsync(out->offsets, 0, sizeof(long long) * static_cast<size_t>(src + 1), stream));
+	if (src == 0 || dst == 0 || p == 0 || col_hi <= col_lo) {
+		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * 8));
+		GEN_CUDA(cudaStreamSynchronize(stream));
+		return 0;
+	}
+	{
+		static bool uploaded[64] = {};
+		static std::mutex upload_mutex;
+		std::lock_guard<std::mutex> lock(upload_mutex);
+		int dev = 0;
+		GEN_CUDA(cudaGetDevice(&dev));
+		if (dev >= 0 && dev < 64 && !uploaded[dev]) {
+			GEN_CUDA(cudaMemcpyToSymbol(g_log_tab, spice::detail::glibc::log_tab, sizeof(g_log_tab)));
+			uploaded[dev] = true;
+		}
+	}
+	long long* degree = nullptr;
+	void* tmp         = nullptr;
+	GEN_CUDA(S.alloc(&degree, static_cast<size_t>(src + 1)));
+	GEN_CUDA(cudaMemsetAsync(degree, 0, sizeof(long long) * static_cast<size_t>(src + 1), stream));
+	fast_args fa{src, dst, col_lo, col_hi, seed_lo, seed_hi, p < 1 ? 1.0 / std::log1p(-p) : -0.0, degree, nullptr, nullptr};
+	int const grid = static_cast<int>(std::min<long long>((src + 7) / 8, 148 * 16));
+	fp_fast_rows<false><<<grid, 256, 0, stream>>>(fa);
+	size_t bytes = 0;
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, degree, out->offsets, static_cast<long long>(src + 1), stream));
+	GEN_CUDA(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+	S.dev.push_back(tmp);
+	GEN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, degree, out->offsets, static_cast<long long>(src + 1), stream));
+	long long edges = 0;
+	GEN_CUDA(cudaMemcpyAsync(&edges, out->offsets + src, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+	GEN_CUDA(cudaStreamSynchronize(stream));
+	GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(edges + 8)));
+	fa.offsets   = out->offsets;
+	fa.neighbors = out->neighbors;
+	fp_fast_rows<true><<<grid, 256, 0, stream>>>(fa);
+	GEN_CUDA(cudaGetLastError());
+	GEN_CUDA(cudaEventRecord(ev1, stream));
+	GEN_CUDA(cudaStreamSynchronize(stream));
+	out->edges    = edges;
+	out->launches = 4;
+	cudaEventElapsedTime(&out->total_ms, ev0, ev1);
+	(void)err;
+	return 0;
+}
 }

@@ -27,6 +27,11 @@ long long max_degree(long long dst, double p);
 int generate_adj_list(void* cuda_stream, int const* edges_src, int const* edges_dst, long long n_edges, long long src, long long dst,
                       long long col_lo, long long col_hi, result* out, bool* duplicates, std::string* err);
 
+// The counter-based generator (one engine per (row, lane): seed_seq::stream): independent Bernoulli(p) per pair by geometric
+// skips, rows in parallel, bounded by write bandwidth.  Same interface; NOT the reference's matrix for the same seed.
+int generate_fixed_probability_fast(void* cuda_stream, long long src, long long dst, double p, unsigned long long seed_lo,
+                                    unsigned long long seed_hi, long long col_lo, long long col_hi, result* out, std::string* err);
+
 int generate_fixed_probability(void* cuda_stream, long long src, long long dst, double p, unsigned long long seed_lo,
                                unsigned long long seed_hi, long long col_lo, long long col_hi, long long chunk_draws,
                                result* out, std::string* err);

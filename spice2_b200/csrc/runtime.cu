@@ -445,6 +445,7 @@ struct connection {
 	apply_events_fn apply_events = nullptr;
 	// fixed_probability connections are generated when the network is finalized, all of them concurrently
 	bool pending_fp  = false;
+	bool fp_fast     = false; // the counter-based generator (gen::generate_fixed_probability_fast): not the reference's matrix
 	double fp_p      = 0;
 	UInt128 fp_seed{0, 0};   // the graph's seed (synapse_population.h:31), drawn at connect() time
 	UInt128 init_seed{0, 0}; // the per-synapse init hook's (synapse_population.h:35), drawn right behind it
@@ -632,8 +633,10 @@ int build_pending(spice_ctx* ctx) {
 			jobs[j].err = "cannot create a stream for synapse generation";
 			return;
 		}
-		jobs[j].rc = gen::generate_fixed_probability(st, src.size, dst.size, c.fp_p, c.fp_seed.lo, c.fp_seed.hi, dst.lo, dst.hi, 0, &jobs[j].r,
-		                                             &jobs[j].err);
+		jobs[j].rc = c.fp_fast ? gen::generate_fixed_probability_fast(st, src.size, dst.size, c.fp_p, c.fp_seed.lo, c.fp_seed.hi, dst.lo, dst.hi,
+		                                                              &jobs[j].r, &jobs[j].err)
+		                       : gen::generate_fixed_probability(st, src.size, dst.size, c.fp_p, c.fp_seed.lo, c.fp_seed.hi, dst.lo, dst.hi, 0,
+		                                                         &jobs[j].r, &jobs[j].err);
 		cudaStreamDestroy(st);
 	};
 	if (serial || todo.size() == 1)
@@ -1788,6 +1791,18 @@ int spice_population_range(spice_ctx const* ctx, int pop, int64_t* lo, int64_t* 
 	return SPICE_OK;
 }
 
+int spice_connect_fixed_probability_fast(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop, double p, float delay,
+                                         void const* functor, int* conn_out) {
+	int idx      = -1;
+	int const rc = spice_connect_fixed_probability(ctx, ops, src_pop, dst_pop, p, delay, functor, &idx);
+	if (rc != SPICE_OK)
+		return rc;
+	ctx->conns[static_cast<size_t>(idx)].fp_fast = true;
+	if (conn_out)
+		*conn_out = idx;
+	return SPICE_OK;
+}
+
 int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops, int src_pop, int dst_pop, double p,
                                     float delay, void const* functor, int* conn_out) {
 	PRE(ctx, 0 <= p && p <= 1); // topology.cpp:73
@@ -2286,6 +2301,35 @@ int spice_fixed_probability_generate(int device, int64_t src_count, int64_t dst_
 	a->src    = src_count;
 	std::string err;
 	int const rc = gen::generate_fixed_probability(nullptr, src_count, dst_count, p, seed_lo, seed_hi, col_lo, col_hi, 0, &a->r, &err);
+	if (rc != 0) {
+		cudaFree(a->r.offsets);
+		cudaFree(a->r.neighbors);
+		g_create_error = err;
+		return rc;
+	}
+	*out = a.release();
+	return SPICE_OK;
+}
+
+int spice_fixed_probability_generate_fast(int device, int64_t src_count, int64_t dst_count, double p, uint64_t seed_lo, uint64_t seed_hi,
+                                          int64_t col_lo, int64_t col_hi, spice_adjacency** out) {
+	*out = nullptr;
+	if (!(0 <= p && p <= 1) || src_count < 0 || dst_count < 0 || src_count >= 2147483647 || dst_count >= 2147483647 || col_lo < 0 ||
+	    col_hi > dst_count || col_lo > col_hi) {
+		g_create_error = "spice_fixed_probability_generate_fast: invalid argument";
+		return SPICE_ERR_PRECONDITION;
+	}
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) {
+		g_create_error = "no CUDA device — this backend has no CPU fallback";
+		return SPICE_ERR_NO_DEVICE;
+	}
+	cudaSetDevice(device);
+	auto a    = std::make_unique<spice_adjacency>();
+	a->device = device;
+	a->src    = src_count;
+	std::string err;
+	int const rc = gen::generate_fixed_probability_fast(nullptr, src_count, dst_count, p, seed_lo, seed_hi, col_lo, col_hi, &a->r, &err);
 	if (rc != 0) {
 		cudaFree(a->r.offsets);
 		cudaFree(a->r.neighbors);

@@ -7,9 +7,10 @@ import numpy as np
 from . import fixed_probability, snn
 
 
-def brunel(N=20000, p=0.1, w_exc=None, w_inh=None, dt=1e-4, delay=15e-4, seed=(1337,), plastic=False, **ctx):
+def brunel(N=20000, p=0.1, w_exc=None, w_inh=None, dt=1e-4, delay=15e-4, seed=(1337,), plastic=False, fast_topology=False, **ctx):
     """P (poisson, N/2), E (lif, 4N/10), I (lif, N/10); P->E, P->I, E->E, E->I, I->E, I->I.
-    plastic=True: E->E carries the STDP synapse of samples/brunel+.cpp:59-99,114."""
+    plastic=True: E->E carries the STDP synapse of samples/brunel+.cpp:59-99,114.
+    fast_topology=True: the connections are drawn by the counter-based generator (not the reference's matrices)."""
     w_exc = np.float32(2.0 / N) if w_exc is None else np.float32(w_exc)
     w_inh = np.float32(-10.0 / N) if w_inh is None else np.float32(w_inh)
     net = snn(dt, delay, seed, **ctx)
@@ -18,9 +19,9 @@ def brunel(N=20000, p=0.1, w_exc=None, w_inh=None, dt=1e-4, delay=15e-4, seed=(1
     I = net.add_population("brunel.lif", N // 10)
     for (s, d, w) in ((P, E, w_exc), (P, I, w_exc), (E, E, w_exc), (E, I, w_exc), (I, E, w_inh), (I, I, w_inh)):
         if plastic and s is E and d is E:
-            net.connect("brunel+.plastic", s, d, fixed_probability(p), delay)
+            net.connect("brunel+.plastic", s, d, fixed_probability(p, fast_topology), delay)
         else:
-            net.connect("brunel.fixed_weight", s, d, fixed_probability(p), delay, weight=w)
+            net.connect("brunel.fixed_weight", s, d, fixed_probability(p, fast_topology), delay, weight=w)
     return net, (P, E, I)
 
 

@@ -134,3 +134,78 @@ def test_adj_list_generate_matches_sorted_keys(sp):
         assert r["edges"] == nb.size and np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (n, src, dst)
     with pytest.raises(sp.SpiceError):
         sp.generate_adj_list(np.array([0, 9], np.int32), np.array([0, 1], np.int32), 5, 5)
+
+
+# ---- the counter-based generator (spice_fixed_probability_generate_fast) ---------------------------------------------------
+# Not the reference's matrix (its stream is sequential): what is pinned is (1) the algorithm as include/spice_b200.h states
+# it, restated here with the oracle's seed_seq::stream / xoroshiro128+ and the host libm's log (which the device restates
+# bit for bit, tests/golden/libm_pins.npz), and (2) the distribution the reference's sampler targets.
+def _fast_rows_restated(orc, seed, src, dst, p, col_lo, col_hi):
+    import math
+
+    inv = 1.0 / math.log1p(-p) if p < 1 else -0.0
+    offsets, nb = [0], []
+    for r in range(src):
+        draws = [orc.xoroshiro(orc.L.orc_seed_stream(seed, r * 32 + lane), 64) for lane in range(32)]
+        base, it = -1, 0
+        while base < dst - 1:
+            if it == len(draws[0]):
+                draws = [orc.xoroshiro(orc.L.orc_seed_stream(seed, r * 32 + lane), 2 * it) for lane in range(32)]
+            for lane in range(32):
+                u = float((int(draws[lane][it]) >> 11) + 1) * 2.0 ** -53
+                g = math.log(u) * inv
+                base += 1 + (int(g) if g < 4.0e9 else 4000000000)
+                if base < dst and col_lo <= base < col_hi:
+                    nb.append(base - col_lo)
+            it += 1
+        offsets.append(len(nb))
+    return np.asarray(offsets, np.int64), np.asarray(nb, np.int32)
+
+
+def test_fast_generator_matches_its_restatement(sp, orc):
+    for (s, d, p, lo, hi, il) in [(40, 700, 0.1, 0, 700, (1337,)), (25, 3000, 0.02, 0, 3000, (7, 9)), (30, 500, 0.75, 100, 320, (5,)),
+                                  (9, 100, 1.0, 0, 100, (1,)), (6, 40000, 0.001, 0, 40000, (3,))]:
+        r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
+        off, nb = _fast_rows_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
+        assert np.array_equal(r["offsets"], off), (s, d, p)
+        assert np.array_equal(r["neighbors"], nb), (s, d, p)
+
+
+def test_fast_generator_distribution_and_structure(sp):
+    """Rows strictly ascending (no multapses), degrees ~ Binomial(dst, p), every pair equally likely, deterministic per
+    seed; the reference's sampler has the same mean degree (topology.cpp:80-112) and clips rows at mean + 3 sigma."""
+    s, d, p = 4000, 20000, 0.1
+    r = sp.generate_fixed_probability(s, d, p, (1337,), fast=True)
+    off, nb = r["offsets"], r["neighbors"]
+    assert off[0] == 0 and off[-1] == r["edges"] == nb.size
+    deg = np.diff(off)
+    inner = np.ones(nb.size, bool)
+    inner[off[1:-1][deg[1:] > 0]] = False  # first entry of every row but the first
+    inner[0] = False
+    assert (np.diff(nb.astype(np.int64))[inner[1:]] > 0).all() and nb.min() >= 0 and nb.max() < d
+    mean, sd = d * p, (d * p * (1 - p)) ** 0.5
+    assert abs(deg.mean() - mean) < 4 * sd / s ** 0.5
+    assert 0.9 * sd < deg.std() < 1.1 * sd
+    col = np.bincount(nb, minlength=d)  # in-degrees ~ Binomial(src, p): columns are not favoured by position
+    assert abs(col[: d // 2].mean() - col[d // 2:].mean()) < 6 * (s * p * (1 - p)) ** 0.5 / (d / 2) ** 0.5
+    assert 0.9 < col.std() / (s * p * (1 - p)) ** 0.5 < 1.1
+    gaps = np.diff(nb.astype(np.int64))[inner[1:]]  # geometric: P(gap = 1) = p, mean 1/p
+    assert abs((gaps == 1).mean() - p) < 0.002 and abs(gaps.mean() - 1 / p) < 0.05
+    again = sp.generate_fixed_probability(s, d, p, (1337,), fast=True)
+    other = sp.generate_fixed_probability(s, d, p, (1338,), fast=True)
+    assert np.array_equal(again["neighbors"], nb) and not np.array_equal(other["neighbors"][:1000], nb[:1000])
+    for (a, b, q) in [(0, 10, 0.5), (10, 0, 0.5), (10, 10, 0.0)]:
+        z = sp.generate_fixed_probability(a, b, q, fast=True)
+        assert z["edges"] == 0 and not z["offsets"].any()
+
+
+def test_fast_generator_column_slices_tile_the_matrix(sp):
+    s, d, p, world = 300, 9000, 0.05, 4
+    full = sp.generate_fixed_probability(s, d, p, (11,), fast=True)
+    rows = [[] for _ in range(s)]
+    for k in range(world):
+        lo, hi = d * k // world, d * (k + 1) // world
+        part = sp.generate_fixed_probability(s, d, p, (11,), col_lo=lo, col_hi=hi, fast=True)
+        for i in range(s):
+            rows[i].append(part["neighbors"][part["offsets"][i]: part["offsets"][i + 1]] + lo)
+    assert np.array_equal(np.concatenate([np.concatenate(x) for x in rows]), full["neighbors"])

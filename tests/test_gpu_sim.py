@@ -299,6 +299,41 @@ def test_fast_mode_tolerances(sp, orc):
     assert np.mean(np.abs(gs["W"].astype(np.float64) - ws["W"].astype(np.float64)) <= 1e-7) >= 0.995
 
 
+FAST_TOPOLOGY_BAND = 0.10  # the rates must lie within the spread of the reference's own seeds, widened by this much
+
+
+def test_fast_topology_keeps_the_firing_rates(sp, orc):
+    """fixed_probability(p, fast=True): the counter-based generator draws another matrix from the distribution the
+    reference's sampler targets, so the raster differs.  At this size the rates of the E and I populations depend on the
+    drawn graph by +-16 % (six reference seeds, 6000 steps), so the stated tolerance is that spread: the rates with the
+    counter-based graph must lie inside the band the reference's own graphs span.  The Poisson input is the same stream
+    (the connection consumes the same seed increment), spike for spike."""
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=8000, p=0.1, w_exc=np.float32(2.0 / 800), w_inh=np.float32(-10.0 / 800))
+    steps, skip = 1500, 300
+    net, pops = brunel(fast_topology=True, seed=(1337,), **kw)
+    net.raster_enable(True)
+    net.step(steps)
+    counts, _ids = net.raster_read(steps)
+    band = []
+    for seed in ((1337,), (1,), (2,), (3,), (4,), (5,)):
+        onet, opops = brunel_oracle(orc, seed=seed, **kw)
+        ocounts = np.zeros_like(counts)
+        for s in range(steps):
+            onet.step()
+            ocounts[s] = [len(onet.spikes(op, 0)) for op in opops]
+        if seed == (1337,):
+            assert np.array_equal(counts[:, 0], ocounts[:, 0])  # the Poisson population does not depend on the graph
+        band.append(ocounts[skip:].sum(0).astype(float))
+    band = np.array(band)
+    got = counts[skip:].sum(0).astype(float)
+    assert np.all(got >= band.min(0) * (1 - FAST_TOPOLOGY_BAND)) and np.all(got <= band.max(0) * (1 + FAST_TOPOLOGY_BAND)), (got, band)
+    off, nb = net.connection_csr(2)
+    deg = np.diff(off)
+    assert abs(deg.mean() - 320.0) < 4 * (3200 * 0.1 * 0.9) ** 0.5 / 3200 ** 0.5
+
+
 def test_brunel_plus_300_golden(sp, orc, golden):
     """samples/brunel+ (N = 20000, 300 steps): raster of the compiled reference (strict flavour)."""
     from spice2_b200.samples import brunel
