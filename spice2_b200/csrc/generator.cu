@@ -1231,11 +1231,24 @@ int generate_adj_list(void* stream_, int const* edges_src, int const* edges_dst,
 
 // ---- fixed_probability, counter-based ------------------------------------------------------------------------------------
 // The generator the north star describes ("counter-based RNG and geometric skip sampling ... bounded by write bandwidth"),
-// NOT the reference's stream: every (row, lane) has its own engine, seed_seq::stream(row * 32 + lane) (random.h:169, unused
-// by the reference), so rows are independent.  A warp generates a row 32 gaps at a time: gap = 1 + floor(log(u) / log(1 - p))
-// (the distance to the next connected target under independent Bernoulli(p) trials), an inclusive scan turns the gaps into
-// targets, the stores are coalesced.  Same distribution family as the reference's sampler (which rounds an exponential
-// and truncates rows at mean + 3 sigma), not the same matrix: no bit-exactness claim, tests are statistical.
+// NOT the reference's stream: independent Bernoulli(p) per (source, target) pair, drawn as geometric gaps between connected
+// targets by engines addressed with seed_seq::stream(id) (random.h:169, which the reference defines and never uses).  Same
+// distribution family as the reference's sampler (which rounds an exponential and truncates rows at mean + 3 sigma), not
+// the same matrix.  Two definitions, by p (both restated in tests/test_gpu_generator.py):
+//
+//  p >= 2^-13  "tiles" (fp_fast_tiles, ONE pass):  a row is cut into blocks of B = 2^ceil(log2(512 / p)) consecutive
+//     targets (geometric gaps are memoryless, so restarting at block starts changes nothing), unit (row r, block b) has the
+//     engines stream((r * nblocks + b) * 32 + lane).  Per iteration every lane takes two 64-bit draws = four 32-bit
+//     uniforms (high word first), each mapped to gap = 1 + #{k >= 1 : u < T[k]}, T[k] = floor(2^32 (1-p)^k) — an integer
+//     table built on the host, so the map is exact and restatable; the device finds k from a MUFU.LG2 estimate and fixes it
+//     against the table.  Lane l's four gaps follow lane l-1's; a warp scan of the lane sums turns them into targets.  A
+//     warp collects its unit in shared memory; a CTA of 8 warps = one tile of 8 consecutive units, tiles are claimed in
+//     order from a ticket and get their place in the output by decoupled look-back over (status, count) words, so the
+//     neighbours are written once, coalesced, with no counting pass and no host round trip (the output is allocated at
+//     mean + 10 sigma entries; the run repeats with the exact size in the never-seen case that this is too small).
+//     A rank generates only the blocks that overlap its columns.
+//  p <  2^-13  "log path" (fp_fast_rows, count + write passes): a warp per row, engines stream(r * 32 + lane),
+//     gap = 1 + floor(log(u) / log(1 - p)) in double with the glibc log restatement, 32 gaps per iteration.
 namespace {
 struct fast_args {
 	long long src, dst, col_lo, col_hi;
@@ -1287,12 +1300,287 @@ __global__ void __launch_bounds__(256) fp_fast_rows(fast_args a) {
 			a.degree[r] = kept;
 	}
 }
+
+// ---- tiles ----
+constexpr int kTileWarps = 8;    // units per tile = warps per CTA
+constexpr int kUnitCap   = 1536; // entries a warp can hold: the mean is < 1024, sigma < 32
+constexpr int kTabSmem   = 8192; // table entries kept in shared memory (p >= 0.0027); larger tables are read through L1
+
+struct tile_args {
+	long long src, dst, col_lo, col_hi;
+	unsigned long long seed_lo, seed_hi;
+	int block_log2;             // B = 1 << block_log2
+	long long nblocks;          // blocks per row, ceil(dst / B)
+	long long b_lo, nb_local;   // blocks that overlap [col_lo, col_hi)
+	long long units, tiles;
+	float s;                    // -1 / log2(1 - p): gaps per halving of u
+	int K;                      // tab[1 .. K], tab[K] = 0 (tab[0] unused)
+	unsigned const* tab;
+	unsigned long long* desc;   // [tiles] status << 62 | count
+	unsigned long long* ticket;
+	long long* offsets;
+	int* neighbors;
+	long long cap;              // entries allocated in neighbors
+	int* flags;                 // 1: a unit did not fit kUnitCap, 2: neighbors too small
+};
+
+__device__ __forceinline__ int gap_of(unsigned u, unsigned const* __restrict__ tab, int K, float s) {
+	int c = static_cast<int>((32.0f - __log2f(static_cast<float>(u) + 1.0f)) * s);
+	c     = min(max(c, 0), K - 1);
+	while (tab[c + 1] > u)
+		c++;
+	while (c > 0 && tab[c] <= u)
+		c--;
+	return c + 1;
+}
+
+__global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
+	extern __shared__ __align__(16) int smem[];
+	__shared__ int wcount[kTileWarps];
+	__shared__ long long s_tile, s_excl;
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int* const buf = smem + warp * kUnitCap;
+	unsigned const* tab = a.tab;
+	if (a.K + 1 <= kTabSmem) {
+		unsigned* t = reinterpret_cast<unsigned*>(smem + kTileWarps * kUnitCap);
+		for (int i = threadIdx.x; i <= a.K; i += blockDim.x)
+			t[i] = a.tab[i];
+		tab = t;
+	}
+	util::seed_seq const seed(UInt128{a.seed_lo, a.seed_hi});
+	long long const B = 1ll << a.block_log2;
+	for (;;) {
+		__syncthreads(); // the table is loaded; the previous tile is done with s_tile / s_excl / wcount
+		if (threadIdx.x == 0)
+			s_tile = static_cast<long long>(atomicAdd(a.ticket, 1ull));
+		__syncthreads();
+		long long const tile = s_tile;
+		if (tile >= a.tiles)
+			return;
+		long long const v = tile * kTileWarps + warp;
+		int n             = 0;
+		long long r = 0, b = 0;
+		if (v < a.units) {
+			r                     = v / a.nb_local;
+			b                     = a.b_lo + (v - r * a.nb_local);
+			long long const blk0  = b << a.block_log2;
+			int const bsize       = static_cast<int>(min(B, a.dst - blk0));
+			int const lo_rel      = static_cast<int>(max(a.col_lo - blk0, 0ll));
+			int const hi_rel      = static_cast<int>(min(a.col_hi - blk0, static_cast<long long>(bsize)));
+			int const add         = static_cast<int>(blk0 - a.col_lo); // block-relative target -> local column
+			UInt128 const st      = seed.stream(static_cast<UInt>(r * a.nblocks + b) * 32 + static_cast<UInt>(lane)).seed();
+			unsigned long long s0 = st.lo, s1 = st.hi;
+			int pos               = -1; // the last target drawn so far
+			while (pos < hi_rel - 1) {
+				unsigned long long const x0 = s0 + s1;
+				xoro_advance(s0, s1);
+				unsigned long long const x1 = s0 + s1;
+				xoro_advance(s0, s1);
+				int const l1 = gap_of(static_cast<unsigned>(x0 >> 32), tab, a.K, a.s);
+				int const l2 = l1 + gap_of(static_cast<unsigned>(x0), tab, a.K, a.s);
+				int const l3 = l2 + gap_of(static_cast<unsigned>(x1 >> 32), tab, a.K, a.s);
+				int const l4 = l3 + gap_of(static_cast<unsigned>(x1), tab, a.K, a.s);
+				int incl     = l4;
+#pragma unroll
+				for (int off = 1; off < 32; off <<= 1) {
+					int const o = __shfl_up_sync(0xffffffffu, incl, off);
+					if (lane >= off)
+						incl += o;
+				}
+				int const tot  = __shfl_sync(0xffffffffu, incl, 31);
+				int const base = pos + incl - l4;
+				int const t0 = base + l1, t1 = base + l2, t2 = base + l3, t3 = base + l4;
+				if (n + 128 > kUnitCap) {
+					if (lane == 0)
+						atomicOr(a.flags, 1);
+					break;
+				}
+				if (pos + 1 >= lo_rel && pos + tot < hi_rel) { // every target of the iteration is kept
+					int* const at = buf + n + lane * 4;
+					if ((n & 3) == 0) {
+						*reinterpret_cast<int4*>(at) = make_int4(t0 + add, t1 + add, t2 + add, t3 + add);
+					} else { // only behind a first iteration that dropped targets in front of this rank's columns
+						at[0] = t0 + add;
+						at[1] = t1 + add;
+						at[2] = t2 + add;
+						at[3] = t3 + add;
+					}
+					n += 128;
+				} else {
+					bool const k0 = t0 >= lo_rel && t0 < hi_rel, k1 = t1 >= lo_rel && t1 < hi_rel, k2 = t2 >= lo_rel && t2 < hi_rel,
+					           k3      = t3 >= lo_rel && t3 < hi_rel;
+					int const mine = k0 + k1 + k2 + k3;
+					int cs         = mine;
+#pragma unroll
+					for (int off = 1; off < 32; off <<= 1) {
+						int const o = __shfl_up_sync(0xffffffffu, cs, off);
+						if (lane >= off)
+							cs += o;
+					}
+					int at = n + cs - mine;
+					if (k0)
+						buf[at++] = t0 + add;
+					if (k1)
+						buf[at++] = t1 + add;
+					if (k2)
+						buf[at++] = t2 + add;
+					if (k3)
+						buf[at++] = t3 + add;
+					n += __shfl_sync(0xffffffffu, cs, 31);
+				}
+				pos += tot;
+			}
+		}
+		if (lane == 0)
+			wcount[warp] = n;
+		__syncthreads();
+		if (warp == 0) {
+			int const c   = lane < kTileWarps ? wcount[lane] : 0;
+			long long tot = c;
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1)
+				tot += __shfl_xor_sync(0xffffffffu, tot, off);
+			long long excl = 0;
+			if (tile > 0) {
+				if (lane == 0)
+					atomicExch(a.desc + tile, (1ull << 62) | static_cast<unsigned long long>(tot));
+				long long idx = tile - 1;
+				for (;;) { // 32 predecessors at a time, nearest first
+					long long const j = idx - lane;
+					unsigned long long d;
+					do {
+						d = j >= 0 ? *reinterpret_cast<unsigned long long volatile*>(a.desc + j) : (2ull << 62);
+					} while (__any_sync(0xffffffffu, (d >> 62) == 0));
+					unsigned const incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+					int const stop           = incl_mask ? __ffs(incl_mask) - 1 : 31;
+					long long part           = lane <= stop ? static_cast<long long>(d & ((1ull << 62) - 1)) : 0;
+#pragma unroll
+					for (int off = 16; off > 0; off >>= 1)
+						part += __shfl_xor_sync(0xffffffffu, part, off);
+					excl += part;
+					if (incl_mask)
+						break;
+					idx -= 32;
+				}
+			}
+			if (lane == 0) {
+				atomicExch(a.desc + tile, (2ull << 62) | static_cast<unsigned long long>(excl + tot));
+				s_excl = excl;
+			}
+		}
+		__syncthreads();
+		if (v < a.units) {
+			long long base = s_excl;
+			for (int w = 0; w < warp; w++)
+				base += wcount[w];
+			if (base + n > a.cap) {
+				if (lane == 0)
+					atomicOr(a.flags, 2);
+			} else {
+				for (int i = lane; i < n; i += 32)
+					a.neighbors[base + i] = buf[i];
+			}
+			if (lane == 0) {
+				if (b == a.b_lo)
+					a.offsets[r] = base;
+				if (v == a.units - 1)
+					a.offsets[a.src] = base + n;
+			}
+		}
+	}
+}
+}
+
+namespace {
+int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, double p, unsigned long long seed_lo, unsigned long long seed_hi,
+                        long long col_lo, long long col_hi, result* out, std::string* err) {
+	scratch S;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	GEN_CUDA(S.event(&ev0));
+	GEN_CUDA(S.event(&ev1));
+	// gap = 1 + #{k >= 1 : u < T[k]}, T[k] = floor(2^32 (1-p)^k): P(gap > k) = T[k] / 2^32
+	std::vector<unsigned> tab{0xffffffffu};
+	double const lq = std::log1p(-p); // -inf for p = 1: T[1] = 0, every gap is 1
+	for (long long k = 1;; k++) {
+		unsigned const t = static_cast<unsigned>(std::floor(4294967296.0 * std::exp(static_cast<double>(k) * lq)));
+		tab.push_back(t);
+		if (t == 0)
+			break;
+	}
+	tile_args a{};
+	a.src = src, a.dst = dst, a.col_lo = col_lo, a.col_hi = col_hi, a.seed_lo = seed_lo, a.seed_hi = seed_hi;
+	a.K = static_cast<int>(tab.size()) - 1;
+	a.s = p < 1 ? static_cast<float>(-1.0 / std::log2(1.0 - p)) : 0.0f;
+	a.block_log2 = 0;
+	while (static_cast<double>(1ll << a.block_log2) < 512.0 / p)
+		a.block_log2++;
+	long long const B = 1ll << a.block_log2;
+	a.nblocks  = (dst + B - 1) / B;
+	a.b_lo     = col_lo / B;
+	a.nb_local = (col_hi + B - 1) / B - a.b_lo;
+	a.units    = src * a.nb_local;
+	a.tiles    = (a.units + kTileWarps - 1) / kTileWarps;
+	double const mean = static_cast<double>(src) * static_cast<double>(col_hi - col_lo) * p;
+	a.cap             = static_cast<long long>(mean + 10.0 * std::sqrt(mean * (1 - p) + 1.0)) + 1024;
+	unsigned* d_tab = nullptr;
+	int* d_flags    = nullptr;
+	GEN_CUDA(S.alloc(&d_tab, tab.size()));
+	GEN_CUDA(S.alloc(&a.desc, static_cast<size_t>(a.tiles) + 1));
+	GEN_CUDA(S.alloc(&d_flags, 4));
+	GEN_CUDA(cudaMalloc(&out->offsets, sizeof(long long) * static_cast<size_t>(src + 1)));
+	GEN_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(unsigned) * tab.size(), cudaMemcpyHostToDevice, stream));
+	a.tab     = d_tab;
+	a.ticket  = a.desc + a.tiles;
+	a.offsets = out->offsets;
+	a.flags   = d_flags;
+	size_t const smem = sizeof(int) * static_cast<size_t>(kTileWarps * kUnitCap + (a.K + 1 <= kTabSmem ? a.K + 1 : 0));
+	GEN_CUDA(cudaFuncSetAttribute(fp_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	int dev = 0, sms = 148, per_sm = 1;
+	GEN_CUDA(cudaGetDevice(&dev));
+	GEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	GEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fp_fast_tiles, kTileWarps * 32, smem));
+	int const grid = static_cast<int>(std::min<long long>(a.tiles, static_cast<long long>(sms) * std::max(per_sm, 1)));
+	for (int attempt = 0; attempt < 2; attempt++) {
+		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(a.cap + 8)));
+		a.neighbors = out->neighbors;
+		GEN_CUDA(cudaEventRecord(ev0, stream));
+		GEN_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (static_cast<size_t>(a.tiles) + 1), stream));
+		GEN_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream));
+		fp_fast_tiles<<<grid, kTileWarps * 32, smem, stream>>>(a);
+		GEN_CUDA(cudaGetLastError());
+		GEN_CUDA(cudaEventRecord(ev1, stream));
+		long long edges = 0;
+		int flags       = 0;
+		GEN_CUDA(cudaMemcpyAsync(&edges, out->offsets + src, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+		GEN_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+		GEN_CUDA(cudaStreamSynchronize(stream));
+		out->edges = edges;
+		out->launches += 1;
+		cudaEventElapsedTime(&out->total_ms, ev0, ev1);
+		out->rows_ms = out->total_ms;
+		if (flags & 1) {
+			if (err)
+				*err = "counter-based generator: a unit exceeded its capacity (mean + 16 sigma)";
+			return 4; // SPICE_ERR_INTERNAL
+		}
+		if (!(flags & 2))
+			return 0;
+		cudaFree(out->neighbors); // mean + 10 sigma was too small: the run has counted the edges, repeat with that size
+		out->neighbors = nullptr;
+		a.cap          = edges;
+	}
+	if (err)
+		*err = "counter-based generator: the output did not fit its exact size";
+	return 4;
+}
 }
 
 int generate_fixed_probability_fast(void* stream_, long long src, long long dst, double p, unsigned long long seed_lo, unsigned long long seed_hi,
                                     long long col_lo, long long col_hi, result* out, std::string* err) {
 	auto stream = static_cast<cudaStream_t>(stream_);
 	*out        = result{};
+	if (src > 0 && dst > 0 && col_hi > col_lo && p >= 0x1p-13 && std::getenv("SPICE_GEN_FAST_LOG_PATH") == nullptr)
+		return generate_fast_tiles(stream, src, dst, p, seed_lo, seed_hi, col_lo, col_hi, out, err);
 	scratch S;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	GEN_CUDA(S.event(&ev0));

@@ -137,10 +137,53 @@ def test_adj_list_generate_matches_sorted_keys(sp):
 
 
 # ---- the counter-based generator (spice_fixed_probability_generate_fast) ---------------------------------------------------
-# Not the reference's matrix (its stream is sequential): what is pinned is (1) the algorithm as include/spice_b200.h states
-# it, restated here with the oracle's seed_seq::stream / xoroshiro128+ and the host libm's log (which the device restates
-# bit for bit, tests/golden/libm_pins.npz), and (2) the distribution the reference's sampler targets.
+# Not the reference's matrix (its stream is sequential): what is pinned is (1) the algorithm as csrc/generator.cu states it
+# (two definitions, by p), restated here with the oracle's seed_seq::stream / xoroshiro128+ and the host libm (whose log the
+# device restates bit for bit, tests/golden/libm_pins.npz), and (2) the distribution the reference's sampler targets.
+def _fast_tiles_restated(orc, seed, src, dst, p, col_lo, col_hi):
+    """p >= 2^-13: blocks of B targets, unit (row, block) = engines stream((row * nblocks + block) * 32 + lane); per
+    iteration a lane maps two 64-bit draws to four gaps (high word first) with the integer table T[k] = floor(2^32 q^k)."""
+    import math
+
+    lq = math.log1p(-p) if p < 1 else -math.inf
+    tab = [0xFFFFFFFF]
+    k = 1
+    while True:
+        t = int(math.floor(4294967296.0 * math.exp(k * lq)))
+        tab.append(t)
+        if t == 0:
+            break
+        k += 1
+    thresholds = -np.asarray(tab[1:], np.int64)  # ascending, for searchsorted: #{k >= 1: T[k] > u}
+    blog = 0
+    while float(1 << blog) < 512.0 / p:
+        blog += 1
+    B = 1 << blog
+    nblocks = (dst + B - 1) // B
+    offsets, nb = [0], []
+    for r in range(src):
+        for b in range(col_lo // B, (col_hi + B - 1) // B):
+            blk0 = b * B
+            bsize = min(B, dst - blk0)
+            gid = r * nblocks + b
+            draws = np.stack([orc.xoroshiro(orc.L.orc_seed_stream(seed, gid * 32 + lane), 256) for lane in range(32)])  # [lane, draw]
+            pos, it = -1, 0
+            while pos < bsize - 1:
+                x = draws[:, 2 * it: 2 * it + 2]
+                u = np.stack([x[:, 0] >> np.uint64(32), x[:, 0] & np.uint64(0xFFFFFFFF), x[:, 1] >> np.uint64(32),
+                              x[:, 1] & np.uint64(0xFFFFFFFF)], axis=1).astype(np.int64).reshape(-1)  # lane-major, then the four gaps
+                gaps = 1 + np.searchsorted(thresholds, -u, side="left")  # #{k: T[k] > u} = #{k: -T[k] < -u}
+                t = pos + np.cumsum(gaps)
+                keep = t[(t < bsize) & (t + blk0 >= col_lo) & (t + blk0 < col_hi)]
+                nb.extend((keep + blk0 - col_lo).tolist())
+                pos = int(t[-1])
+                it += 1
+        offsets.append(len(nb))
+    return np.asarray(offsets, np.int64), np.asarray(nb, np.int32)
+
+
 def _fast_rows_restated(orc, seed, src, dst, p, col_lo, col_hi):
+    """p < 2^-13: a warp per row, engines stream(row * 32 + lane), gap = 1 + floor(log(u) / log(1 - p)) in double."""
     import math
 
     inv = 1.0 / math.log1p(-p) if p < 1 else -0.0
@@ -162,13 +205,24 @@ def _fast_rows_restated(orc, seed, src, dst, p, col_lo, col_hi):
     return np.asarray(offsets, np.int64), np.asarray(nb, np.int32)
 
 
-def test_fast_generator_matches_its_restatement(sp, orc):
-    for (s, d, p, lo, hi, il) in [(40, 700, 0.1, 0, 700, (1337,)), (25, 3000, 0.02, 0, 3000, (7, 9)), (30, 500, 0.75, 100, 320, (5,)),
-                                  (9, 100, 1.0, 0, 100, (1,)), (6, 40000, 0.001, 0, 40000, (3,))]:
+def test_fast_generator_matches_its_restatement(sp, orc, monkeypatch):
+    cases = [(40, 700, 0.1, 0, 700, (1337,)), (25, 30000, 0.02, 0, 30000, (7, 9)), (30, 5000, 0.75, 1000, 3200, (5,)),
+             (9, 2100, 1.0, 0, 2100, (1,)), (6, 400000, 0.001, 0, 400000, (3,)), (12, 20000, 0.1, 9000, 17000, (8,)),
+             (5, 300000, 0.00013, 100000, 290000, (2,))]
+    for (s, d, p, lo, hi, il) in cases:
         r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
-        off, nb = _fast_rows_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
+        off, nb = _fast_tiles_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
         assert np.array_equal(r["offsets"], off), (s, d, p)
         assert np.array_equal(r["neighbors"], nb), (s, d, p)
+    for (s, d, p, lo, hi, il) in [(6, 400000, 0.0001, 0, 400000, (3,)), (4, 1000000, 0.00002, 200000, 900000, (4,))]:  # the log path
+        r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
+        off, nb = _fast_rows_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
+        assert np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (s, d, p)
+    monkeypatch.setenv("SPICE_GEN_FAST_LOG_PATH", "1")  # the log path at ordinary p
+    for (s, d, p, lo, hi, il) in [(40, 700, 0.1, 0, 700, (1337,)), (30, 500, 0.75, 100, 320, (5,)), (9, 100, 1.0, 0, 100, (1,))]:
+        r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
+        off, nb = _fast_rows_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
+        assert np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (s, d, p)
 
 
 def test_fast_generator_distribution_and_structure(sp):
