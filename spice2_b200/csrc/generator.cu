@@ -1302,9 +1302,9 @@ __global__ void __launch_bounds__(256) fp_fast_rows(fast_args a) {
 }
 
 // ---- tiles ----
-constexpr int kTileWarps = 8;    // units per tile = warps per CTA
+constexpr int kTileWarps = 8;    // units per tile = warps per CTA (4 measures the same)
 constexpr int kUnitCap   = 1536; // entries a warp can hold: the mean is < 1024, sigma < 32
-constexpr int kTabSmem   = 8192; // table entries kept in shared memory (p >= 0.0027); larger tables are read through L1
+constexpr int kTabSmem   = 4096; // table entries (pairs) kept in shared memory (p >= 0.0054); larger tables are read through L1
 
 struct tile_args {
 	long long src, dst, col_lo, col_hi;
@@ -1314,8 +1314,8 @@ struct tile_args {
 	long long b_lo, nb_local;   // blocks that overlap [col_lo, col_hi)
 	long long units, tiles;
 	float s;                    // -1 / log2(1 - p): gaps per halving of u
-	int K;                      // tab[1 .. K], tab[K] = 0 (tab[0] unused)
-	unsigned const* tab;
+	int K;                      // T[1 .. K], T[K] = 0, T[0] = 2^32 - 1 (never read as a threshold)
+	uint2 const* tab;           // [K] (T[c], T[c + 1])
 	unsigned long long* desc;   // [tiles] status << 62 | count
 	unsigned long long* ticket;
 	long long* offsets;
@@ -1324,32 +1324,69 @@ struct tile_args {
 	int* flags;                 // 1: a unit did not fit kUnitCap, 2: neighbors too small
 };
 
-__device__ __forceinline__ int gap_of(unsigned u, unsigned const* __restrict__ tab, int K, float s) {
-	int c = static_cast<int>((32.0f - __log2f(static_cast<float>(u) + 1.0f)) * s);
-	c     = min(max(c, 0), K - 1);
-	while (tab[c + 1] > u)
-		c++;
-	while (c > 0 && tab[c] <= u)
-		c--;
-	return c + 1;
+// #{k >= 1 : u < T[k]} from an estimate that is wrong once in ~1e5 draws
+template <bool kSmemTab>
+__device__ __forceinline__ uint2 tab_at(uint2 const* tab, unsigned tab_s, int c) {
+	if constexpr (kSmemTab) {
+		uint2 t;
+		asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(tab_s + 8u * static_cast<unsigned>(c)));
+		return t;
+	} else
+		return __ldg(tab + c);
 }
 
+template <bool kSmemTab>
+__device__ __noinline__ int gap_fix(unsigned u, uint2 const* tab, unsigned tab_s, int K, int c) {
+	while (c + 1 < K && tab_at<kSmemTab>(tab, tab_s, c).y > u)
+		c++;
+	while (c > 0 && tab_at<kSmemTab>(tab, tab_s, c).x <= u)
+		c--;
+	return c;
+}
+
+// the estimate floor((32 - log2(u + 1)) s) and whether the table confirms it
+template <bool kSmemTab>
+__device__ __forceinline__ int gap_est(unsigned u, uint2 const* tab, unsigned tab_s, int K, float neg_s, float s32, bool& ok) {
+	float lg;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(__uint2float_rn(u) + 1.0f)); // the argument is in [1, 2^32]
+	int const c   = min(__float2int_rz(fmaf(lg, neg_s, s32)), K - 1);
+	uint2 const t = tab_at<kSmemTab>(tab, tab_s, c);
+	ok            = ok && t.y <= u && (t.x > u || c == 0);
+	return c;
+}
+
+__device__ __forceinline__ int scan_up(int v) { // inclusive warp scan: shfl.up hands back whether the source lane exists
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1)
+		asm("{ .reg .s32 r; .reg .pred p; shfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, r; }" : "+r"(v) : "r"(off));
+	return v;
+}
+
+// Entry: how a warp keeps a block-relative target until its place in the output is known (u16 while B <= 65536, p >= 2^-7)
+template <bool kSmemTab, class Entry>
 __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
-	extern __shared__ __align__(16) int smem[];
+	extern __shared__ __align__(16) unsigned char smem[];
 	__shared__ int wcount[kTileWarps];
 	__shared__ long long s_tile, s_excl;
 	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int* const buf = smem + warp * kUnitCap;
-	unsigned const* tab = a.tab;
-	if (a.K + 1 <= kTabSmem) {
-		unsigned* t = reinterpret_cast<unsigned*>(smem + kTileWarps * kUnitCap);
-		for (int i = threadIdx.x; i <= a.K; i += blockDim.x)
+	Entry* const buf  = reinterpret_cast<Entry*>(smem) + warp * kUnitCap;
+	Entry* const buf4 = buf + lane * 4;
+	uint2 const* tab;
+	if constexpr (kSmemTab) {
+		uint2* const t = reinterpret_cast<uint2*>(smem + sizeof(Entry) * kTileWarps * kUnitCap);
+		for (int i = threadIdx.x; i < a.K; i += blockDim.x)
 			t[i] = a.tab[i];
 		tab = t;
-	}
+	} else
+		tab = a.tab;
+	unsigned const tab_s = kSmemTab ? static_cast<unsigned>(__cvta_generic_to_shared(tab)) : 0u;
 	util::seed_seq const seed(UInt128{a.seed_lo, a.seed_hi});
 	long long const B = 1ll << a.block_log2;
+	float const neg_s = -a.s, s32 = 32.0f * a.s;
+	int const K = a.K;
 	for (;;) {
+		// A ticket is claimed only when the CTA is free to work on it (measured: claiming the next one while the current tile is
+		// in its look-back hides the round trip but makes later tiles wait for a tile nobody generates yet: 2.3 -> 6.6 ms at 1e5^2)
 		__syncthreads(); // the table is loaded; the previous tile is done with s_tile / s_excl / wcount
 		if (threadIdx.x == 0)
 			s_tile = static_cast<long long>(atomicAdd(a.ticket, 1ull));
@@ -1367,26 +1404,30 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 			int const bsize       = static_cast<int>(min(B, a.dst - blk0));
 			int const lo_rel      = static_cast<int>(max(a.col_lo - blk0, 0ll));
 			int const hi_rel      = static_cast<int>(min(a.col_hi - blk0, static_cast<long long>(bsize)));
-			int const add         = static_cast<int>(blk0 - a.col_lo); // block-relative target -> local column
 			UInt128 const st      = seed.stream(static_cast<UInt>(r * a.nblocks + b) * 32 + static_cast<UInt>(lane)).seed();
 			unsigned long long s0 = st.lo, s1 = st.hi;
-			int pos               = -1; // the last target drawn so far
-			while (pos < hi_rel - 1) {
+			int pos               = -1; // the last target drawn so far, relative to the block
+			int const lo = lo_rel, hi = hi_rel;
+			while (pos < hi - 1) {
 				unsigned long long const x0 = s0 + s1;
 				xoro_advance(s0, s1);
 				unsigned long long const x1 = s0 + s1;
 				xoro_advance(s0, s1);
-				int const l1 = gap_of(static_cast<unsigned>(x0 >> 32), tab, a.K, a.s);
-				int const l2 = l1 + gap_of(static_cast<unsigned>(x0), tab, a.K, a.s);
-				int const l3 = l2 + gap_of(static_cast<unsigned>(x1 >> 32), tab, a.K, a.s);
-				int const l4 = l3 + gap_of(static_cast<unsigned>(x1), tab, a.K, a.s);
-				int incl     = l4;
-#pragma unroll
-				for (int off = 1; off < 32; off <<= 1) {
-					int const o = __shfl_up_sync(0xffffffffu, incl, off);
-					if (lane >= off)
-						incl += o;
+				unsigned const u0 = static_cast<unsigned>(x0 >> 32), u1 = static_cast<unsigned>(x0), u2 = static_cast<unsigned>(x1 >> 32),
+				               u3 = static_cast<unsigned>(x1);
+				bool ok = true;
+				int c0  = gap_est<kSmemTab>(u0, tab, tab_s, K, neg_s, s32, ok);
+				int c1  = gap_est<kSmemTab>(u1, tab, tab_s, K, neg_s, s32, ok);
+				int c2  = gap_est<kSmemTab>(u2, tab, tab_s, K, neg_s, s32, ok);
+				int c3  = gap_est<kSmemTab>(u3, tab, tab_s, K, neg_s, s32, ok);
+				if (!ok) [[unlikely]] {
+					c0 = gap_fix<kSmemTab>(u0, tab, tab_s, K, c0);
+					c1 = gap_fix<kSmemTab>(u1, tab, tab_s, K, c1);
+					c2 = gap_fix<kSmemTab>(u2, tab, tab_s, K, c2);
+					c3 = gap_fix<kSmemTab>(u3, tab, tab_s, K, c3);
 				}
+				int const l1 = c0 + 1, l2 = l1 + c1 + 1, l3 = l2 + c2 + 1, l4 = l3 + c3 + 1;
+				int const incl = scan_up(l4);
 				int const tot  = __shfl_sync(0xffffffffu, incl, 31);
 				int const base = pos + incl - l4;
 				int const t0 = base + l1, t1 = base + l2, t2 = base + l3, t3 = base + l4;
@@ -1395,37 +1436,33 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 						atomicOr(a.flags, 1);
 					break;
 				}
-				if (pos + 1 >= lo_rel && pos + tot < hi_rel) { // every target of the iteration is kept
-					int* const at = buf + n + lane * 4;
+				if (pos + 1 >= lo && pos + tot < hi) { // every target of the iteration is kept
 					if ((n & 3) == 0) {
-						*reinterpret_cast<int4*>(at) = make_int4(t0 + add, t1 + add, t2 + add, t3 + add);
+						if constexpr (sizeof(Entry) == 2)
+							*reinterpret_cast<uint2*>(buf4 + n) = make_uint2(static_cast<unsigned>(t0) | static_cast<unsigned>(t1) << 16,
+							                                                 static_cast<unsigned>(t2) | static_cast<unsigned>(t3) << 16);
+						else
+							*reinterpret_cast<int4*>(buf4 + n) = make_int4(t0, t1, t2, t3);
 					} else { // only behind a first iteration that dropped targets in front of this rank's columns
-						at[0] = t0 + add;
-						at[1] = t1 + add;
-						at[2] = t2 + add;
-						at[3] = t3 + add;
+						buf4[n]     = static_cast<Entry>(t0);
+						buf4[n + 1] = static_cast<Entry>(t1);
+						buf4[n + 2] = static_cast<Entry>(t2);
+						buf4[n + 3] = static_cast<Entry>(t3);
 					}
 					n += 128;
 				} else {
-					bool const k0 = t0 >= lo_rel && t0 < hi_rel, k1 = t1 >= lo_rel && t1 < hi_rel, k2 = t2 >= lo_rel && t2 < hi_rel,
-					           k3      = t3 >= lo_rel && t3 < hi_rel;
+					bool const k0 = t0 >= lo && t0 < hi, k1 = t1 >= lo && t1 < hi, k2 = t2 >= lo && t2 < hi, k3 = t3 >= lo && t3 < hi;
 					int const mine = k0 + k1 + k2 + k3;
-					int cs         = mine;
-#pragma unroll
-					for (int off = 1; off < 32; off <<= 1) {
-						int const o = __shfl_up_sync(0xffffffffu, cs, off);
-						if (lane >= off)
-							cs += o;
-					}
+					int const cs   = scan_up(mine);
 					int at = n + cs - mine;
 					if (k0)
-						buf[at++] = t0 + add;
+						buf[at++] = static_cast<Entry>(t0);
 					if (k1)
-						buf[at++] = t1 + add;
+						buf[at++] = static_cast<Entry>(t1);
 					if (k2)
-						buf[at++] = t2 + add;
+						buf[at++] = static_cast<Entry>(t2);
 					if (k3)
-						buf[at++] = t3 + add;
+						buf[at++] = static_cast<Entry>(t3);
 					n += __shfl_sync(0xffffffffu, cs, 31);
 				}
 				pos += tot;
@@ -1434,6 +1471,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 		if (lane == 0)
 			wcount[warp] = n;
 		__syncthreads();
+
 		if (warp == 0) {
 			int const c   = lane < kTileWarps ? wcount[lane] : 0;
 			long long tot = c;
@@ -1477,8 +1515,11 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 				if (lane == 0)
 					atomicOr(a.flags, 2);
 			} else {
-				for (int i = lane; i < n; i += 32)
-					a.neighbors[base + i] = buf[i];
+				int const add    = static_cast<int>((b << a.block_log2) - a.col_lo); // block-relative target -> local column
+				int* dst         = a.neighbors + base + lane;
+				Entry const* src = buf + lane;
+				for (int i = lane; i < n; i += 32, dst += 32, src += 32)
+					*dst = static_cast<int>(*src) + add;
 			}
 			if (lane == 0) {
 				if (b == a.b_lo)
@@ -1522,23 +1563,30 @@ int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, doubl
 	a.tiles    = (a.units + kTileWarps - 1) / kTileWarps;
 	double const mean = static_cast<double>(src) * static_cast<double>(col_hi - col_lo) * p;
 	a.cap             = static_cast<long long>(mean + 10.0 * std::sqrt(mean * (1 - p) + 1.0)) + 1024;
-	unsigned* d_tab = nullptr;
-	int* d_flags    = nullptr;
-	GEN_CUDA(S.alloc(&d_tab, tab.size()));
+	std::vector<uint2> tab2(static_cast<size_t>(a.K));
+	for (int c = 0; c < a.K; c++)
+		tab2[static_cast<size_t>(c)] = make_uint2(tab[static_cast<size_t>(c)], tab[static_cast<size_t>(c) + 1]);
+	uint2* d_tab = nullptr;
+	int* d_flags = nullptr;
+	GEN_CUDA(S.alloc(&d_tab, tab2.size()));
 	GEN_CUDA(S.alloc(&a.desc, static_cast<size_t>(a.tiles) + 1));
 	GEN_CUDA(S.alloc(&d_flags, 4));
 	GEN_CUDA(cudaMalloc(&out->offsets, sizeof(long long) * static_cast<size_t>(src + 1)));
-	GEN_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(unsigned) * tab.size(), cudaMemcpyHostToDevice, stream));
+	GEN_CUDA(cudaMemcpyAsync(d_tab, tab2.data(), sizeof(uint2) * tab2.size(), cudaMemcpyHostToDevice, stream));
 	a.tab     = d_tab;
 	a.ticket  = a.desc + a.tiles;
 	a.offsets = out->offsets;
 	a.flags   = d_flags;
-	size_t const smem = sizeof(int) * static_cast<size_t>(kTileWarps * kUnitCap + (a.K + 1 <= kTabSmem ? a.K + 1 : 0));
-	GEN_CUDA(cudaFuncSetAttribute(fp_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	bool const smem_tab = a.K <= kTabSmem;
+	bool const narrow   = a.block_log2 <= 16;
+	auto const kernel   = smem_tab ? (narrow ? fp_fast_tiles<true, unsigned short> : fp_fast_tiles<true, int>)
+	                               : (narrow ? fp_fast_tiles<false, unsigned short> : fp_fast_tiles<false, int>);
+	size_t const smem   = (narrow ? 2 : 4) * static_cast<size_t>(kTileWarps * kUnitCap) + (smem_tab ? sizeof(uint2) * static_cast<size_t>(a.K) : 0);
+	GEN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 	int dev = 0, sms = 148, per_sm = 1;
 	GEN_CUDA(cudaGetDevice(&dev));
 	GEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	GEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fp_fast_tiles, kTileWarps * 32, smem));
+	GEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTileWarps * 32, smem));
 	int const grid = static_cast<int>(std::min<long long>(a.tiles, static_cast<long long>(sms) * std::max(per_sm, 1)));
 	for (int attempt = 0; attempt < 2; attempt++) {
 		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(a.cap + 8)));
@@ -1546,7 +1594,7 @@ int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, doubl
 		GEN_CUDA(cudaEventRecord(ev0, stream));
 		GEN_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (static_cast<size_t>(a.tiles) + 1), stream));
 		GEN_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream));
-		fp_fast_tiles<<<grid, kTileWarps * 32, smem, stream>>>(a);
+		kernel<<<grid, kTileWarps * 32, smem, stream>>>(a);
 		GEN_CUDA(cudaGetLastError());
 		GEN_CUDA(cudaEventRecord(ev1, stream));
 		long long edges = 0;

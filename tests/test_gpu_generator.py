@@ -208,7 +208,7 @@ def _fast_rows_restated(orc, seed, src, dst, p, col_lo, col_hi):
 def test_fast_generator_matches_its_restatement(sp, orc, monkeypatch):
     cases = [(40, 700, 0.1, 0, 700, (1337,)), (25, 30000, 0.02, 0, 30000, (7, 9)), (30, 5000, 0.75, 1000, 3200, (5,)),
              (9, 2100, 1.0, 0, 2100, (1,)), (6, 400000, 0.001, 0, 400000, (3,)), (12, 20000, 0.1, 9000, 17000, (8,)),
-             (5, 300000, 0.00013, 100000, 290000, (2,))]
+             (5, 300000, 0.00013, 100000, 290000, (2,)), (10, 200000, 0.006, 50000, 200000, (6,))]
     for (s, d, p, lo, hi, il) in cases:
         r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
         off, nb = _fast_tiles_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
