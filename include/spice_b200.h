@@ -100,6 +100,15 @@ SPICE_API int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, 
 typedef int64_t (*spice_host_update_fn)(void* user, float dt, uint64_t seed_lo, uint64_t seed_hi, uint64_t rng_offset,
                                         int32_t* ids_out, int64_t capacity, int64_t* draws_out);
 SPICE_API int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn update, void* user, int* pop_out);
+/* Not in the reference (it has one address space): the target ranges of the NEXT population added with
+ * spice_add_population, bounds[world + 1], bounds[0] = 0, bounds[world] = size, non-decreasing; rank r owns neurons
+ * [bounds[r], bounds[r + 1]) and all their incoming synapses.  Every rank must pass the same bounds.  NULL (the default)
+ * = equal widths, which balances fixed_probability.  For non-uniform topologies (adj_list, user-defined Topology) pass the
+ * ranges spice_balance_ranges computes from the targets' in-degrees: static synapse-count load balancing. */
+SPICE_API int spice_set_next_partition(spice_ctx* ctx, int64_t const* bounds);
+/* bounds[world + 1] such that every range holds about the same sum of weight[i] + 1 (weight = in-degree of target i summed
+ * over the connections into the population; + 1 = the neuron's own update).  Host arithmetic, no device needed. */
+SPICE_API int spice_balance_ranges(int64_t const* weight, int64_t n, int world, int64_t* bounds);
 /* NeuronPopulation::size()                                           (neuron_population.h:114) */
 SPICE_API int64_t spice_population_size(spice_ctx const* ctx, int pop);
 /* the contiguous range of the population this rank owns */

@@ -18,7 +18,7 @@ import numpy as np
 
 from .build import build as _build
 
-__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "generate_fixed_probability", "generate_adj_list", "Adjacency", "seed_seq", "fnv1a64",
+__all__ = ["snn", "fixed_probability", "adj_list", "SpiceError", "lib", "balance_ranges", "generate_fixed_probability", "generate_adj_list", "Adjacency", "seed_seq", "fnv1a64",
            "MODE_DETERMINISTIC", "MODE_FAST"]
 
 MODE_DETERMINISTIC, MODE_FAST = 0, 1
@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
             "spice_add_population": (i32, [vp, vp, i64, vp, C.POINTER(i32)]),
             "spice_add_host_population": (i32, [vp, i64, vp, vp, C.POINTER(i32)]),
             "spice_population_size": (i64, [vp, i32]),
+            "spice_set_next_partition": (i32, [vp, vp]),
+            "spice_balance_ranges": (i32, [vp, i64, i32, vp]),
             "spice_population_range": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
             "spice_connect_fixed_probability": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
             "spice_connect_fixed_probability_fast": (i32, [vp, vp, i32, i32, C.c_double, C.c_float, vp, C.POINTER(i32)]),
@@ -140,8 +142,10 @@ class fixed_probability:
 class adj_list:
     """spice::adj_list (spice/include/spice/topology.h:37-46)."""
 
-    def __init__(self):
-        self.src, self.dst = [], []
+    def __init__(self, src=None, dst=None):
+        """Empty (filled with connect(), as the reference's), or from two index arrays."""
+        self.src = [] if src is None else list(np.asarray(src).tolist())
+        self.dst = [] if dst is None else list(np.asarray(dst).tolist())
 
     def connect(self, src: int, dst: int):
         self.src.append(src)
@@ -234,12 +238,16 @@ class snn:
     def set_stream(self, cuda_stream: int):
         self._check(lib().spice_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
-    def add_population(self, model: str, size: int, **params) -> Population:
+    def add_population(self, model: str, size: int, bounds=None, **params) -> Population:
+        """bounds (optional, world + 1 entries): the ranks' target ranges instead of equal widths (balance_ranges())."""
         ops = lib().spice_builtin_neuron(model.encode())
         if not ops:
             raise SpiceError(3, f"unknown neuron model {model!r}")
         functor = NEURON_MODELS[model][0](**params)
         idx = C.c_int()
+        if bounds is not None:
+            b = np.ascontiguousarray(bounds, np.int64)
+            self._check(lib().spice_set_next_partition(self._h, _ptr(b)))
         self._check(lib().spice_add_population(self._h, ops, size, functor, C.byref(idx)))
         pop = Population(self, idx.value, model, size)
         self.populations.append(pop)
@@ -450,6 +458,16 @@ def generate_adj_list(edges_src, edges_dst, src_count, dst_count, device=0, col_
         return out
     finally:
         L.spice_adjacency_destroy(h)
+
+
+def balance_ranges(in_degree, world: int) -> np.ndarray:
+    """Static synapse-count load balancing: target ranges holding about equal sums of in_degree + 1."""
+    w = np.ascontiguousarray(in_degree, np.int64)
+    out = np.zeros(world + 1, np.int64)
+    rc = lib().spice_balance_ranges(_ptr(w), len(w), world, _ptr(out))
+    if rc != 0:
+        raise SpiceError(rc, "spice_balance_ranges: invalid argument")
+    return out
 
 
 def generate_fixed_probability(src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, copy=True, fast=False):

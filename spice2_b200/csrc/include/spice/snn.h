@@ -163,6 +163,15 @@ public:
 		return static_cast<detail::neuron_population<Neur>*>(_neurons.back().get());
 	}
 
+	// Not in the reference (one address space): the population's target ranges over the ranks, bounds[world + 1], instead of
+	// equal widths — e.g. the in-degree-balanced ranges of spice_balance_ranges for a non-uniform topology.
+	template <Neuron Neur>
+	detail::neuron_population<Neur>* add_population(Int const size, Neur neur, std::span<Int const> bounds) {
+		static_assert(sizeof(Int) == sizeof(int64_t));
+		detail::check(_ctx.get(), spice_set_next_partition(_ctx.get(), reinterpret_cast<int64_t const*>(bounds.data())));
+		return add_population<Neur>(size, std::move(neur));
+	}
+
 	template <class Syn, Neuron SrcNeur, StatefulNeuron DstNeur>
 	requires Synapse<Syn, SrcNeur, DstNeur>
 	void connect(detail::neuron_population<SrcNeur>* source, detail::neuron_population<DstNeur>* target, Topology& c,

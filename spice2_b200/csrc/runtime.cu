@@ -410,6 +410,7 @@ struct population {
 	long long ring_ids_off = 0, ring_cnt_off = 0; // byte offsets in the exchange region
 	std::vector<int> incoming;                     // connection indices, connect() order
 	std::vector<long long> seg_lo;                 // [world]
+	std::vector<long long> bounds;                 // [world + 1] rank r owns [bounds[r], bounds[r + 1]) (equal widths unless set)
 };
 
 struct connection {
@@ -458,6 +459,7 @@ struct host_spikes {
 }
 
 struct spice_ctx {
+	std::vector<long long> next_bounds; // spice_set_next_partition: the target ranges of the next population added
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream     = false;
@@ -916,7 +918,7 @@ int finalize(spice_ctx* ctx) {
 			d.ring_cap   = std::max<long long>(src.size, 1);
 			d.cnt_stride = flat ? 1 : ctx->world;
 			for (int r = 0; r < ctx->world; r++)
-				d.seg_lo[r] = static_cast<std::int32_t>(src.size * r / ctx->world);
+				d.seg_lo[r] = static_cast<std::int32_t>(src.bounds[static_cast<size_t>(r)]);
 			d.packed      = c.packed;
 			d.run_ptr     = c.run_ptr;
 			d.neighbors   = c.neighbors;
@@ -961,7 +963,7 @@ int finalize(spice_ctx* ctx) {
 		h_cap[pi] = std::max<long long>(p.size, 1);
 		p.seg_lo.resize(ctx->world);
 		for (int r = 0; r < ctx->world; r++) {
-			p.seg_lo[r]                    = p.size * r / ctx->world;
+			p.seg_lo[r]                    = p.bounds[static_cast<size_t>(r)];
 			h_seg[pi * ctx->world + r]     = p.seg_lo[r];
 		}
 		p.rng_offset = rng_offset;
@@ -1291,7 +1293,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 				sa.ring_ids = xptr<std::int32_t>(ctx->xbase, src.ring_ids_off) + slot * std::max<long long>(src.size, 1);
 				sa.ring_cnt = xptr<std::uint32_t>(ctx->xbase, src.ring_cnt_off) + slot * ctx->world;
 				for (int r = 0; r < ctx->world; r++)
-					sa.seg_lo[r] = src.size * r / ctx->world;
+					sa.seg_lo[r] = src.bounds[static_cast<size_t>(r)];
 				sa.world       = ctx->world;
 				sa.n_src       = src.size;
 				sa.n_dst       = dst.hi - dst.lo;
@@ -1733,6 +1735,7 @@ int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn
 	p.size        = size;
 	p.lo          = 0;
 	p.hi          = size;
+	p.bounds      = {0, size};
 	p.stride      = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(size, 1)), 32));
 	p.host_update = update;
 	p.host_user   = user;
@@ -1750,8 +1753,18 @@ int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t si
 	population p;
 	p.ops    = ops;
 	p.size   = size;
-	p.lo     = size * ctx->rank / ctx->world;
-	p.hi     = size * (ctx->rank + 1) / ctx->world;
+	if (!ctx->next_bounds.empty()) { // spice_set_next_partition: in-degree-balanced (or any other) target ranges
+		PRE(ctx, static_cast<int>(ctx->next_bounds.size()) == ctx->world + 1 && ctx->next_bounds.front() == 0 && ctx->next_bounds.back() == size &&
+		             std::is_sorted(ctx->next_bounds.begin(), ctx->next_bounds.end()));
+		p.bounds = std::move(ctx->next_bounds);
+		ctx->next_bounds.clear();
+	} else {
+		p.bounds.resize(static_cast<size_t>(ctx->world) + 1);
+		for (int r = 0; r <= ctx->world; r++)
+			p.bounds[static_cast<size_t>(r)] = size * r / ctx->world;
+	}
+	p.lo     = p.bounds[static_cast<size_t>(ctx->rank)];
+	p.hi     = p.bounds[static_cast<size_t>(ctx->rank) + 1];
 	p.stride = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(p.hi - p.lo, 1)), 32));
 	std::vector<unsigned char> zero(std::max<std::uint32_t>(ops->functor_bytes, 1), 0);
 	unsigned char const* f = functor ? static_cast<unsigned char const*>(functor) : zero.data();
@@ -1776,6 +1789,38 @@ int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t si
 	ctx->pops.push_back(std::move(p));
 	if (pop_out)
 		*pop_out = static_cast<int>(ctx->pops.size()) - 1;
+	return SPICE_OK;
+}
+
+int spice_set_next_partition(spice_ctx* ctx, int64_t const* bounds) {
+	ctx->next_bounds.clear();
+	if (bounds)
+		ctx->next_bounds.assign(bounds, bounds + ctx->world + 1);
+	return SPICE_OK;
+}
+
+int spice_balance_ranges(int64_t const* weight, int64_t n, int world, int64_t* bounds) {
+	if (n < 0 || world < 1 || !bounds || (n > 0 && !weight))
+		return SPICE_ERR_PRECONDITION;
+	// static synapse-count load balancing: rank r's range ends where the running sum of the in-degrees first reaches
+	// (r + 1) / world of the total (prefix sum of the in-degree histogram); every neuron also counts as one
+	// unit of update work, which keeps ranges of unconnected neurons from collapsing onto one rank
+	long double total = 0;
+	for (int64_t i = 0; i < n; i++) {
+		if (weight[i] < 0)
+			return SPICE_ERR_PRECONDITION;
+		total += static_cast<long double>(weight[i]) + 1;
+	}
+	bounds[0]        = 0;
+	long double run  = 0;
+	int64_t i        = 0;
+	for (int r = 1; r < world; r++) {
+		long double const want = total * r / world;
+		while (i < n && run + (static_cast<long double>(weight[i]) + 1) / 2 < want)
+			run += static_cast<long double>(weight[i++]) + 1;
+		bounds[r] = i;
+	}
+	bounds[world] = n;
 	return SPICE_OK;
 }
 

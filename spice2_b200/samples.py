@@ -7,16 +7,18 @@ import numpy as np
 from . import fixed_probability, snn
 
 
-def brunel(N=20000, p=0.1, w_exc=None, w_inh=None, dt=1e-4, delay=15e-4, seed=(1337,), plastic=False, fast_topology=False, **ctx):
+def brunel(N=20000, p=0.1, w_exc=None, w_inh=None, dt=1e-4, delay=15e-4, seed=(1337,), plastic=False, fast_topology=False, partition=None, **ctx):
     """P (poisson, N/2), E (lif, 4N/10), I (lif, N/10); P->E, P->I, E->E, E->I, I->E, I->I.
     plastic=True: E->E carries the STDP synapse of samples/brunel+.cpp:59-99,114.
-    fast_topology=True: the connections are drawn by the counter-based generator (not the reference's matrices)."""
+    fast_topology=True: the connections are drawn by the counter-based generator (not the reference's matrices).
+    partition: size -> the ranks' target ranges (world + 1 bounds) instead of equal widths."""
     w_exc = np.float32(2.0 / N) if w_exc is None else np.float32(w_exc)
     w_inh = np.float32(-10.0 / N) if w_inh is None else np.float32(w_inh)
     net = snn(dt, delay, seed, **ctx)
-    P = net.add_population("brunel.poisson", N // 2)
-    E = net.add_population("brunel.lif", N * 4 // 10)
-    I = net.add_population("brunel.lif", N // 10)
+    bounds = (lambda n: None) if partition is None else partition
+    P = net.add_population("brunel.poisson", N // 2, bounds=bounds(N // 2))
+    E = net.add_population("brunel.lif", N * 4 // 10, bounds=bounds(N * 4 // 10))
+    I = net.add_population("brunel.lif", N // 10, bounds=bounds(N // 10))
     for (s, d, w) in ((P, E, w_exc), (P, I, w_exc), (E, E, w_exc), (E, I, w_exc), (I, E, w_inh), (I, I, w_inh)):
         if plastic and s is E and d is E:
             net.connect("brunel+.plastic", s, d, fixed_probability(p, fast_topology), delay)

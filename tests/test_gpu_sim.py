@@ -185,6 +185,89 @@ def test_two_ranks_one_device(sp, orc):
     assert sum(net.stats()["synaptic_events"] for net, _ in nets) == onet.events()
 
 
+def test_two_ranks_uneven_target_ranges(sp, orc):
+    """spice_set_next_partition: rank 0 owns 30 % of every population, rank 1 the rest (the ranges a non-uniform topology's
+    in-degree balance would produce): still the reference's raster and state, bit for bit."""
+    from spice2_b200.samples import brunel
+
+    kw = dict(N=3000, p=0.1, w_exc=np.float32(2.0 / 300), w_inh=np.float32(-10.0 / 300))
+    onet, opops = brunel_oracle(orc, **kw)
+    world = 2
+    part = lambda n: [0, n * 3 // 10, n]
+    nets = [brunel(rank=r, world=world, partition=part, **kw) for r in range(world)]
+    assert nets[0][1][1].range() == (0, 360) and nets[1][1][1].range() == (360, 1200)
+    for net, _ in nets:
+        net.finalize()
+    handles = [net.peer_handle() for net, _ in nets]
+    for net, _ in nets:
+        net.set_peers(handles)
+    for chunk in range(8):
+        for net, _ in nets:
+            net.step(15)
+        for _ in range(15):
+            onet.step()
+        for net, pops in nets:
+            for p, op in zip(pops, opops):
+                assert np.array_equal(p.spikes(0), onet.spikes(op, 0))
+    for pi in (1, 2):
+        got = np.concatenate([pops[pi].get_neurons() for _, pops in nets])
+        assert np.array_equal(got, onet.neurons(pi))
+    for _ in range(14):
+        onet.step()
+    assert sum(net.stats()["synaptic_events"] for net, _ in nets) == onet.events()
+    with pytest.raises(sp.SpiceError, match="Assertion failed"):
+        brunel(rank=0, world=2, partition=lambda n: [0, n + 1, n], **kw)
+
+
+def test_in_degree_balanced_ranges_on_a_skewed_adj_list(sp):
+    """Static synapse-count load balancing (SURVEY 8e): an adj_list network whose in-degrees fall off like 1 / (1 + i / 40);
+    spice_balance_ranges cuts the targets where the prefix sum of the in-degrees crosses r / world of the total, the two
+    ranks then hold the same number of synapses within 5 % (equal widths: 4 : 1) and reproduce the one-rank run bit for bit."""
+    rng = np.random.default_rng(17)
+    n_src, n_dst = 1500, 2000
+    deg = np.maximum((600.0 / (1.0 + np.arange(n_dst) / 40.0)).astype(np.int64), 1)
+    dst = np.repeat(np.arange(n_dst, dtype=np.int32), deg)
+    src = np.concatenate([rng.choice(n_src, d, replace=False) for d in deg]).astype(np.int32)
+    rec_src = rng.integers(0, n_dst, 40000).astype(np.int32)
+    rec_dst = np.minimum((rng.random(40000) ** 3 * n_dst).astype(np.int32), n_dst - 1)
+    in_deg = np.bincount(dst, minlength=n_dst) + np.bincount(rec_dst, minlength=n_dst)
+    bounds = sp.balance_ranges(in_deg, 2)
+    cut = int(bounds[1])
+    assert bounds[0] == 0 and bounds[2] == n_dst and 0 < cut < n_dst // 2
+    share = in_deg[:cut].sum() / in_deg.sum()
+    assert abs(share - 0.5) < 0.05 and in_deg[: n_dst // 2].sum() / in_deg.sum() > 0.75
+
+    def build(rank, world):
+        net = sp.snn(1e-4, 5e-4, (3,), rank=rank, world=world)
+        P = net.add_population("brunel.poisson", n_src)
+        E = net.add_population("brunel.lif", n_dst, bounds=None if world == 1 else bounds)
+        net.connect("brunel.fixed_weight", P, E, sp.adj_list(src, dst), 5e-4, weight=np.float32(0.004))
+        net.connect("brunel.fixed_weight", E, E, sp.adj_list(rec_src, rec_dst), 3e-4, weight=np.float32(-0.002))
+        return net, (P, E)
+
+    one, one_pops = build(0, 1)
+    nets = [build(r, 2) for r in range(2)]
+    for net, _ in nets:
+        net.finalize()
+    handles = [net.peer_handle() for net, _ in nets]
+    for net, _ in nets:
+        net.set_peers(handles)
+    edges = [sum(net.connection_edges(c) for c in range(2)) for net, _ in nets]
+    assert sum(edges) == len(src) + len(rec_src) and abs(edges[0] / sum(edges) - 0.5) < 0.05
+    total = 0
+    for chunk in range(20):
+        one.step(9)
+        for net, _ in nets:
+            net.step(9)
+        for net, pops in nets:
+            for p, q in zip(pops, one_pops):
+                assert np.array_equal(p.spikes(0), q.spikes(0))
+        total += len(one_pops[1].spikes(0))
+    assert total > 0
+    got = np.concatenate([pops[1].get_neurons() for _, pops in nets])
+    assert np.array_equal(got, one_pops[1].get_neurons())
+
+
 # ---- plastic synapses (samples/brunel+.cpp): lazy event-driven STDP --------------------------------
 # Parity contract (DESIGN.md §2): the plastic path calls libm (expf, pow).  expf is restated
 # bit-exactly, pow(base, n) is evaluated correctly rounded, which glibc's pow is except in rare

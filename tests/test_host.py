@@ -321,3 +321,23 @@ int main() {
     subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", f"-I{inc}", str(src), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_balance_ranges_host_arithmetic(sp):
+    """spice_balance_ranges (static synapse-count load balancing) is host arithmetic: equal in-degrees give
+    equal widths, a skewed histogram is cut where its prefix sum crosses r / world of the total."""
+    assert sp.balance_ranges(np.full(1000, 7), 4).tolist() == [0, 250, 500, 750, 1000]
+    assert sp.balance_ranges(np.zeros(0, np.int64), 3).tolist() == [0, 0, 0, 0]
+    w = np.zeros(100, np.int64)
+    w[:10] = 1000  # ten heavy targets: each is ~1/10 of the work
+    b = sp.balance_ranges(w, 2)
+    assert b.tolist() == [0, 5, 100]
+    rng = np.random.default_rng(1)
+    w = (rng.pareto(1.5, 50000) * 100).astype(np.int64)
+    for world in (2, 3, 8):
+        b = sp.balance_ranges(w, world)
+        assert b[0] == 0 and b[-1] == len(w) and np.all(np.diff(b) >= 0)
+        load = np.add.reduceat(w + 1, b[:-1])
+        assert load.max() <= (w + 1).sum() / world + (w.max() + 1)
+    with pytest.raises(sp.SpiceError):
+        sp.balance_ranges(np.array([1, -2, 3]), 2)
