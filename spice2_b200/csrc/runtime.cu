@@ -447,6 +447,8 @@ struct connection {
 	// fixed_probability connections are generated when the network is finalized, all of them concurrently
 	bool pending_fp  = false;
 	bool fp_fast     = false; // the counter-based generator (gen::generate_fixed_probability_fast): not the reference's matrix
+	bool from_fp     = false; // drawn by fixed_probability (the per-synapse init hook of a sharded network regenerates the whole matrix)
+	std::vector<std::int32_t> adj_src, adj_dst; // world > 1, per-synapse init hook: the adj_list's pairs until the hook has run
 	double fp_p      = 0;
 	UInt128 fp_seed{0, 0};   // the graph's seed (synapse_population.h:31), drawn at connect() time
 	UInt128 init_seed{0, 0}; // the per-synapse init hook's (synapse_population.h:35), drawn right behind it
@@ -1516,7 +1518,56 @@ int init_synapses(spice_ctx* ctx, connection* c) {
 	population const& dst = ctx->pops[c->dst];
 	c->syn_stride         = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(c->edges, 1)), 32));
 	CHECK_CUDA(ctx, cudaMalloc(&c->syn, sizeof(std::uint32_t) * static_cast<size_t>(words) * static_cast<size_t>(c->syn_stride)));
-	if (c->ops->per_synapse_init) {
+	if (c->ops->per_synapse_init && ctx->world > 1) {
+		// The hook walks the WHOLE connection with one engine (synapse_population.h:34-41), so what a synapse receives
+		// depends on every synapse before it: each rank builds the whole adjacency once more (all columns, a temporary),
+		// runs the hook over it on the host and keeps the states of its own columns.  Costs the full matrix in host memory
+		// per rank; hooks are a feature of small networks (samples/ping_pong, sssp).
+		UInt128 const sd = c->init_seed;
+		gen::result full;
+		std::string err;
+		int grc = 0;
+		CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (c->from_fp)
+			grc = c->fp_fast ? gen::generate_fixed_probability_fast(ctx->stream, src.size, dst.size, c->fp_p, c->fp_seed.lo, c->fp_seed.hi, 0, dst.size, &full, &err)
+			                 : gen::generate_fixed_probability(ctx->stream, src.size, dst.size, c->fp_p, c->fp_seed.lo, c->fp_seed.hi, 0, dst.size, 0, &full, &err);
+		else {
+			bool dup = false;
+			grc      = gen::generate_adj_list(ctx->stream, c->adj_src.data(), c->adj_dst.data(), static_cast<long long>(c->adj_src.size()), src.size,
+			                                  dst.size, 0, dst.size, &full, &dup, &err);
+		}
+		std::vector<long long> off(static_cast<size_t>(src.size) + 1);
+		std::vector<std::int32_t> nb(static_cast<size_t>(std::max<long long>(full.edges, 1)));
+		cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+		if (grc == 0) {
+			e1 = cudaMemcpy(off.data(), full.offsets, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost);
+			if (full.edges)
+				e2 = cudaMemcpy(nb.data(), full.neighbors, sizeof(std::int32_t) * static_cast<size_t>(full.edges), cudaMemcpyDeviceToHost);
+		}
+		cudaFree(full.offsets);
+		cudaFree(full.neighbors);
+		if (grc != 0)
+			return fail(ctx, grc == 1 ? SPICE_ERR_PRECONDITION : grc, err);
+		CHECK_CUDA(ctx, e1);
+		CHECK_CUDA(ctx, e2);
+		std::vector<unsigned char> aos(static_cast<size_t>(std::max<long long>(full.edges, 1)) * c->ops->synapse_bytes);
+		c->ops->init_host(c->functor_host.data(), aos.data(), reinterpret_cast<std::int64_t const*>(off.data()), nb.data(), src.size, sd.lo, sd.hi);
+		std::vector<std::uint32_t> soa(static_cast<size_t>(words) * static_cast<size_t>(c->syn_stride), 0);
+		long long mine = 0; // this rank's synapses are the whole matrix's entries with a local target, in the same order
+		for (long long e = 0; e < full.edges; e++) {
+			if (nb[static_cast<size_t>(e)] < dst.lo || nb[static_cast<size_t>(e)] >= dst.hi)
+				continue;
+			if (mine < c->edges)
+				for (int w = 0; w < words; w++)
+					std::memcpy(&soa[static_cast<size_t>(w) * c->syn_stride + mine], aos.data() + e * c->ops->synapse_bytes + 4 * w, 4);
+			mine++;
+		}
+		if (mine != c->edges)
+			return fail(ctx, SPICE_ERR_INTERNAL, "per-synapse init: the regenerated adjacency does not contain this rank's columns");
+		CHECK_CUDA(ctx, cudaMemcpy(c->syn, soa.data(), sizeof(std::uint32_t) * soa.size(), cudaMemcpyHostToDevice));
+		c->adj_src = {};
+		c->adj_dst = {};
+	} else if (c->ops->per_synapse_init) {
 		UInt128 const sd = c->init_seed; // the hook's own engine (synapse_population.h:35), drawn at connect() time
 		std::vector<long long> off(static_cast<size_t>(src.size) + 1);
 		std::vector<std::int32_t> nb(static_cast<size_t>(std::max<long long>(c->edges, 1)));
@@ -1727,15 +1778,17 @@ int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn
 	PRE(ctx, update != nullptr);
 	PRE(ctx, size >= 0 && size < 2147483647);
 	PRE(ctx, !ctx->finalized && "add_population() after the first step is not supported");
-	if (ctx->world > 1)
-		return fail(ctx, SPICE_ERR_UNSUPPORTED, "host-fed populations (per-population update()) are single-rank for now");
 	CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	population p;
 	p.ops         = &host_pop_ops;
 	p.size        = size;
 	p.lo          = 0;
 	p.hi          = size;
-	p.bounds      = {0, size};
+	// More than one rank: a host-fed population is REPLICATED, not partitioned — every rank calls its own copy of the functor
+	// (which must emit the same spikes on every rank, as the reference's single instance would) and fills its own ring, as
+	// if rank 0 owned every neuron: no spike of this population crosses NVLink.
+	p.bounds.assign(static_cast<size_t>(ctx->world) + 1, size);
+	p.bounds[0] = 0;
 	p.stride      = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(size, 1)), 32));
 	p.host_update = update;
 	p.host_user   = user;
@@ -1859,11 +1912,10 @@ int spice_connect_fixed_probability(spice_ctx* ctx, spice_synapse_ops const* ops
 	// synapse_population ctor: _graph(c, seed++) (synapse_population.h:30-31), then the init hook's engine (:35)
 	c.fp_seed = (ctx->seed++).seed();
 	if (c.stateful && ops->per_synapse_init) {
-		if (ctx->world != 1)
-			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
 		c.init_seed = (ctx->seed++).seed();
 	}
 	c.fp_p       = p;
+	c.from_fp    = true;
 	c.pending_fp = true; // generated by finalize(), together with the network's other connections
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
@@ -1904,9 +1956,11 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 		ctx->launches += r.launches;
 	}
 	if (c.stateful && ops->per_synapse_init) {
-		if (ctx->world != 1)
-			return fail(ctx, SPICE_ERR_UNSUPPORTED, "per-synapse init hooks are not supported with more than one rank");
 		c.init_seed = (ctx->seed++).seed();
+		if (ctx->world > 1) { // the hook runs over the whole adjacency (init_synapses)
+			c.adj_src.assign(edges_src, edges_src + n_edges);
+			c.adj_dst.assign(edges_dst, edges_dst + n_edges);
+		}
 	}
 	rc = init_synapses(ctx, &c);
 	if (rc != SPICE_OK)

@@ -37,3 +37,13 @@ def test_facade_spec_program():
         subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
     r = subprocess.run([str(exe)], capture_output=True, timeout=600)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+
+
+def test_multi_rank_spec_program():
+    """tests/cpp/multi_rank_spec.cu: per-synapse init hooks (over fixed_probability and adj_list connections) and a host-fed
+    population on two ranks reproduce the one-rank run: weights, spikes and neuron state."""
+    exe = ROOT / "tests" / "cpp" / "build" / "multi_rank_spec"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
