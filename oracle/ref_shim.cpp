@@ -137,6 +137,45 @@ void ref_exponential(std::uint32_t const* il, int n, int increments, double scal
 		out[i] = d(rng);
 }
 
+// The reference's remaining engines / distributions on one stream (random.h:204-220, 236-330), so the drop-in header's
+// versions can be pinned value for value.  kind: 0 xoroshiro32_128p raw draws, 1 generate_canonical<double> from the 32-bit
+// engine, 2 normal_distribution<double>(a, b), 3 normal_distribution<float>(a, b), 4 binomial_distribution<Int>(a, b),
+// 5 exponential_distribution<float>(a), 6 seed_seq(std::seed_seq{il...})'s seed words.
+void ref_random_sample(int kind, std::uint32_t const* il, int n, int increments, double a, double b, std::int64_t count, double* out) {
+	auto const seed = make_seed(il, n, increments);
+	spice::util::xoroshiro32_128p rng32(seed);
+	spice::util::xoroshiro64_128p rng64(seed);
+	if (kind == 0)
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = static_cast<double>(rng32());
+	else if (kind == 1)
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = spice::util::generate_canonical<double>(rng32);
+	else if (kind == 2) {
+		spice::util::normal_distribution<double> d(a, b);
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = d(rng64);
+	} else if (kind == 3) {
+		spice::util::normal_distribution<float> d(static_cast<float>(a), static_cast<float>(b));
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = d(rng64);
+	} else if (kind == 4) {
+		spice::util::binomial_distribution<std::int64_t> d(static_cast<std::int64_t>(a), b);
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = static_cast<double>(d(rng64));
+	} else if (kind == 5) {
+		spice::util::exponential_distribution<float> d(static_cast<float>(a));
+		for (std::int64_t i = 0; i < count; i++)
+			out[i] = d(rng64);
+	} else if (kind == 6) {
+		spice::util::seed_seq s{std::seed_seq(il, il + n)}; // by value: only a temporary can be passed (std::seed_seq does not copy)
+		std::uint32_t w[8];
+		s.generate(reinterpret_cast<std::int32_t*>(w), reinterpret_cast<std::int32_t*>(w) + 8);
+		for (std::int64_t i = 0; i < count && i < 8; i++)
+			out[i] = static_cast<double>(w[i]);
+	}
+}
+
 // ---- kahan-compensated dt exactly as snn::step() produces it (snn.cpp:8-10) -------------------
 void ref_kahan_dt(float dt, std::int64_t steps, float* out) {
 	spice::util::kahan_sum<float> simtime;

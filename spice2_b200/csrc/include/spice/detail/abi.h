@@ -127,6 +127,7 @@ struct update_args {
 	// random access into the step streams
 	rng_window rng;
 	u128 const* jump_poly;  // per chunk of kRngChunk local neurons: x^(offset of chunk start) mod charpoly
+	int* error;             // bit 64: a neuron's update() drew more values than its rng_draws declares
 };
 
 struct export_args {

@@ -468,9 +468,14 @@ __global__ void __launch_bounds__(256) update_stateless_kernel(update_args a) {
 			null_rng none;
 			spiked = neur.update(dt, none);
 		}
-		if constexpr (draws > 0)
+		if constexpr (draws > 0) {
+			// fewer draws than declared: skip the rest so the next neuron starts at its own position.  More: every neuron
+			// behind this one in the chunk would read the wrong part of the stream — reported, not papered over
+			if (rng.used > draws)
+				atomicOr(a.error, 64);
 			for (; rng.used < draws; rng.used++)
 				rng.g.advance();
+		}
 		if (spiked) {
 			unsigned const pos    = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], 1u);
 			std::int64_t const at = slot * a.ring_cap + a.lo + pos;

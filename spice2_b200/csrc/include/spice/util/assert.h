@@ -26,3 +26,9 @@ namespace spice::util::detail {
 // them too, CMakeLists.txt:6-7): they run on the host, outside the kernels.
 #define SPICE_PRE(X) SPICE_ASSERT(X)
 #define SPICE_INV(X) SPICE_ASSERT(X)
+// in a function that also compiles for the device: checked where it can throw
+#ifdef __CUDA_ARCH__
+#define SPICE_PRE_HOST(X) ((void)0)
+#else
+#define SPICE_PRE_HOST(X) SPICE_ASSERT(X)
+#endif

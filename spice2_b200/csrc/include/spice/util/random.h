@@ -9,10 +9,13 @@
 // helpers at the bottom compute such polynomials on the host and apply them on host or device.
 #pragma once
 
+#include <cmath>
 #include <cstddef>
 #include <cstring>
 #include <initializer_list>
 #include <limits>
+#include <random>
+#include <type_traits>
 
 #include "spice/util/assert.h"
 #include "spice/util/platform.h"
@@ -97,6 +100,20 @@ public:
 		SPICE_PRE(n > 0 && "Please provide at least 1 seed to seed_seq");
 	}
 	SPICE_HD constexpr explicit seed_seq(UInt128 raw) : _seed(raw) {}
+	// from the standard library's seed sequence: its first four 32-bit outputs are the seed (reference: random.h:145-148)
+	seed_seq(std::seed_seq seq) {
+		UInt32 words[4];
+		seq.generate(words, words + 4);
+		_seed = {static_cast<UInt>(words[0]) | static_cast<UInt>(words[1]) << 32, static_cast<UInt>(words[2]) | static_cast<UInt>(words[3]) << 32};
+	}
+	// SeedSequence::generate: the seed's four 32-bit words, repeated (reference: random.h:154-159)
+	template <class OutputIt>
+	constexpr void generate(OutputIt first, OutputIt last) const {
+		UInt32 const words[4] = {static_cast<UInt32>(_seed.lo), static_cast<UInt32>(_seed.lo >> 32), static_cast<UInt32>(_seed.hi),
+		                         static_cast<UInt32>(_seed.hi >> 32)};
+		for (int i = 0; first != last; ++first, i = (i + 1) & 3)
+			*first = words[i];
+	}
 
 	SPICE_HD constexpr UInt128 seed() const { return _seed; }
 
@@ -138,14 +155,44 @@ struct xoroshiro64_128p {
 	}
 };
 
-// Uniform in [0,1) (LeftOpen: (0,1]) from the top mantissa-many bits of one 64-bit draw
-// (reference: random.h:236-247; only 64-bit engines exist in this backend).
+// xoshiro128+ on four 32-bit words (reference: random.h:204-220, "xoroshiro32_128p"): 32-bit output, state = the seed's
+// words in order.  Not used by the simulation loop (its one stream is the 64-bit engine above); kept for user models.
+struct xoroshiro32_128p {
+	using result_type = UInt32;
+
+	UInt32 s[4] = {0, 0, 0, 0};
+
+	SPICE_HD constexpr explicit xoroshiro32_128p(seed_seq const& seq) :
+	s{static_cast<UInt32>(seq.seed().lo), static_cast<UInt32>(seq.seed().lo >> 32), static_cast<UInt32>(seq.seed().hi),
+	  static_cast<UInt32>(seq.seed().hi >> 32)} {}
+
+	SPICE_HD static constexpr UInt32 min() { return 0; }
+	SPICE_HD static constexpr UInt32 max() { return ~UInt32(0); }
+
+	SPICE_HD constexpr UInt32 operator()() {
+		UInt32 const out = s[0] + s[3];
+		UInt32 const t   = s[1] << 9;
+		s[2] ^= s[0];
+		s[3] ^= s[1];
+		s[1] ^= s[2];
+		s[0] ^= s[3];
+		s[2] ^= t;
+		s[3] = (s[3] << 11) | (s[3] >> 21);
+		return out;
+	}
+};
+
+// Uniform in [0,1) (LeftOpen: (0,1]) from the top mantissa-many bits of one draw; an engine narrower than Real (the 32-bit
+// engine feeding a double) contributes two draws, first draw in the high half (reference: random.h:236-247).
 template <class Real, bool LeftOpen = false, class Rng>
 SPICE_HD constexpr Real generate_canonical(Rng& rng) {
-	constexpr int digits = std::numeric_limits<Real>::digits;
-	UInt const draw      = rng();
-	return static_cast<Real>((draw >> (64 - digits)) + (LeftOpen ? 1u : 0u)) /
-	       static_cast<Real>(1_u64 << digits);
+	constexpr int digits   = std::numeric_limits<Real>::digits;
+	constexpr int rng_bits = 8 * static_cast<int>(sizeof(decltype(rng())));
+	constexpr int width    = rng_bits < 8 * static_cast<int>(sizeof(Real)) ? 8 * static_cast<int>(sizeof(Real)) : rng_bits;
+	UInt draw              = rng();
+	if constexpr (rng_bits < 8 * static_cast<int>(sizeof(Real)))
+		draw = (draw << rng_bits) | rng();
+	return static_cast<Real>((draw >> (width - digits)) + (LeftOpen ? 1u : 0u)) / static_cast<Real>(1_u64 << digits);
 }
 
 template <class Real, bool LeftOpen = false>
@@ -159,6 +206,68 @@ public:
 
 private:
 	Real _a, _w;
+};
+
+// The reference's remaining distributions (random.h:264-330), for user models.  On the device log / sqrt / cos / sin are
+// CUDA's (within an ulp of the host's libm, not bit-identical to it); the simulation loop's own bit-exact paths do not use
+// these classes (the generator restates glibc's log, spice/detail/glibc_log.h).  A neuron whose update() draws through them
+// declares the draws per call in rng_draws: 1 for exponential; normal draws 2 on every second call, so a model keeps the
+// object per call (2 draws) or per neuron.
+template <class Real>
+class exponential_distribution {
+public:
+	SPICE_HD explicit exponential_distribution(Real scale = 1) : _scale(scale) { SPICE_PRE_HOST(scale >= 0); }
+	template <class Rng>
+	SPICE_HD Real operator()(Rng& rng) const {
+		return -_scale * std::log(generate_canonical<Real, true>(rng)); // (0, 1] -> [0, inf)
+	}
+
+private:
+	Real _scale;
+};
+
+// Box-Muller, both variates kept: a call either draws two uniforms or returns the second variate of the call before
+template <class Real>
+class normal_distribution {
+public:
+	SPICE_HD explicit normal_distribution(Real mu = 0, Real sigma = 1) : _mu(mu), _sigma(sigma) { SPICE_PRE_HOST(sigma >= 0); }
+	template <class Rng>
+	SPICE_HD Real operator()(Rng& rng) {
+		_have = !_have;
+		if (!_have)
+			return _next;
+		Real const radius = std::sqrt(Real(-2) * std::log(generate_canonical<Real, true>(rng)));
+		// 2 pi u in double whatever Real is, as the reference's `2 * std::numbers::pi * u` evaluates
+		Real const angle = static_cast<Real>(2 * 3.141592653589793238462643383279502884 * generate_canonical<Real, false>(rng));
+		_next             = fp::fma(radius * std::sin(angle), _sigma, _mu);
+		return fp::fma(radius * std::cos(angle), _sigma, _mu);
+	}
+
+private:
+	bool _have = false; // _next holds the sine variate of the last pair
+	Real _next = 0;
+	Real _mu, _sigma;
+};
+
+// the normal approximation N(Np, Np(1-p)) rounded and clamped to [0, N]
+template <class Integer>
+class binomial_distribution {
+public:
+	using Real = std::conditional_t<sizeof(Integer) == 8, double, float>;
+	SPICE_HD explicit binomial_distribution(Integer N, Real p) : _n(N), _normal(N * p, std::sqrt(N * p * (1 - p))) {
+		SPICE_PRE_HOST(N >= 0);
+		SPICE_PRE_HOST(0 <= p && p <= 1);
+	}
+	template <class Rng>
+	SPICE_HD Integer operator()(Rng& rng) {
+		Real const x       = std::round(_normal(rng));
+		Integer const k    = x > Real(0) ? static_cast<Integer>(x) : Integer(0);
+		return k < _n ? k : _n;
+	}
+
+private:
+	Integer _n;
+	normal_distribution<Real> _normal;
 };
 
 // ---------------------------------------------------------------------------------------------

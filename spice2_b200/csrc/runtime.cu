@@ -1208,6 +1208,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		ua.world    = ctx->world;
 		ua.history  = p.history;
 		fill_incoming(ctx, p, ua.in, &ua.n_in);
+		ua.error     = ctx->d_error;
 		ua.rng.nib   = ctx->d_nib;
 		ua.jump_poly = p.jump_poly;
 		if (ua.n_local > 0) {
@@ -1468,6 +1469,8 @@ int check_device_error(spice_ctx* ctx) {
 		return fail(ctx, SPICE_ERR_INTERNAL, "spike delivery: internal error (pipeline made no progress)");
 	if (h & 32)
 		return fail(ctx, SPICE_ERR_INTERNAL, "stateful delivery: event list capacity exceeded");
+	if (h & 64)
+		return fail(ctx, SPICE_ERR_PRECONDITION, "a neuron's update() drew more random numbers than its rng_draws declares");
 	if (h & 4)
 		return fail(ctx, SPICE_ERR_INTERNAL, "raster log: step capacity exceeded (read the raster more often)");
 	if (h & 8)
@@ -1502,9 +1505,24 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	int e = ops->get_apply(&c->apply);
 	if (e == 0 && c->stateful)
 		e = ops->get_apply_events(&c->apply_events);
-	if (e != 0)
+	if (e != 0) {
+		cudaFree(c->functor_dev);
+		c->functor_dev = nullptr;
 		return fail(ctx, SPICE_ERR_CUDA, std::string("get_apply: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+	}
 	return SPICE_OK;
+}
+
+// a connection that failed before it reached ctx->conns (whose entries spice_ctx_destroy frees)
+void drop_connection(connection& c) {
+	cudaFree(c.functor_dev);
+	cudaFree(c.offsets);
+	cudaFree(c.neighbors);
+	cudaFree(c.syn);
+	c.functor_dev = nullptr;
+	c.offsets     = nullptr;
+	c.neighbors   = nullptr;
+	c.syn         = nullptr;
 }
 
 // per-synapse state of a stateful connection: default-constructed synapses, then the model's init
@@ -1944,6 +1962,7 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 		if (grc != 0) {
 			cudaFree(r.offsets);
 			cudaFree(r.neighbors);
+			drop_connection(c);
 			if (grc == 1) // the reference's SPICE_PRE on every streamed edge (topology.cpp:16-18)
 				return fail(ctx, SPICE_ERR_PRECONDITION, std::string("Assertion failed (") + __FILE__ + ":" + std::to_string(__LINE__) +
 				                                            "): 0 <= src && src < src_count && 0 <= dst && dst < dst_count");
@@ -1963,8 +1982,10 @@ int spice_connect_adj_list(spice_ctx* ctx, spice_synapse_ops const* ops, int src
 		}
 	}
 	rc = init_synapses(ctx, &c);
-	if (rc != SPICE_OK)
+	if (rc != SPICE_OK) {
+		drop_connection(c);
 		return rc;
+	}
 	ctx->conns.push_back(std::move(c));
 	if (conn_out)
 		*conn_out = static_cast<int>(ctx->conns.size()) - 1;

@@ -90,6 +90,14 @@ struct from_to_stateless {
 };
 static_assert(Synapse<from_to_stateless, tagged_source, stateful_neuron> && !StatefulSynapse<from_to_stateless>);
 
+// a stateless neuron that declares one draw per update() and takes two: every neuron behind it in its chunk of the step's
+// stream would read the wrong draws, so the run must fail loudly (the rng_draws contract, DESIGN.md boundary)
+struct greedy {
+	static constexpr int rng_draws = 1;
+	SPICE_HD bool update(float, auto& rng) const { return ((rng() ^ rng()) & 7) == 0; }
+};
+static_assert(StatelessNeuron<greedy>);
+
 adj_list graph() { // synapse_population.cpp:33-40
 	adj_list adj;
 	adj.connect(0, 0);
@@ -220,6 +228,20 @@ int main() {
 		bool threw = false;
 		try {
 			net.connect<stateless_synapse>(src, dst, adj, 2);
+		} catch (std::logic_error const&) {
+			threw = true;
+		}
+		EXPECT_EQ(threw, true);
+	}
+	{ // rng_draws is checked in both directions: drawing more than declared is reported by the next synchronising call
+		snn net(1, 1, {1337});
+		auto src = net.add_population<greedy>(100);
+		auto dst = net.add_population<stateful_neuron>(5);
+		net.connect<stateless_synapse>(src, dst, fixed_probability(0.5), 1);
+		bool threw = false;
+		try {
+			net.step();
+			(void)src->spikes(0);
 		} catch (std::logic_error const&) {
 			threw = true;
 		}

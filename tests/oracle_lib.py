@@ -348,6 +348,15 @@ class RefShim:
                                C.c_int64(count), _ptr(out))
         return out
 
+    def random_sample(self, kind, il, increments, a, b, count):
+        """oracle/ref_shim.cpp ref_random_sample: the reference's 32-bit engine, normal / binomial / float exponential
+        distributions and seed_seq(std::seed_seq), as doubles."""
+        w = np.asarray(il, np.uint32)
+        out = np.zeros(count, np.float64)
+        self.L.ref_random_sample(C.c_int(kind), _ptr(w), C.c_int(len(w)), C.c_int(increments), C.c_double(a), C.c_double(b),
+                                 C.c_int64(count), _ptr(out))
+        return out
+
     def kahan_dt(self, dt, steps):
         out = np.zeros(steps, np.float32)
         self.L.ref_kahan_dt(C.c_float(dt), C.c_int64(steps), _ptr(out))

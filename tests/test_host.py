@@ -100,6 +100,18 @@ int main(int argc, char** argv) {
 		xoroshiro64_128p s(strtoull(argv[2], 0, 16), strtoull(argv[3], 0, 16));
 		auto r = jump::apply(jump::xpow(strtoull(argv[4], 0, 10)), s);
 		printf("%016llx %016llx\n", (unsigned long long)r.s0, (unsigned long long)r.s1);
+	} else if (!strcmp(argv[1], "dist")) { // args: kind a b count ; seed {7, 9} advanced 2 times -> values as double bit patterns
+		int kind = atoi(argv[2]); double a = atof(argv[3]), b = atof(argv[4]); int n = atoi(argv[5]);
+		seed_seq seq{7, 9}; seq++; seq++;
+		xoroshiro32_128p r32(seq); xoroshiro64_128p r64(seq);
+		auto put = [](double v) { unsigned long long u; memcpy(&u, &v, 8); printf("%016llx\n", u); };
+		if (kind == 0) for (int i = 0; i < n; i++) put((double)r32());
+		if (kind == 1) for (int i = 0; i < n; i++) put(generate_canonical<double>(r32));
+		if (kind == 2) { normal_distribution<double> d(a, b); for (int i = 0; i < n; i++) put(d(r64)); }
+		if (kind == 3) { normal_distribution<float> d((float)a, (float)b); for (int i = 0; i < n; i++) put(d(r64)); }
+		if (kind == 4) { binomial_distribution<Int> d((Int)a, b); for (int i = 0; i < n; i++) put((double)d(r64)); }
+		if (kind == 5) { exponential_distribution<float> d((float)a); for (int i = 0; i < n; i++) put(d(r64)); }
+		if (kind == 6) { unsigned w[2] = {7, 9}; seed_seq s2{std::seed_seq(w, w + 2)}; unsigned o[8]; s2.generate(o, o + 8); for (int i = 0; i < n && i < 8; i++) put((double)o[i]); }
 	} else if (!strcmp(argv[1], "kahan")) {
 		kahan_sum<float> k; int n = atoi(argv[2]);
 		for (int i = 0; i < n; i++) { float d = k += 1e-4f; if (k >= 1) k.reset(); unsigned b; memcpy(&b, &d, 4); printf("%08x\n", b); }
@@ -341,3 +353,20 @@ def test_balance_ranges_host_arithmetic(sp):
         assert load.max() <= (w + 1).sum() / world + (w.max() + 1)
     with pytest.raises(sp.SpiceError):
         sp.balance_ranges(np.array([1, -2, 3]), 2)
+
+
+def test_random_header_distributions_match_the_compiled_reference(hosttool):
+    """The drop-in random.h's 32-bit engine, two-draw canonical, normal / binomial / float exponential distributions and
+    seed_seq(std::seed_seq) against the reference's own header compiled with IEEE flags (oracle/_ref, strict flavour): value
+    for value on the same seed (the facade must carry the reference's whole random.h surface)."""
+    from oracle_lib import RefShim
+
+    if not RefShim.available("strict"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = RefShim("strict")
+    for kind, a, b, n in [(0, 0, 0, 64), (1, 0, 0, 64), (2, 1.5, 0.25, 101), (3, -2.0, 3.0, 101), (4, 1000, 0.3, 51), (5, 0.7, 0, 64), (6, 0, 0, 8)]:
+        out = subprocess.run([str(hosttool), "dist", str(kind), repr(float(a)), repr(float(b)), str(n)], capture_output=True, text=True,
+                             check=True).stdout.split()
+        got = np.array([int(v, 16) for v in out], np.uint64).view(np.float64)
+        want = ref.random_sample(kind, (7, 9), 2, a, b, n)
+        assert np.array_equal(got, want), (kind, got[:4], want[:4])
