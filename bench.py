@@ -236,6 +236,16 @@ def generation_check(local_rank):
                 "write_roofline_frac": best["edges"] * 4.0 / (best["total_ms"] * 1e-3) / 1e9 / measured_peaks()[0],
                 "config": "fixed_probability(0.1) 1e5 x 1e5, seed {1337} (BASELINE configs[1]); best of 2, CUDA events"})
     out["golden_hash_ok"] = bool(out.get("golden_hash_ok", True) and best["edges"] == 999991208)
+    # the counter-based generator (north star: "counter-based RNG and geometric skip sampling ... bounded by write bandwidth"):
+    # another matrix of the same distribution, same shape, same seed
+    fast = None
+    for _ in range(2):
+        f5 = sp.generate_fixed_probability(100000, 100000, 0.1, (1337,), device=local_rank, copy=False, fast=True)
+        if fast is None or f5["total_ms"] < fast["total_ms"]:
+            fast = f5
+    out["counter_based"] = {"edges": fast["edges"], "device_ms": fast["total_ms"], "edges_per_s": fast["edges"] / (fast["total_ms"] * 1e-3),
+                            "write_roofline_frac": fast["edges"] * 4.0 / (fast["total_ms"] * 1e-3) / 1e9 / measured_peaks()[0],
+                            "mean_degree_error_sigmas": (fast["edges"] - 1e9) / (1e10 * 0.1 * 0.9) ** 0.5}
     return out
 
 

@@ -388,13 +388,14 @@ class Adjacency:
     """A generated adjacency that stays on the device (bench/connectivity sizes whose arrays do not fit the host):
     offsets() and rows(lo, hi) copy what is asked for."""
 
-    def __init__(self, src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None):
+    def __init__(self, src, dst, p, seed=(1337,), increments=0, device=0, col_lo=0, col_hi=None, fast=False):
         L = lib()
         lo, hi = seed_seq(seed, increments)
         self.src, self.dst = src, dst
         self.col_lo, self.col_hi = col_lo, dst if col_hi is None else col_hi
         self.h = C.c_void_p()
-        rc = L.spice_fixed_probability_generate(device, src, dst, p, lo, hi, self.col_lo, self.col_hi, C.byref(self.h))
+        gen = L.spice_fixed_probability_generate_fast if fast else L.spice_fixed_probability_generate
+        rc = gen(device, src, dst, p, lo, hi, self.col_lo, self.col_hi, C.byref(self.h))
         if rc != 0:
             raise SpiceError(rc, L.spice_last_error(None).decode())
         self.edges = int(L.spice_adjacency_edges(self.h))
