@@ -33,7 +33,9 @@ using apply_fn = void (*)(void const* functor, void* neuron, unsigned k);
 // Synapses whose deliver() also takes the SOURCE neuron (concepts.h DeliverFromTo;
 // synapse_population.h:125-131) find it through `from`: the source of edge e is the row that holds e
 // (binary search in offsets), its state is read from a snapshot of the source population taken at the
-// end of the step in which the spike was emitted (from.state == null for all other synapses).
+// end of the step in which the spike was emitted (from.state == null for all other synapses).  With more than
+// one rank the snapshot holds the WHOLE source population (every rank stores its slice into every peer's copy
+// ahead of the step's exchange flag) and `stride` is the global population's.
 struct from_ctx {
 	std::uint32_t const* state; // word-SoA snapshot of the source population
 	std::int64_t stride;
@@ -178,7 +180,7 @@ struct spice_synapse_ops {
 	std::uint32_t functor_bytes; // sizeof(Syn)
 	std::uint32_t dst_neuron_bytes;
 	std::uint32_t plastic;         // has update()/skip()
-	std::uint32_t deliver_from_to; // deliver takes the source neuron (stateful synapses, single rank: see from_ctx)
+	std::uint32_t deliver_from_to; // deliver takes the source neuron (see from_ctx; more than one rank: snapshots in the exchange region)
 	// device function pointer of apply<Syn, DstNeur>, fetched from the module that holds the kernels
 	int (*get_apply)(spice::detail::apply_fn* out);
 	// stateful synapses: default-construct `n_edges` synapses (AoS) and run the model's init hook, if any,

@@ -436,6 +436,9 @@ struct connection {
 	bool stateful = false, plastic = false;
 	bool from_to              = false;   // deliver() also reads the source neuron (concepts.h DeliverFromTo)
 	std::uint32_t* src_snapshot = nullptr; // from_to: the source population's state at the end of the last step
+	// from_to, world > 1: two snapshots of the WHOLE source population (by step parity) in the exchange region; every rank
+	// stores its slice into every peer's copy before it publishes the step
+	long long snap_off = 0, snap_half = 0, snap_stride = 0;
 	std::uint32_t* syn        = nullptr; // word-SoA synapse state, parallel to neighbors
 	long long syn_stride      = 0;
 	std::uint64_t* ages       = nullptr; // [src] (synapse_population.h:89-94)
@@ -773,6 +776,15 @@ int finalize(spice_ctx* ctx) {
 		p.ring_cnt_off = static_cast<long long>(off);
 		off            = align_up(off + sizeof(std::uint32_t) * static_cast<size_t>(ctx->ring) * ctx->world, 256);
 	}
+	if (ctx->world > 1)
+		for (auto& c : ctx->conns)
+			if (c.from_to) {
+				population const& src = ctx->pops[c.src];
+				c.snap_stride         = static_cast<long long>(align_up(static_cast<size_t>(std::max<long long>(src.size, 1)), 32));
+				c.snap_half           = static_cast<long long>(align_up(sizeof(std::uint32_t) * ((src.ops->neuron_bytes + 3) / 4) * static_cast<size_t>(c.snap_stride), 256));
+				c.snap_off            = static_cast<long long>(off);
+				off += 2 * static_cast<size_t>(c.snap_half);
+			}
 	ctx->flags_off = off;
 	off            = align_up(off + sizeof(unsigned long long) * kMaxWorld, 256);
 	ctx->xbytes    = off;
@@ -1045,6 +1057,10 @@ void fill_incoming(spice_ctx* ctx, population const& p, incoming* in, int* n_in)
 		                               c.stateful ? c.evt_cnt : nullptr, c.evt_off, c.evt_list, c.syn, c.syn_stride, c.apply_events,
 		                               from_ctx{c.src_snapshot, ctx->pops[c.src].stride, reinterpret_cast<std::int64_t const*>(c.offsets),
 		                                        ctx->pops[c.src].size, ctx->mode == SPICE_MODE_FAST ? 1 : 0}};
+		if (c.from_to && ctx->world > 1) { // the whole source population as every rank left it at the end of the step before
+			in[k].from.state  = xptr<std::uint32_t>(ctx->xbase, c.snap_off + ((ctx->time + 1) & 1) * c.snap_half);
+			in[k].from.stride = c.snap_stride;
+		}
 	}
 }
 
@@ -1241,6 +1257,22 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	if (ctx->profile)
 		prof_mark(ctx);
 	if (ctx->world > 1) {
+		// DeliverFromTo synapses read their source neuron as it is at the end of this step, wherever it lives: this rank's
+		// slice of the source population goes into every rank's snapshot of parity (step & 1) ahead of the window flag.  A peer
+		// is at most one step ahead (it needs this rank's flag of step t to start step t + 2), so two snapshots suffice.
+		for (auto& c : ctx->conns)
+			if (c.from_to) {
+				population const& src = ctx->pops[c.src];
+				if (src.hi <= src.lo)
+					continue;
+				size_t const words = (src.ops->neuron_bytes + 3) / 4;
+				for (int r = 0; r < ctx->world; r++)
+					CHECK_CUDA(ctx, cudaMemcpy2DAsync(xptr<std::uint32_t>(ctx->peer_base[r], c.snap_off + (ctx->time & 1) * c.snap_half) + src.lo,
+					                                  sizeof(std::uint32_t) * static_cast<size_t>(c.snap_stride), src.state,
+					                                  sizeof(std::uint32_t) * static_cast<size_t>(src.stride),
+					                                  sizeof(std::uint32_t) * static_cast<size_t>(src.hi - src.lo), words, cudaMemcpyDeviceToDevice,
+					                                  ctx->stream));
+			}
 		ctx->seq++;
 		publish_args pb{};
 		pb.local_cnt = ctx->d_ring_cnt;
@@ -1330,7 +1362,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		// (synapse_population.h:125-131 runs after every population's update, snn.cpp:21-25); the events
 		// counted above are applied at the start of the next step, so keep that state
 		for (auto& c : ctx->conns)
-			if (c.from_to) {
+			if (c.from_to && ctx->world == 1) { // (more than one rank: stored into every rank's snapshot before the exchange)
 				population const& src = ctx->pops[c.src];
 				size_t const bytes    = sizeof(std::uint32_t) * ((src.ops->neuron_bytes + 3) / 4) * static_cast<size_t>(src.stride);
 				CHECK_CUDA(ctx, cudaMemcpyAsync(c.src_snapshot, src.state, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1488,9 +1520,9 @@ int add_connection_common(spice_ctx* ctx, spice_synapse_ops const* ops, int src_
 	long long const d = static_cast<long long>(std::round(delay / ctx->dt)); // snn.h:33
 	PRE(ctx, d >= 1 && "The delay must be at least 1dt.");                 // snn.h:35
 	PRE(ctx, d <= ctx->max_delay && "The delay of a synapse population may not exceed the maximum delay of the network."); // snn.h:36-38
-	if (ops->deliver_from_to && (ops->synapse_bytes == 0 || ctx->world > 1))
-		return fail(ctx, SPICE_ERR_UNSUPPORTED, // (stateless ones arrive here with one carried word of state: model_ops.cuh carried_from_to)
-		            "synapses whose deliver() reads the source neuron are on the GPU path on a single rank only");
+	if (ops->deliver_from_to && ops->synapse_bytes == 0)
+		return fail(ctx, SPICE_ERR_UNSUPPORTED, // (the facade hands stateless ones over with one carried word of state: model_ops.cuh carried_from_to)
+		            "a synapse whose deliver() reads the source neuron needs per-synapse state in this ABI");
 	PRE(ctx, ops->synapse_bytes % 4 == 0);
 	c->stateful = ops->synapse_bytes != 0;
 	c->from_to  = ops->deliver_from_to != 0;

@@ -1,6 +1,7 @@
 // More than one rank for what the reference's samples use beside fixed_probability + stateless synapses: per-synapse init
-// hooks (synapse_population.h:34-41) over fixed_probability and adj_list connections, and host-fed populations
-// (per-population update(), neuron_population.h:86-101).  Two rank contexts of one process on one device (peer handles
+// hooks (synapse_population.h:34-41) over fixed_probability and adj_list connections, host-fed populations
+// (per-population update(), neuron_population.h:86-101) and synapses whose deliver() reads the source neuron
+// (DeliverFromTo, concepts.h:76-99).  Two rank contexts of one process on one device (peer handles
 // resolved without CUDA IPC) must reproduce the one-rank run of this backend — which the samples and facade_spec pin to the
 // reference — spike for spike, neuron for neuron and synapse for synapse.
 // Exit status 0 = every expectation holds.
@@ -64,6 +65,104 @@ struct drawn_weight {
 	}
 };
 static_assert(StatefulSynapse<drawn_weight>);
+
+// DeliverFromTo (concepts.h:76-99, synapse_population.h:125-131): deliver() reads the SOURCE neuron as it is at the end of the
+// step in which it fired — on another rank, for most synapses of a sharded network
+struct charger {
+	struct neuron {
+		float charge = 0;
+		int phase    = 0;
+	};
+	SPICE_HD void init(neuron& n, Int id, auto&) const { n.phase = static_cast<int>(id % 11); }
+	SPICE_HD bool update(neuron& n, float, auto&) const {
+		n.charge += 0.125f * static_cast<float>(1 + n.phase % 3);
+		n.phase++;
+		if (n.phase % 11 != 0)
+			return false;
+		n.charge *= 0.5f;
+		return true;
+	}
+};
+static_assert(StatefulNeuron<charger>);
+struct carry_charge {
+	struct synapse {
+		float gain = 1;
+	};
+	SPICE_HD void init(synapse& syn, Int src, Int dst, auto& rng) const {
+		uniform_real_distribution<float> u(0.5f, 1.5f);
+		syn.gain = u(rng) + 0.01f * static_cast<float>((src + dst) % 3);
+	}
+	SPICE_HD void deliver(synapse const& syn, charger::neuron const& from, integrator::neuron& to) const {
+		to.v += 0.01f * syn.gain * from.charge;
+		to.count++;
+	}
+};
+static_assert(StatefulSynapse<carry_charge>);
+
+struct from_to_network {
+	std::unique_ptr<snn> net;
+	spice::detail::neuron_population<charger>* C    = nullptr;
+	spice::detail::neuron_population<integrator>* T = nullptr;
+};
+
+static from_to_network build_from_to(int rank, int world) {
+	from_to_network w;
+	w.net = std::make_unique<snn>(1e-3f, 3e-3f, seed_seq{21}, 0, rank, world);
+	w.C   = w.net->add_population<charger>(407);
+	w.T   = w.net->add_population<integrator>(311);
+	w.net->connect<carry_charge>(w.C, w.T, fixed_probability(0.08), 2e-3f);
+	w.net->connect<carry_charge>(w.C, w.T, fixed_probability(0.04), 3e-3f);
+	return w;
+}
+
+static void connect_ranks(snn* a, snn* b) {
+	std::vector<unsigned char> handles;
+	int64_t each = 0;
+	for (snn* n : {a, b}) {
+		EXPECT(spice_ctx_finalize(n->context()) == SPICE_OK);
+		int64_t bytes = 0;
+		EXPECT(spice_ctx_peer_handle(n->context(), nullptr, &bytes) == SPICE_OK);
+		each = bytes;
+		handles.resize(handles.size() + static_cast<size_t>(bytes));
+		EXPECT(spice_ctx_peer_handle(n->context(), handles.data() + handles.size() - bytes, &bytes) == SPICE_OK);
+	}
+	for (snn* n : {a, b})
+		EXPECT(spice_ctx_set_peers(n->context(), handles.data(), each) == SPICE_OK);
+}
+
+static void from_to_on_two_ranks() {
+	from_to_network one = build_from_to(0, 1);
+	from_to_network r[2] = {build_from_to(0, 2), build_from_to(1, 2)};
+	connect_ranks(r[0].net.get(), r[1].net.get());
+	long long spikes = 0;
+	for (int step = 0; step < 60; step++) {
+		one.net->step();
+		for (auto& w : r)
+			w.net->step();
+		for (auto& w : r)
+			for (Int p = 0; p < 2; p++) {
+				auto got = w.net->spikes(p), want = one.net->spikes(p);
+				EXPECT(got.size() == want.size());
+				for (std::size_t i = 0; i < got.size(); i++)
+					EXPECT(got[i] == want[i]);
+			}
+		spikes += static_cast<long long>(one.net->spikes(0).size() + one.net->spikes(1).size());
+	}
+	auto t1 = one.T->get_neurons();
+	std::vector<integrator::neuron> t2;
+	for (auto& w : r) {
+		auto t = w.T->get_neurons();
+		t2.insert(t2.end(), t.begin(), t.end());
+	}
+	EXPECT(t1.size() == t2.size());
+	long long delivered = 0;
+	for (std::size_t i = 0; i < t1.size(); i++) {
+		EXPECT(t1[i].v == t2[i].v && t1[i].count == t2[i].count);
+		delivered += t1[i].count;
+	}
+	EXPECT(spikes > 1000 && delivered > 10000);
+	std::printf("from_to on two ranks ok: %lld spikes, %lld deliveries\n", spikes, delivered);
+}
 
 struct network {
 	std::unique_ptr<snn> net;
@@ -170,6 +269,7 @@ int main() {
 	for (std::size_t i = 0; i < b1.size(); i++)
 		EXPECT(b1[i].v == b2[i].v && b1[i].count == b2[i].count);
 	EXPECT(delivered > 100);
+	from_to_on_two_ranks();
 	std::printf("multi_rank_spec ok: %lld spikes, %lld deliveries into A\n", spikes, delivered);
 	return 0;
 }
