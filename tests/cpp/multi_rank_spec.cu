@@ -23,6 +23,16 @@ using namespace spice::util;
 		}                                                               \
 	} while (0)
 
+// SPICE_SPEC_TWO_DEVICES=1 (and two GPUs): rank r lives on device r, so every peer store crosses NVLink
+static int device_of(int rank) {
+	static int const two = [] {
+		int n = 0;
+		char const* e = std::getenv("SPICE_SPEC_TWO_DEVICES");
+		return (e && e[0] == '1' && cudaGetDeviceCount(&n) == cudaSuccess && n >= 2) ? 1 : 0;
+	}();
+	return two ? rank : 0;
+}
+
 // a deterministic spike train: neuron i fires in step t when (i * 7 + t * 13) % 17 == 0
 struct drummer {
 	Int n    = 0;
@@ -107,7 +117,7 @@ struct from_to_network {
 
 static from_to_network build_from_to(int rank, int world) {
 	from_to_network w;
-	w.net = std::make_unique<snn>(1e-3f, 3e-3f, seed_seq{21}, 0, rank, world);
+	w.net = std::make_unique<snn>(1e-3f, 3e-3f, seed_seq{21}, device_of(rank), rank, world);
 	w.C   = w.net->add_population<charger>(407);
 	w.T   = w.net->add_population<integrator>(311);
 	w.net->connect<carry_charge>(w.C, w.T, fixed_probability(0.08), 2e-3f);
@@ -173,7 +183,7 @@ struct network {
 
 static network build(int rank, int world) {
 	network w;
-	w.net = std::make_unique<snn>(1e-3f, 4e-3f, seed_seq{7, 11}, 0, rank, world);
+	w.net = std::make_unique<snn>(1e-3f, 4e-3f, seed_seq{7, 11}, device_of(rank), rank, world);
 	w.D   = w.net->add_population<drummer>(300, drummer{300});
 	w.A   = w.net->add_population<integrator>(501);
 	w.B   = w.net->add_population<integrator>(233);
@@ -270,6 +280,7 @@ int main() {
 		EXPECT(b1[i].v == b2[i].v && b1[i].count == b2[i].count);
 	EXPECT(delivered > 100);
 	from_to_on_two_ranks();
+	std::printf("devices: rank 1 on device %d\n", device_of(1));
 	std::printf("multi_rank_spec ok: %lld spikes, %lld deliveries into A\n", spikes, delivered);
 	return 0;
 }

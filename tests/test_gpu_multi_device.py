@@ -128,3 +128,20 @@ def test_ranks_on_separate_devices_match_oracle(orc, plastic):
         for _ in range(14):  # the reference tallies a spike's events delay - 1 steps after this backend does
             onet.step()
         assert sum(out["events"] for out in res) == onet.events()
+
+
+def test_multi_rank_spec_across_two_devices():
+    """tests/cpp/multi_rank_spec.cu with rank r on device r: per-synapse init hooks, a host-fed population and DeliverFromTo
+    synapses (source snapshots stored into the peer over NVLink) reproduce the one-rank run."""
+    import os
+    import subprocess
+    from pathlib import Path
+
+    if _gpu_count() < 2:
+        pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "tests" / "cpp" / "build" / "multi_rank_spec"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(root / "tests" / "cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, timeout=600, env=dict(os.environ, SPICE_SPEC_TWO_DEVICES="1"))
+    assert r.returncode == 0 and b"rank 1 on device 1" in r.stdout, r.stdout.decode() + r.stderr.decode()
