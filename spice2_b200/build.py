@@ -48,9 +48,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             return OUT  # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
         raise RuntimeError(f"nvcc not found at {NVCC} and no prebuilt {OUT.name}")
     OBJ.mkdir(exist_ok=True)
+    # several ranks of one box may find the library stale at the same moment (torchrun): one of them builds, into private
+    # names, and renames the result into place; the others wait for the lock and find the stamp up to date
+    import fcntl
+
+    with open(OBJ / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and OUT.exists() and stamp.exists() and stamp.read_text() == digest:
+            return OUT
+        return _build_locked(digest, stamp, verbose)
+
+
+def _build_locked(digest: str, stamp: Path, verbose: bool) -> Path:
+    tag = f".{os.getpid()}"
     procs = []
     for src, extra in UNITS:
-        obj = OBJ / (src.rsplit(".", 1)[0] + ".o")
+        obj = OBJ / (src.rsplit(".", 1)[0] + tag + ".o")
         cmd = [NVCC, *COMMON, *extra, "-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
@@ -63,10 +76,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out.strip():
             print(out)
         objs.append(str(obj))
-    cmd = [NVCC, "-shared", "-o", str(OUT), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp_out = OUT.with_name(OUT.name + tag)
+    cmd = [NVCC, "-shared", "-o", str(tmp_out), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    for o in objs:
+        Path(o).unlink(missing_ok=True)
     if r.returncode != 0:
+        tmp_out.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_out, OUT)  # atomic: a process that has the old library mapped keeps it
     stamp.write_text(digest)
     return OUT
 
