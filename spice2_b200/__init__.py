@@ -42,6 +42,12 @@ def lib() -> C.CDLL:
     back to a CPU path."""
     global _lib
     if _lib is None:
+        # Several rank contexts in ONE process (tests): a kernel loaded lazily at its first launch can synchronise the device,
+        # which never returns while another rank's wait kernel spins for work this thread has not enqueued yet.  Load every
+        # kernel when the module is loaded instead (no effect once CUDA is initialised; one process per GPU never needs it).
+        import os
+
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
         path = _build()
         L = C.CDLL(str(path))
         vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int

@@ -185,17 +185,17 @@ def test_two_ranks_one_device(sp, orc):
     assert sum(net.stats()["synaptic_events"] for net, _ in nets) == onet.events()
 
 
-def test_two_ranks_uneven_target_ranges(sp, orc):
-    """spice_set_next_partition: rank 0 owns 30 % of every population, rank 1 the rest (the ranges a non-uniform topology's
-    in-degree balance would produce): still the reference's raster and state, bit for bit."""
+@pytest.mark.parametrize("shape", ["30/70", "0/25/75"])
+def test_ranks_with_uneven_target_ranges(sp, orc, shape):
+    """spice_set_next_partition: rank 0 owns 30 % of every population and rank 1 the rest, or three ranks of which the first
+    owns nothing (ranges an in-degree balance can produce): still the reference's raster and state, bit for bit."""
     from spice2_b200.samples import brunel
 
     kw = dict(N=3000, p=0.1, w_exc=np.float32(2.0 / 300), w_inh=np.float32(-10.0 / 300))
     onet, opops = brunel_oracle(orc, **kw)
-    world = 2
-    part = lambda n: [0, n * 3 // 10, n]
+    world, part = (2, lambda n: [0, n * 3 // 10, n]) if shape == "30/70" else (3, lambda n: [0, 0, n // 4, n])
     nets = [brunel(rank=r, world=world, partition=part, **kw) for r in range(world)]
-    assert nets[0][1][1].range() == (0, 360) and nets[1][1][1].range() == (360, 1200)
+    assert [pops[1].range() for _, pops in nets] == ([(0, 360), (360, 1200)] if world == 2 else [(0, 0), (0, 300), (300, 1200)])
     for net, _ in nets:
         net.finalize()
     handles = [net.peer_handle() for net, _ in nets]
