@@ -337,7 +337,13 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 	N n                      = load_soa<N>(a.state, a.stride, ii);
 	std::uint64_t hist       = (a.history && active) ? a.history[ii] : 0;
 	std::int32_t const my_id = static_cast<std::int32_t>(a.lo + i);
-	null_rng rng;
+	// a neuron that draws: its draws of step t sit at (population offset + global index * draws) of the step's stream
+	// (neuron_population.h:116-124 walks the neurons in order with the step's one engine): the chunk's jump polynomial
+	// gives the engine at the chunk's first neuron, this neuron's own position is (index in chunk) * draws steps on
+	constexpr int draws = rng_draws_v<Neur>;
+	u128 my_poly{0, 0};
+	if constexpr (draws > 0)
+		my_poly = a.jump_poly[ii / kRngChunk];
 	constexpr int C = NIN > 0 ? NIN : 1;
 
 	// event counters of the step, one per incoming connection; the next step's are fetched while
@@ -397,8 +403,29 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 			}
 			kk[c] = kn[c];
 		}
-		bool const spiked = active && neur.update(n, a.dt[s], rng);
-		hist              = (hist << 1) | (spiked ? 1u : 0u);
+		bool spiked;
+		if constexpr (draws > 0) {
+			u128 const* nib = a.rng.nib + static_cast<std::int64_t>(s) * 32 * 16;
+			UInt s0 = 0, s1 = 0;
+#pragma unroll 8
+			for (int g = 0; g < 32; g++) {
+				unsigned const v   = static_cast<unsigned>(((g < 16 ? my_poly.lo : my_poly.hi) >> (4 * (g & 15))) & 15);
+				ulonglong2 const e = __ldg(reinterpret_cast<ulonglong2 const*>(nib + g * 16 + v));
+				s0 ^= e.x;
+				s1 ^= e.y;
+			}
+			counting_rng rng;
+			rng.g = util::xoroshiro64_128p(s0, s1);
+			for (int k = static_cast<int>(ii % kRngChunk) * draws; k > 0; k--)
+				rng.g.advance();
+			spiked = active && neur.update(n, a.dt[s], rng);
+			if (rng.used > draws)
+				atomicOr(a.error, 64);
+		} else {
+			null_rng rng;
+			spiked = active && neur.update(n, a.dt[s], rng);
+		}
+		hist = (hist << 1) | (spiked ? 1u : 0u);
 
 		unsigned const m = __ballot_sync(0xffffffffu, spiked);
 		if (m) {
@@ -554,7 +581,6 @@ struct neuron_ops_builder {
 	static int launch_update(update_args const* a) {
 		auto stream = static_cast<cudaStream_t>(a->stream);
 		if constexpr (StatefulNeuron<Neur>) {
-			static_assert(rng_draws_v<Neur> == 0, "stateful neurons that draw from the rng are not supported yet");
 			if (a->n_local > 0) {
 				bool fast = a->n_in <= 4;
 				for (int c = 0; c < a->n_in; c++)

@@ -97,6 +97,32 @@ struct greedy {
 	SPICE_HD bool update(float, auto& rng) const { return ((rng() ^ rng()) & 7) == 0; }
 };
 static_assert(StatelessNeuron<greedy>);
+struct greedy_ok { // the same with its one draw declared
+	static constexpr int rng_draws = 1;
+	SPICE_HD bool update(float, auto& rng) const { return (rng() & 7) == 0; }
+};
+
+// a STATEFUL neuron that draws (the everyday "LIF with noise"): neuron_population.h:116-124 updates the neurons in index
+// order with the step's one engine, so neuron i of a population takes draws [offset + 2 i, offset + 2 i + 2) of the stream
+struct noisy {
+	static constexpr int rng_draws = 2;
+	struct neuron {
+		float v   = 0;
+		int fired = 0;
+	};
+	SPICE_HD bool update(neuron& n, float, auto& rng) const {
+		uniform_real_distribution<float> kick(0.0f, 0.3f);
+		n.v += kick(rng);
+		if ((rng() & 7) == 0) // a second draw that sometimes takes the charge away again
+			n.v *= 0.5f;
+		if (n.v < 1.0f)
+			return false;
+		n.v = 0;
+		n.fired++;
+		return true;
+	}
+};
+static_assert(StatefulNeuron<noisy>);
 
 adj_list graph() { // synapse_population.cpp:33-40
 	adj_list adj;
@@ -232,6 +258,55 @@ int main() {
 			threw = true;
 		}
 		EXPECT_EQ(threw, true);
+	}
+	{ // stateful neurons that draw, two populations of them behind a stateless one that draws as well: every population's
+	  // draws start where the population before it stopped (snn.cpp:12-15), checked against the loop run on the host
+		snn net(1, 1, {4711});
+		Int const n0 = 77, n1 = 333, n2 = 150;
+		auto pre = net.add_population<greedy_ok>(n0);
+		auto a   = net.add_population<noisy>(n1);
+		auto b   = net.add_population<noisy>(n2);
+		auto sink = net.add_population<stateful_neuron>(5); // behind the drawing populations: no draws, one seed++
+		net.connect<stateless_synapse>(pre, sink, fixed_probability(0.5), 1);
+		uint64_t sd[2];
+		EXPECT_EQ(spice_ctx_seed(net.context(), sd), SPICE_OK);
+		util::seed_seq seed(UInt128{sd[0], sd[1]});
+		std::vector<noisy::neuron> ha(n1), hb(n2);
+		for (int step = 0; step < 40; step++) {
+			util::xoroshiro64_128p rng(seed++);
+			std::vector<Int32> s0, sa, sb;
+			greedy_ok g;
+			noisy m;
+			for (Int i = 0; i < n0; i++)
+				if (g.update(1.0f, rng))
+					s0.push_back(static_cast<Int32>(i));
+			for (Int i = 0; i < n1; i++)
+				if (m.update(ha[i], 1.0f, rng))
+					sa.push_back(static_cast<Int32>(i));
+			for (Int i = 0; i < n2; i++)
+				if (m.update(hb[i], 1.0f, rng))
+					sb.push_back(static_cast<Int32>(i));
+			net.step();
+			auto check = [](std::span<Int32 const> got, std::vector<Int32> const& want) {
+				EXPECT_EQ(got.size(), want.size());
+				for (std::size_t k = 0; k < want.size(); k++)
+					EXPECT_EQ(got[k], want[k]);
+			};
+			check(pre->spikes(0), s0);
+			check(a->spikes(0), sa);
+			check(b->spikes(0), sb);
+		}
+		auto ga = a->get_neurons();
+		auto gb = b->get_neurons();
+		long long fired = 0;
+		for (Int i = 0; i < n1; i++) {
+			EXPECT_EQ(ga[i].v == ha[i].v, true);
+			EXPECT_EQ(ga[i].fired, ha[i].fired);
+			fired += ha[i].fired;
+		}
+		for (Int i = 0; i < n2; i++)
+			EXPECT_EQ(gb[i].v == hb[i].v && gb[i].fired == hb[i].fired, true);
+		EXPECT_EQ(fired > 100, true);
 	}
 	{ // rng_draws is checked in both directions: drawing more than declared is reported by the next synchronising call
 		snn net(1, 1, {1337});
