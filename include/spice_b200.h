@@ -95,9 +95,11 @@ SPICE_API int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, 
  * ids_out, capacity, &draws): it writes the population-relative ids (0 <= id < size) of the neurons
  * that fire in this step and returns how many (<= capacity = size; < 0: failure).  (seed, rng_offset)
  * address the step's random stream — the engine of snn.cpp:12 advanced by the draws of the
- * populations added before this one; a functor that DRAWS from it (draws != 0) is not supported
- * yet.  With more than one rank the population is replicated: every rank calls its own copy of the
- * functor, which must emit the same spikes everywhere. */
+ * populations added before this one (and by the host functors that ran before this one in the same step);
+ * *draws_out = how many values this call took.  A functor that draws must come after every device
+ * population that draws (those jump into the stream at positions fixed when the network is built).
+ * With more than one rank the population is replicated: every rank calls its own copy of the functor,
+ * which must emit the same spikes everywhere. */
 typedef int64_t (*spice_host_update_fn)(void* user, float dt, uint64_t seed_lo, uint64_t seed_hi, uint64_t rng_offset,
                                         int32_t* ids_out, int64_t capacity, int64_t* draws_out);
 SPICE_API int spice_add_host_population(spice_ctx* ctx, int64_t size, spice_host_update_fn update, void* user, int* pop_out);

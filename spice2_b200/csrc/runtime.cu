@@ -1141,10 +1141,16 @@ int run_window(spice_ctx* ctx, int nsteps) {
 	ctx->launches++;
 
 	// host-fed populations: ask the host for every step's spikes, in step order, and copy them into the ring
-	for (int s = 0; s < nsteps; s++)
+	for (int s = 0; s < nsteps; s++) {
+		long long host_draws = 0; // drawn by this step's host functors so far: the next one's stream position moves by that much
 		for (auto& p : ctx->pops) {
-			if (!p.host_update)
+			if (!p.host_update) {
+				// a device population jumps into the step's stream at a position fixed when the network was built
+				if (host_draws != 0 && p.ops->rng_draws != 0)
+					return fail(ctx, SPICE_ERR_UNSUPPORTED,
+					            "a per-population update() that draws from the step's random stream must come after every device population that draws");
 				continue;
+			}
 			long long const slot = (ctx->time + s) % ctx->ring;
 			long long const cap  = std::max<long long>(p.size, 1);
 			cudaEvent_t& done    = p.stage_done[static_cast<size_t>(slot)];
@@ -1153,12 +1159,11 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			else
 				CHECK_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
 			int64_t draws   = 0;
-			int64_t const n = p.host_update(p.host_user, dts[s], pa.seed[s].lo, pa.seed[s].hi, static_cast<uint64_t>(p.rng_offset),
+			int64_t const n = p.host_update(p.host_user, dts[s], pa.seed[s].lo, pa.seed[s].hi, static_cast<uint64_t>(p.rng_offset + host_draws),
 			                                p.h_stage + slot * cap, p.size, &draws);
-			if (n < 0 || n > p.size)
+			if (n < 0 || n > p.size || draws < 0)
 				return fail(ctx, SPICE_ERR_PRECONDITION, "per-population update(): spike count out of range");
-			if (draws != 0)
-				return fail(ctx, SPICE_ERR_UNSUPPORTED, "a per-population update() that draws from the step's random stream is not supported yet");
+			host_draws += draws;
 			for (int64_t i = 0; i < n; i++)
 				if (p.h_stage[slot * cap + i] < 0 || p.h_stage[slot * cap + i] >= p.size)
 					return fail(ctx, SPICE_ERR_PRECONDITION, "per-population update(): spike id out of range");
@@ -1170,6 +1175,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			                                sizeof(std::uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 			CHECK_CUDA(ctx, cudaEventRecord(done, ctx->stream));
 		}
+	}
 
 	// The populations' update kernels are independent of each other (each reads counters written in
 	// earlier windows and writes its own state and spike lists), and the smaller ones do not fill the

@@ -4,6 +4,7 @@
 // (per-population update()) emits the test's spike list, an adj_list carries the 3 x 5 graph, and the
 // counters the synapses leave in the target neurons are read back with get_neurons().
 // Exit status 0 = every expectation of the reference tests holds.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -123,6 +124,18 @@ struct noisy {
 	}
 };
 static_assert(StatefulNeuron<noisy>);
+
+// a per-population update() that draws (concepts.h:46-57): two neighbouring neurons fire, chosen by the step's engine
+struct roulette {
+	Int n = 0;
+	void update(float, auto& rng, std::vector<Int32>& out) {
+		Int const first = static_cast<Int>(rng() % static_cast<UInt>(n));
+		out.push_back(static_cast<Int32>(first));
+		if (rng() & 1)
+			out.push_back(static_cast<Int32>((first + 1) % n));
+	}
+};
+static_assert(PerPopulationUpdate<roulette>);
 
 adj_list graph() { // synapse_population.cpp:33-40
 	adj_list adj;
@@ -307,6 +320,42 @@ int main() {
 		for (Int i = 0; i < n2; i++)
 			EXPECT_EQ(gb[i].v == hb[i].v && gb[i].fired == hb[i].fired, true);
 		EXPECT_EQ(fired > 100, true);
+	}
+	{ // a host-fed population that draws, behind a device population that draws: it continues the step's stream where the
+	  // device population stopped (snn.cpp:12-15), and its own draws (1 or 2 per step) move nobody else
+		snn net(1, 1, {99});
+		Int const n0 = 45, n1 = 20;
+		auto pre  = net.add_population<greedy_ok>(n0);
+		auto host = net.add_population<roulette>(n1, roulette{n1});
+		auto sink = net.add_population<stateful_neuron>(n1);
+		net.connect<stateless_synapse>(host, sink, fixed_probability(1.0), 1);
+		uint64_t sd[2];
+		EXPECT_EQ(spice_ctx_seed(net.context(), sd), SPICE_OK);
+		util::seed_seq seed(UInt128{sd[0], sd[1]});
+		long long delivered = 0;
+		for (int step = 0; step < 30; step++) {
+			util::xoroshiro64_128p rng(seed++);
+			std::vector<Int32> s0, s1;
+			greedy_ok g;
+			for (Int i = 0; i < n0; i++)
+				if (g.update(1.0f, rng))
+					s0.push_back(static_cast<Int32>(i));
+			roulette{n1}.update(1.0f, rng, s1);
+			delivered += static_cast<long long>(s1.size()) * n1;
+			net.step();
+			auto a = pre->spikes(0), b = host->spikes(0);
+			EXPECT_EQ(a.size(), s0.size());
+			for (std::size_t k = 0; k < s0.size(); k++)
+				EXPECT_EQ(a[k], s0[k]);
+			std::sort(s1.begin(), s1.end()); // spikes() of a host-fed population comes back ascending
+			EXPECT_EQ(b.size(), s1.size());
+			for (std::size_t k = 0; k < s1.size(); k++)
+				EXPECT_EQ(b[k], s1[k]);
+		}
+		long long got = 0;
+		for (auto const& n : sink->get_neurons())
+			got += n.received_count;
+		EXPECT_EQ(got, delivered); // delay 1: delivered at the end of the step that emitted them (get_neurons folds them in)
 	}
 	{ // rng_draws is checked in both directions: drawing more than declared is reported by the next synchronising call
 		snn net(1, 1, {1337});
