@@ -79,7 +79,9 @@ public:
 		return {ids, static_cast<std::size_t>(n)};
 	}
 
-	// copy of this rank's neurons (neuron_population.h:142-145); refreshed on every call
+	// copy of this rank's neurons (neuron_population.h:142-145), refreshed on every call.  The reference hands out a span
+	// over the live state; the state lives on the device here, so the span is read-only (a write into a copy would be lost
+	// silently: it does not compile instead) and set_neurons() carries changes back.
 	auto get_neurons() {
 		static_assert(StatefulNeuron<Neur>, "Can only return collections of stateful neurons.");
 		using N = neuron_traits_t<Neur>;
@@ -87,7 +89,13 @@ public:
 		check(_ctx, spice_population_range(_ctx, _index, &lo, &hi));
 		_cache.values.resize(static_cast<std::size_t>(hi - lo));
 		check(_ctx, spice_neurons(_ctx, _index, _cache.values.data(), static_cast<int64_t>(_cache.values.size() * sizeof(N))));
-		return std::span<N>(_cache.values);
+		return std::span<N const>(_cache.values);
+	}
+	// overwrite this rank's neurons (as many as get_neurons() returns); deliveries still pending for the next step are
+	// part of what get_neurons() returned and are not applied a second time
+	void set_neurons(std::span<neuron_traits_t<Neur> const> values) {
+		static_assert(StatefulNeuron<Neur>, "Can only set collections of stateful neurons.");
+		check(_ctx, spice_set_neurons(_ctx, _index, values.data(), static_cast<int64_t>(values.size_bytes())));
 	}
 
 private:

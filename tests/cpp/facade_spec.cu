@@ -357,6 +357,24 @@ int main() {
 			got += n.received_count;
 		EXPECT_EQ(got, delivered); // delay 1: delivered at the end of the step that emitted them (get_neurons folds them in)
 	}
+	{ // get_neurons() is a read-only copy, set_neurons() carries changes back (the state lives on the device)
+		snn net(1, 1, {1337});
+		auto src = net.add_population<source>(3);
+		auto dst = net.add_population<stateful_neuron>(5);
+		auto adj = graph();
+		net.connect<stateless_synapse>(src, dst, adj, 1);
+		net.step(); // received_count = {1, 1, 0, 2, 0}
+		auto const view = dst->get_neurons();
+		std::vector<stateful_neuron::neuron> mine(view.begin(), view.end());
+		for (auto& n : mine)
+			n.received_count += 100;
+		dst->set_neurons(mine);
+		net.step(); // nothing fires any more: the pending deliveries were part of the copy and are not applied twice
+		int const expect[5] = {101, 101, 100, 102, 100};
+		auto const after = dst->get_neurons();
+		for (int i = 0; i < 5; i++)
+			EXPECT_EQ(after[i].received_count, expect[i]);
+	}
 	{ // rng_draws is checked in both directions: drawing more than declared is reported by the next synchronising call
 		snn net(1, 1, {1337});
 		auto src = net.add_population<greedy>(100);
