@@ -227,14 +227,14 @@ def generation_check(local_rank):
         out["golden_hash_ok"] = bool(r["edges"] == g4["edges"] and sp.fnv1a64(r["offsets"]) == g4["fnv_offsets"]
                                      and sp.fnv1a64(r["neighbors"]) == g4["fnv_neighbors"])
     best = None
-    for _ in range(2):
+    for _ in range(3):  # the generation has host round trips per chunk of the stream: a busy host shows (69 .. 200 ms seen)
         r5 = sp.generate_fixed_probability(100000, 100000, 0.1, (1337,), device=local_rank, copy=False)
         if best is None or r5["total_ms"] < best["total_ms"]:
             best = r5
     out.update({"edges": best["edges"], "edges_expected": 999991208, "device_ms": best["total_ms"],
                 "edges_per_s": best["edges"] / (best["total_ms"] * 1e-3),
                 "write_roofline_frac": best["edges"] * 4.0 / (best["total_ms"] * 1e-3) / 1e9 / measured_peaks()[0],
-                "config": "fixed_probability(0.1) 1e5 x 1e5, seed {1337} (BASELINE configs[1]); best of 2, CUDA events"})
+                "config": "fixed_probability(0.1) 1e5 x 1e5, seed {1337} (BASELINE configs[1]); best of 3, CUDA events"})
     out["golden_hash_ok"] = bool(out.get("golden_hash_ok", True) and best["edges"] == 999991208)
     # the counter-based generator (north star: "counter-based RNG and geometric skip sampling ... bounded by write bandwidth"):
     # another matrix of the same distribution, same shape, same seed
