@@ -1322,6 +1322,7 @@ struct tile_args {
 	int* neighbors;
 	long long cap;              // entries allocated in neighbors
 	int* flags;                 // 1: a unit did not fit kUnitCap, 2: neighbors too small
+	int experiment;             // SPICE_GEN_EXPERIMENT (measurements only, output is wrong): 1 = no look-back (tiles placed by index)
 };
 
 // #{k >= 1 : u < T[k]} from an estimate that is wrong once in ~1e5 draws
@@ -1479,7 +1480,9 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 			for (int off = 16; off > 0; off >>= 1)
 				tot += __shfl_xor_sync(0xffffffffu, tot, off);
 			long long excl = 0;
-			if (tile > 0) {
+			if (a.experiment == 1)
+				excl = tile * 6500;
+			else if (tile > 0) {
 				if (lane == 0)
 					atomicExch(a.desc + tile, (1ull << 62) | static_cast<unsigned long long>(tot));
 				long long idx = tile - 1;
@@ -1502,7 +1505,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 				}
 			}
 			if (lane == 0) {
-				atomicExch(a.desc + tile, (2ull << 62) | static_cast<unsigned long long>(excl + tot));
+				if (a.experiment != 1)
+					atomicExch(a.desc + tile, (2ull << 62) | static_cast<unsigned long long>(excl + tot));
 				s_excl = excl;
 			}
 		}
@@ -1551,6 +1555,8 @@ int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, doubl
 	tile_args a{};
 	a.src = src, a.dst = dst, a.col_lo = col_lo, a.col_hi = col_hi, a.seed_lo = seed_lo, a.seed_hi = seed_hi;
 	a.K = static_cast<int>(tab.size()) - 1;
+	if (char const* e = std::getenv("SPICE_GEN_EXPERIMENT"))
+		a.experiment = std::atoi(e);
 	a.s = p < 1 ? static_cast<float>(-1.0 / std::log2(1.0 - p)) : 0.0f;
 	a.block_log2 = 0;
 	while (static_cast<double>(1ll << a.block_log2) < 512.0 / p)
