@@ -181,8 +181,12 @@ SPICE_API int spice_stats(spice_ctx* ctx, int64_t* synaptic_events, int64_t* spi
 
 /* Phase timing with CUDA events recorded on the context's stream around each window's update
  * and delivery launches (measurement only; bench.py's roofline numbers come from here).
- * spice_profile_read synchronises, returns the sums since the last read and clears them. */
+ * enable = n > 1: around every n-th window only (four timed events per window cost ~3 % of a 270 us
+ * window; sampled, the timed region carries a quarter of that).  spice_profile_read synchronises,
+ * returns the sums over the marked windows since the last read (and how many there were) and clears them. */
 SPICE_API int spice_profile_enable(spice_ctx* ctx, int enable);
+/* launch windows enqueued so far (one per min-delay steps; one per step for networks with stateful synapses) */
+SPICE_API int64_t spice_windows_run(spice_ctx const* ctx);
 SPICE_API int spice_profile_read(spice_ctx* ctx, double* update_ms, double* deliver_ms, double* exchange_ms,
                                  int64_t* windows);
 

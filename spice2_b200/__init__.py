@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
             "spice_raster_read": (i32, [vp, i64, vp, vp]),
             "spice_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
             "spice_profile_enable": (i32, [vp, i32]),
+            "spice_windows_run": (i64, [vp]),
             "spice_profile_read": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(i64)]),
             "spice_ctx_finalize": (i32, [vp]),
@@ -360,8 +361,12 @@ class snn:
         self._check(lib().spice_stats(self._h, C.byref(ev), C.byref(sp), C.byref(kl)))
         return dict(synaptic_events=ev.value, spikes_delivered=sp.value, kernel_launches=kl.value)
 
-    def profile_enable(self, on=True):
-        self._check(lib().spice_profile_enable(self._h, int(on)))
+    def windows_run(self) -> int:
+        return int(lib().spice_windows_run(self._h))
+
+    def profile_enable(self, on=True, every=1):
+        """Phase events around every `every`-th window (1: all of them)."""
+        self._check(lib().spice_profile_enable(self._h, (max(int(every), 1) if on else 0)))
 
     def profile_read(self):
         u, d, x, w = C.c_double(), C.c_double(), C.c_double(), C.c_int64()

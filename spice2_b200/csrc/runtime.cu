@@ -504,6 +504,10 @@ struct spice_ctx {
 	// (and, with several ranks, the wait for the peers' spikes of window w is off the updates' path)
 	bool pipelined                    = false;
 	cudaStream_t dstream              = nullptr;
+	// spike sink: sink_pack runs on its own stream beside the window's delivery and the next window's updates
+	cudaStream_t sink_stream          = nullptr;
+	cudaEvent_t ev_sink_ready = nullptr, ev_sink_done = nullptr;
+	bool sink_pending                 = false;
 	cudaEvent_t ev_upd                = nullptr;
 	cudaEvent_t ev_del[2]             = {nullptr, nullptr};
 	bool del_pending[2]               = {false, false};
@@ -549,6 +553,8 @@ struct spice_ctx {
 
 	// phase timing (spice_profile_*): 4 events per window
 	bool profile = false;
+	int profile_every = 1; // phase events around every profile_every-th window (spice_profile_enable(ctx, n))
+	bool profile_now  = false; // ... this one
 	std::vector<cudaEvent_t> prof_events;
 	size_t prof_used = 0;
 	double prof_update = 0, prof_deliver = 0, prof_exchange = 0;
@@ -1097,7 +1103,8 @@ int prof_collect(spice_ctx* ctx) {
 
 int run_window(spice_ctx* ctx, int nsteps) {
 	int const np = static_cast<int>(ctx->pops.size());
-	if (ctx->profile) {
+	ctx->profile_now = ctx->profile && ctx->windows_run % ctx->profile_every == 0;
+	if (ctx->profile_now) {
 		if (ctx->prof_used >= 4096) {
 			int const rc = prof_collect(ctx);
 			if (rc != SPICE_OK)
@@ -1260,7 +1267,13 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
 		}
 
-	if (ctx->profile)
+	// the sink of the window before reads ring slots that the NEXT window (this rank's prologue, the peers' updates once
+	// they have this window's flag) writes again: it has had that window's delivery and this window's updates to finish
+	if (ctx->sink_pending) {
+		CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sink_done, 0));
+		ctx->sink_pending = false;
+	}
+	if (ctx->profile_now)
 		prof_mark(ctx);
 	if (ctx->world > 1) {
 		// DeliverFromTo synapses read their source neuron as it is at the end of this step, wherever it lives: this rank's
@@ -1309,8 +1322,18 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ctx->launches++;
 		}
 	}
+	// every spike of the window is in this rank's ring now: the sink may read it from here on (on its own stream)
+	bool const sink_aside = ctx->raster_on && np > 0 && !ctx->pipelined && !std::getenv("SPICE_SINK_INLINE");
+	if (sink_aside) {
+		if (!ctx->sink_stream) {
+			CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sink_stream, cudaStreamNonBlocking));
+			CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sink_ready, cudaEventDisableTiming));
+			CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sink_done, cudaEventDisableTiming));
+		}
+		CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_sink_ready, ctx->stream));
+	}
 
-	if (ctx->profile)
+	if (ctx->profile_now)
 		prof_mark(ctx);
 	if (ctx->any_stateful) {
 		// nsteps == 1 here.  snn.cpp:17-25: every 64 steps catch every plastic synapse up, then deliver
@@ -1401,7 +1424,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 				ta.work = ctx->d_work + parity;
 				CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_upd, ctx->stream));
 				CHECK_CUDA(ctx, cudaStreamWaitEvent(on, ctx->ev_upd, 0));
-				if (ctx->profile) {
+				if (ctx->profile_now) {
 					ctx->prof_used--; // the mark behind the exchange goes where the delivery starts
 					prof_mark(ctx, on);
 				}
@@ -1445,7 +1468,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ctx->launches++;
 		}
 
-	if (ctx->profile)
+	if (ctx->profile_now)
 		prof_mark(ctx, ctx->pipelined && ctx->tiled && ctx->n_desc > 0 ? ctx->dstream : nullptr);
 	if (ctx->raster_on && np > 0) {
 		sink_args sa{};
@@ -1471,8 +1494,15 @@ int run_window(spice_ctx* ctx, int nsteps) {
 		sa.consumed_steps = static_cast<unsigned long long>(ctx->sink_steps_read);
 		sa.consumed_ids   = ctx->sink_ids_read;
 		sa.h_error     = ctx->h_sink_error;
-		sink_pack<<<nsteps * np, kSinkThreads, ctx->sink_smem, ctx->stream>>>(sa);
+		cudaStream_t const sink_on = sink_aside ? ctx->sink_stream : ctx->stream;
+		if (sink_aside)
+			CHECK_CUDA(ctx, cudaStreamWaitEvent(sink_on, ctx->ev_sink_ready, 0));
+		sink_pack<<<nsteps * np, kSinkThreads, ctx->sink_smem, sink_on>>>(sa);
 		ctx->launches++;
+		if (sink_aside) {
+			CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_sink_done, sink_on));
+			ctx->sink_pending = true;
+		}
 		ctx->sink_windows++;
 		ctx->sink_steps_issued += nsteps;
 		// completion mark of this window: a readout waits for the event of the steps it takes, not for the stream
@@ -1485,7 +1515,7 @@ int run_window(spice_ctx* ctx, int nsteps) {
 			ctx->sink_marks.pop_front();
 		} else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
 			return fail(ctx, SPICE_ERR_CUDA, "cudaEventCreate (spike sink)");
-		if (cudaEventRecord(ev, ctx->stream) != cudaSuccess)
+		if (cudaEventRecord(ev, sink_on) != cudaSuccess)
 			return fail(ctx, SPICE_ERR_CUDA, "cudaEventRecord (spike sink)");
 		ctx->sink_marks.emplace_back(ctx->sink_steps_issued, ev);
 	}
@@ -1774,6 +1804,12 @@ int spice_ctx_destroy(spice_ctx* ctx) {
 	cudaFree(ctx->d_nib);
 	cudaFree(ctx->d_conn_desc);
 	cudaFree(ctx->d_work);
+	if (ctx->sink_stream) {
+		cudaStreamSynchronize(ctx->sink_stream);
+		cudaStreamDestroy(ctx->sink_stream);
+		cudaEventDestroy(ctx->ev_sink_ready);
+		cudaEventDestroy(ctx->ev_sink_done);
+	}
 	if (ctx->dstream) {
 		cudaStreamSynchronize(ctx->dstream);
 		cudaStreamDestroy(ctx->dstream);
@@ -2332,6 +2368,8 @@ int sink_wait(spice_ctx* ctx, long long upto) {
 			}
 		} else { // its mark was recycled
 			CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->sink_stream)
+				CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->sink_stream));
 			ctx->sink_steps_complete = ctx->sink_steps_issued;
 		}
 	}
@@ -2408,8 +2446,11 @@ int spice_stats(spice_ctx* ctx, int64_t* synaptic_events, int64_t* spikes_delive
 	return SPICE_OK;
 }
 
+int64_t spice_windows_run(spice_ctx const* ctx) { return ctx->windows_run; }
+
 int spice_profile_enable(spice_ctx* ctx, int enable) {
-	ctx->profile = enable != 0;
+	ctx->profile       = enable != 0;
+	ctx->profile_every = enable > 1 ? enable : 1;
 	return SPICE_OK;
 }
 
