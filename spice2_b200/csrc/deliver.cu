@@ -99,6 +99,12 @@ __device__ __forceinline__ void tally(int4 v) {
 	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long wall_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 __device__ unsigned g_zero_pair[2]; // an empty run, for lanes without a spike
 
 // what the unit path needs of a connection (a copy in shared memory; conn_desc stays in global memory)
@@ -198,9 +204,9 @@ __global__ void __launch_bounds__(kW * 32, kW <= 8 ? 2 : 1) deliver_units(tiles_
 	if (a.flags) { // several ranks: every peer's spikes of this window have landed in this rank's ring (NVLink peer stores)
 		if (tid < world) {
 			volatile unsigned long long const* f = a.flags + tid;
-			long long const start                = clock64();
+			unsigned long long const start       = wall_ns();
 			while (*f < a.seq) {
-				if (clock64() - start > 20000000000ll) { // ~10 s: a peer died; do not hang the GPU
+				if (wall_ns() - start > 10000000000ull) { // 10 s of wall time (%globaltimer: independent of the SM clock): a peer died; do not hang the GPU
 					atomicOr(a.error, 1);
 					break;
 				}

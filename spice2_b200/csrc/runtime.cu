@@ -198,13 +198,19 @@ struct wait_args {
 	int* error;
 };
 
+__device__ __forceinline__ unsigned long long wall_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 __global__ void wait_window(wait_args a) {
 	if (static_cast<int>(threadIdx.x) >= a.world)
 		return;
 	volatile unsigned long long const* f = a.flags + threadIdx.x;
-	long long const start                = clock64();
+	unsigned long long const start       = wall_ns();
 	while (*f < a.seq) {
-		if (clock64() - start > 20000000000ll) { // ~10 s: a peer died; do not hang the GPU
+		if (wall_ns() - start > 10000000000ull) { // 10 s of wall time (%globaltimer: independent of the SM clock): a peer died; do not hang the GPU
 			atomicOr(a.error, 1);
 			break;
 		}
