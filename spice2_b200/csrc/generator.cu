@@ -1304,6 +1304,8 @@ __global__ void __launch_bounds__(256) fp_fast_rows(fast_args a) {
 // ---- tiles ----
 constexpr int kTileWarps = 8;    // units per tile = warps per CTA (4 measures the same)
 constexpr int kUnitCap   = 1536; // entries a warp can hold: the mean is < 1024, sigma < 32
+constexpr int kPipedCap  = 1280; // ... in each of its two buffers in the pipelined kernel (mean + 8 sigma: a unit that does not fit
+                                 // sends the whole generation back to the one-buffer kernel)
 constexpr int kTabSmem   = 4096; // table entries (pairs) kept in shared memory (p >= 0.0054); larger tables are read through L1
 
 struct tile_args {
@@ -1364,27 +1366,172 @@ __device__ __forceinline__ int scan_up(int v) { // inclusive warp scan: shfl.up 
 }
 
 // Entry: how a warp keeps a block-relative target until its place in the output is known (u16 while B <= 65536, p >= 2^-7)
+struct gen_env {
+	uint2 const* tab;
+	unsigned tab_s;
+	int K;
+	float neg_s, s32;
+};
+
+// one unit (row r, block b), generated by one warp into buf: returns the number of kept targets
+template <bool kSmemTab, class Entry, int kCap>
+__device__ __forceinline__ int generate_unit(tile_args const& a, gen_env const& g, long long v, Entry* buf, int lane, long long& r, long long& b) {
+	util::seed_seq const seed(UInt128{a.seed_lo, a.seed_hi});
+	Entry* const buf4     = buf + lane * 4;
+	long long const B     = 1ll << a.block_log2;
+	r                     = v / a.nb_local;
+	b                     = a.b_lo + (v - r * a.nb_local);
+	long long const blk0  = b << a.block_log2;
+	int const bsize       = static_cast<int>(min(B, a.dst - blk0));
+	int const lo          = static_cast<int>(max(a.col_lo - blk0, 0ll));
+	int const hi          = static_cast<int>(min(a.col_hi - blk0, static_cast<long long>(bsize)));
+	UInt128 const st      = seed.stream(static_cast<UInt>(r * a.nblocks + b) * 32 + static_cast<UInt>(lane)).seed();
+	unsigned long long s0 = st.lo, s1 = st.hi;
+	int pos               = -1; // the last target drawn so far, relative to the block
+	int n                 = 0;
+	while (pos < hi - 1) {
+		unsigned long long const x0 = s0 + s1;
+		xoro_advance(s0, s1);
+		unsigned long long const x1 = s0 + s1;
+		xoro_advance(s0, s1);
+		unsigned const u0 = static_cast<unsigned>(x0 >> 32), u1 = static_cast<unsigned>(x0), u2 = static_cast<unsigned>(x1 >> 32),
+		               u3 = static_cast<unsigned>(x1);
+		bool ok = true;
+		int c0  = gap_est<kSmemTab>(u0, g.tab, g.tab_s, g.K, g.neg_s, g.s32, ok);
+		int c1  = gap_est<kSmemTab>(u1, g.tab, g.tab_s, g.K, g.neg_s, g.s32, ok);
+		int c2  = gap_est<kSmemTab>(u2, g.tab, g.tab_s, g.K, g.neg_s, g.s32, ok);
+		int c3  = gap_est<kSmemTab>(u3, g.tab, g.tab_s, g.K, g.neg_s, g.s32, ok);
+		if (!ok) [[unlikely]] {
+			c0 = gap_fix<kSmemTab>(u0, g.tab, g.tab_s, g.K, c0);
+			c1 = gap_fix<kSmemTab>(u1, g.tab, g.tab_s, g.K, c1);
+			c2 = gap_fix<kSmemTab>(u2, g.tab, g.tab_s, g.K, c2);
+			c3 = gap_fix<kSmemTab>(u3, g.tab, g.tab_s, g.K, c3);
+		}
+		int const l1 = c0 + 1, l2 = l1 + c1 + 1, l3 = l2 + c2 + 1, l4 = l3 + c3 + 1;
+		int const incl = scan_up(l4);
+		int const tot  = __shfl_sync(0xffffffffu, incl, 31);
+		int const base = pos + incl - l4;
+		int const t0 = base + l1, t1 = base + l2, t2 = base + l3, t3 = base + l4;
+		if (n + 128 > kCap) {
+			if (lane == 0)
+				atomicOr(a.flags, 1);
+			break;
+		}
+		if (pos + 1 >= lo && pos + tot < hi) { // every target of the iteration is kept
+			if ((n & 3) == 0) {
+				if constexpr (sizeof(Entry) == 2)
+					*reinterpret_cast<uint2*>(buf4 + n) = make_uint2(static_cast<unsigned>(t0) | static_cast<unsigned>(t1) << 16,
+					                                                 static_cast<unsigned>(t2) | static_cast<unsigned>(t3) << 16);
+				else
+					*reinterpret_cast<int4*>(buf4 + n) = make_int4(t0, t1, t2, t3);
+			} else { // only behind a first iteration that dropped targets in front of this rank's columns
+				buf4[n]     = static_cast<Entry>(t0);
+				buf4[n + 1] = static_cast<Entry>(t1);
+				buf4[n + 2] = static_cast<Entry>(t2);
+				buf4[n + 3] = static_cast<Entry>(t3);
+			}
+			n += 128;
+		} else {
+			bool const k0 = t0 >= lo && t0 < hi, k1 = t1 >= lo && t1 < hi, k2 = t2 >= lo && t2 < hi, k3 = t3 >= lo && t3 < hi;
+			int const mine = k0 + k1 + k2 + k3;
+			int const cs   = scan_up(mine);
+			int at = n + cs - mine;
+			if (k0)
+				buf[at++] = static_cast<Entry>(t0);
+			if (k1)
+				buf[at++] = static_cast<Entry>(t1);
+			if (k2)
+				buf[at++] = static_cast<Entry>(t2);
+			if (k3)
+				buf[at++] = static_cast<Entry>(t3);
+			n += __shfl_sync(0xffffffffu, cs, 31);
+		}
+		pos += tot;
+	}
+	return n;
+}
+
+// a unit's targets from shared memory to their place in the output, and the row's offset if the unit starts the row
+template <class Entry>
+__device__ __forceinline__ void write_unit(tile_args const& a, long long base, int n, long long v, long long r, long long b, Entry const* buf, int lane) {
+	if (base + n > a.cap) {
+		if (lane == 0)
+			atomicOr(a.flags, 2);
+	} else {
+		int const add    = static_cast<int>((b << a.block_log2) - a.col_lo); // block-relative target -> local column
+		int* dst         = a.neighbors + base + lane;
+		Entry const* src = buf + lane;
+		for (int i = lane; i < n; i += 32, dst += 32, src += 32)
+			*dst = static_cast<int>(*src) + add;
+	}
+	if (lane == 0) {
+		if (b == a.b_lo)
+			a.offsets[r] = base;
+		if (v == a.units - 1)
+			a.offsets[a.src] = base + n;
+	}
+}
+
+// decoupled look-back (one warp): publish the tile's count, add up the counts of the tiles before it back to the nearest one
+// whose inclusive prefix is known, publish this tile's inclusive prefix; returns the exclusive one
+__device__ __forceinline__ long long look_back(tile_args const& a, long long tile, long long tot, int lane) {
+	long long excl = 0;
+	if (a.experiment == 1)
+		return tile * 6500;
+	if (tile > 0) {
+		if (lane == 0)
+			atomicExch(a.desc + tile, (1ull << 62) | static_cast<unsigned long long>(tot));
+		long long idx = tile - 1;
+		for (;;) { // 32 predecessors at a time, nearest first
+			long long const j = idx - lane;
+			unsigned long long d;
+			do {
+				d = j >= 0 ? *reinterpret_cast<unsigned long long volatile*>(a.desc + j) : (2ull << 62);
+			} while (__any_sync(0xffffffffu, (d >> 62) == 0));
+			unsigned const incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+			int const stop           = incl_mask ? __ffs(incl_mask) - 1 : 31;
+			long long part           = lane <= stop ? static_cast<long long>(d & ((1ull << 62) - 1)) : 0;
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1)
+				part += __shfl_xor_sync(0xffffffffu, part, off);
+			excl += part;
+			if (incl_mask)
+				break;
+			idx -= 32;
+		}
+	}
+	if (lane == 0)
+		atomicExch(a.desc + tile, (2ull << 62) | static_cast<unsigned long long>(excl + tot));
+	return excl;
+}
+
+template <bool kSmemTab, class Entry>
+__device__ __forceinline__ gen_env load_env(tile_args const& a, unsigned char* smem_tab) {
+	gen_env g;
+	if constexpr (kSmemTab) {
+		uint2* const t = reinterpret_cast<uint2*>(smem_tab);
+		for (int i = threadIdx.x; i < a.K; i += blockDim.x)
+			t[i] = a.tab[i];
+		g.tab   = t;
+		g.tab_s = static_cast<unsigned>(__cvta_generic_to_shared(t));
+	} else {
+		g.tab   = a.tab;
+		g.tab_s = 0;
+	}
+	g.K     = a.K;
+	g.neg_s = -a.s;
+	g.s32   = 32.0f * a.s;
+	return g;
+}
+
 template <bool kSmemTab, class Entry>
 __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__shared__ int wcount[kTileWarps];
 	__shared__ long long s_tile, s_excl;
 	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	Entry* const buf  = reinterpret_cast<Entry*>(smem) + warp * kUnitCap;
-	Entry* const buf4 = buf + lane * 4;
-	uint2 const* tab;
-	if constexpr (kSmemTab) {
-		uint2* const t = reinterpret_cast<uint2*>(smem + sizeof(Entry) * kTileWarps * kUnitCap);
-		for (int i = threadIdx.x; i < a.K; i += blockDim.x)
-			t[i] = a.tab[i];
-		tab = t;
-	} else
-		tab = a.tab;
-	unsigned const tab_s = kSmemTab ? static_cast<unsigned>(__cvta_generic_to_shared(tab)) : 0u;
-	util::seed_seq const seed(UInt128{a.seed_lo, a.seed_hi});
-	long long const B = 1ll << a.block_log2;
-	float const neg_s = -a.s, s32 = 32.0f * a.s;
-	int const K = a.K;
+	Entry* const buf = reinterpret_cast<Entry*>(smem) + warp * kUnitCap;
+	gen_env const g  = load_env<kSmemTab, Entry>(a, smem + sizeof(Entry) * kTileWarps * kUnitCap);
 	for (;;) {
 		// A ticket is claimed only when the CTA is free to work on it (measured: claiming the next one while the current tile is
 		// in its look-back hides the round trip but makes later tiles wait for a tile nobody generates yet: 2.3 -> 6.6 ms at 1e5^2)
@@ -1398,140 +1545,102 @@ __global__ void __launch_bounds__(kTileWarps * 32) fp_fast_tiles(tile_args a) {
 		long long const v = tile * kTileWarps + warp;
 		int n             = 0;
 		long long r = 0, b = 0;
-		if (v < a.units) {
-			r                     = v / a.nb_local;
-			b                     = a.b_lo + (v - r * a.nb_local);
-			long long const blk0  = b << a.block_log2;
-			int const bsize       = static_cast<int>(min(B, a.dst - blk0));
-			int const lo_rel      = static_cast<int>(max(a.col_lo - blk0, 0ll));
-			int const hi_rel      = static_cast<int>(min(a.col_hi - blk0, static_cast<long long>(bsize)));
-			UInt128 const st      = seed.stream(static_cast<UInt>(r * a.nblocks + b) * 32 + static_cast<UInt>(lane)).seed();
-			unsigned long long s0 = st.lo, s1 = st.hi;
-			int pos               = -1; // the last target drawn so far, relative to the block
-			int const lo = lo_rel, hi = hi_rel;
-			while (pos < hi - 1) {
-				unsigned long long const x0 = s0 + s1;
-				xoro_advance(s0, s1);
-				unsigned long long const x1 = s0 + s1;
-				xoro_advance(s0, s1);
-				unsigned const u0 = static_cast<unsigned>(x0 >> 32), u1 = static_cast<unsigned>(x0), u2 = static_cast<unsigned>(x1 >> 32),
-				               u3 = static_cast<unsigned>(x1);
-				bool ok = true;
-				int c0  = gap_est<kSmemTab>(u0, tab, tab_s, K, neg_s, s32, ok);
-				int c1  = gap_est<kSmemTab>(u1, tab, tab_s, K, neg_s, s32, ok);
-				int c2  = gap_est<kSmemTab>(u2, tab, tab_s, K, neg_s, s32, ok);
-				int c3  = gap_est<kSmemTab>(u3, tab, tab_s, K, neg_s, s32, ok);
-				if (!ok) [[unlikely]] {
-					c0 = gap_fix<kSmemTab>(u0, tab, tab_s, K, c0);
-					c1 = gap_fix<kSmemTab>(u1, tab, tab_s, K, c1);
-					c2 = gap_fix<kSmemTab>(u2, tab, tab_s, K, c2);
-					c3 = gap_fix<kSmemTab>(u3, tab, tab_s, K, c3);
-				}
-				int const l1 = c0 + 1, l2 = l1 + c1 + 1, l3 = l2 + c2 + 1, l4 = l3 + c3 + 1;
-				int const incl = scan_up(l4);
-				int const tot  = __shfl_sync(0xffffffffu, incl, 31);
-				int const base = pos + incl - l4;
-				int const t0 = base + l1, t1 = base + l2, t2 = base + l3, t3 = base + l4;
-				if (n + 128 > kUnitCap) {
-					if (lane == 0)
-						atomicOr(a.flags, 1);
-					break;
-				}
-				if (pos + 1 >= lo && pos + tot < hi) { // every target of the iteration is kept
-					if ((n & 3) == 0) {
-						if constexpr (sizeof(Entry) == 2)
-							*reinterpret_cast<uint2*>(buf4 + n) = make_uint2(static_cast<unsigned>(t0) | static_cast<unsigned>(t1) << 16,
-							                                                 static_cast<unsigned>(t2) | static_cast<unsigned>(t3) << 16);
-						else
-							*reinterpret_cast<int4*>(buf4 + n) = make_int4(t0, t1, t2, t3);
-					} else { // only behind a first iteration that dropped targets in front of this rank's columns
-						buf4[n]     = static_cast<Entry>(t0);
-						buf4[n + 1] = static_cast<Entry>(t1);
-						buf4[n + 2] = static_cast<Entry>(t2);
-						buf4[n + 3] = static_cast<Entry>(t3);
-					}
-					n += 128;
-				} else {
-					bool const k0 = t0 >= lo && t0 < hi, k1 = t1 >= lo && t1 < hi, k2 = t2 >= lo && t2 < hi, k3 = t3 >= lo && t3 < hi;
-					int const mine = k0 + k1 + k2 + k3;
-					int const cs   = scan_up(mine);
-					int at = n + cs - mine;
-					if (k0)
-						buf[at++] = static_cast<Entry>(t0);
-					if (k1)
-						buf[at++] = static_cast<Entry>(t1);
-					if (k2)
-						buf[at++] = static_cast<Entry>(t2);
-					if (k3)
-						buf[at++] = static_cast<Entry>(t3);
-					n += __shfl_sync(0xffffffffu, cs, 31);
-				}
-				pos += tot;
-			}
-		}
+		if (v < a.units)
+			n = generate_unit<kSmemTab, Entry, kUnitCap>(a, g, v, buf, lane, r, b);
 		if (lane == 0)
 			wcount[warp] = n;
 		__syncthreads();
-
 		if (warp == 0) {
 			int const c   = lane < kTileWarps ? wcount[lane] : 0;
 			long long tot = c;
 #pragma unroll
 			for (int off = 16; off > 0; off >>= 1)
 				tot += __shfl_xor_sync(0xffffffffu, tot, off);
-			long long excl = 0;
-			if (a.experiment == 1)
-				excl = tile * 6500;
-			else if (tile > 0) {
-				if (lane == 0)
-					atomicExch(a.desc + tile, (1ull << 62) | static_cast<unsigned long long>(tot));
-				long long idx = tile - 1;
-				for (;;) { // 32 predecessors at a time, nearest first
-					long long const j = idx - lane;
-					unsigned long long d;
-					do {
-						d = j >= 0 ? *reinterpret_cast<unsigned long long volatile*>(a.desc + j) : (2ull << 62);
-					} while (__any_sync(0xffffffffu, (d >> 62) == 0));
-					unsigned const incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-					int const stop           = incl_mask ? __ffs(incl_mask) - 1 : 31;
-					long long part           = lane <= stop ? static_cast<long long>(d & ((1ull << 62) - 1)) : 0;
-#pragma unroll
-					for (int off = 16; off > 0; off >>= 1)
-						part += __shfl_xor_sync(0xffffffffu, part, off);
-					excl += part;
-					if (incl_mask)
-						break;
-					idx -= 32;
-				}
-			}
-			if (lane == 0) {
-				if (a.experiment != 1)
-					atomicExch(a.desc + tile, (2ull << 62) | static_cast<unsigned long long>(excl + tot));
+			long long const excl = look_back(a, tile, tot, lane);
+			if (lane == 0)
 				s_excl = excl;
-			}
 		}
 		__syncthreads();
 		if (v < a.units) {
 			long long base = s_excl;
 			for (int w = 0; w < warp; w++)
 				base += wcount[w];
-			if (base + n > a.cap) {
-				if (lane == 0)
-					atomicOr(a.flags, 2);
-			} else {
-				int const add    = static_cast<int>((b << a.block_log2) - a.col_lo); // block-relative target -> local column
-				int* dst         = a.neighbors + base + lane;
-				Entry const* src = buf + lane;
-				for (int i = lane; i < n; i += 32, dst += 32, src += 32)
-					*dst = static_cast<int>(*src) + add;
-			}
-			if (lane == 0) {
-				if (b == a.b_lo)
-					a.offsets[r] = base;
-				if (v == a.units - 1)
-					a.offsets[a.src] = base + n;
-			}
+			write_unit<Entry>(a, base, n, v, r, b, buf, lane);
 		}
+	}
+}
+
+// The same with the look-back off the generators' path (SPICE_GEN_PIPELINED=1): 8 generator warps with two buffers each and a
+// ninth warp that claims the tickets and places the tiles.  The generators go on to the next tile while the last one's
+// place is being found and write it out afterwards; named barriers (ids 1..6) hand tickets, counts and places back and forth.
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool kSmemTab, class Entry>
+__global__ void __launch_bounds__((kTileWarps + 1) * 32) fp_fast_tiles_piped(tile_args a) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ int s_cnt[2][kTileWarps];
+	__shared__ long long s_tile[2], s_base[2][kTileWarps];
+	constexpr int kAll = (kTileWarps + 1) * 32;
+	constexpr int kTicket = 1, kFull = 3, kBase = 5; // + buffer index
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	gen_env const g = load_env<kSmemTab, Entry>(a, smem + sizeof(Entry) * 2 * kTileWarps * kPipedCap);
+	__syncthreads(); // the table is loaded
+	if (warp == kTileWarps) { // ---- the placing warp
+		if (lane == 0)
+			s_tile[0] = static_cast<long long>(atomicAdd(a.ticket, 1ull));
+		__syncwarp();
+		bar_arrive(kTicket + 0, kAll);
+		for (int i = 0;; i++) {
+			int const bf = i & 1;
+			bar_sync(kFull + bf, kAll); // the counts of tile i are in
+			long long const tile = s_tile[bf];
+			if (tile >= a.tiles)
+				return;
+			// The generators want their next tile now — not earlier: a ticket held by a CTA that is still busy with the tile
+			// before makes every later tile's look-back wait for it.  The round trip hides behind their stores of tile i - 1.
+			if (lane == 0)
+				s_tile[bf ^ 1] = static_cast<long long>(atomicAdd(a.ticket, 1ull));
+			__syncwarp();
+			bar_arrive(kTicket + (bf ^ 1), kAll);
+			int const c = lane < kTileWarps ? s_cnt[bf][lane] : 0;
+			int incl    = scan_up(c);
+			long long const tot  = __shfl_sync(0xffffffffu, incl, kTileWarps - 1);
+			long long const excl = look_back(a, tile, tot, lane);
+			if (lane < kTileWarps)
+				s_base[bf][lane] = excl + incl - c;
+			__syncwarp();
+			bar_arrive(kBase + bf, kAll);
+		}
+	}
+	// ---- the generators
+	Entry* const bufs = reinterpret_cast<Entry*>(smem) + warp * kPipedCap;
+	long long pv = -1, pr = 0, pb = 0; // the tile before: unit (-1: none), row, block
+	int pn = 0;
+	for (int i = 0;; i++) {
+		int const bf     = i & 1;
+		Entry* const buf = bufs + bf * kTileWarps * kPipedCap;
+		bar_sync(kTicket + bf, kAll);
+		long long const tile = s_tile[bf];
+		bool const valid     = tile < a.tiles;
+		long long const v    = tile * kTileWarps + warp;
+		int n                = 0;
+		long long r = 0, b = 0;
+		if (valid && v < a.units)
+			n = generate_unit<kSmemTab, Entry, kPipedCap>(a, g, v, buf, lane, r, b);
+		if (lane == 0)
+			s_cnt[bf][warp] = n;
+		__syncwarp();
+		bar_arrive(kFull + bf, kAll);
+		if (i > 0) { // the tile before has had this tile's generation to find its place
+			bar_sync(kBase + (bf ^ 1), kAll);
+			if (pv >= 0)
+				write_unit<Entry>(a, s_base[bf ^ 1][warp], pn, pv, pr, pb, bufs + (bf ^ 1) * kTileWarps * kPipedCap, lane);
+		}
+		if (!valid)
+			return;
+		pv = v < a.units ? v : -1;
+		pr = r, pb = b, pn = n;
 	}
 }
 }
@@ -1585,22 +1694,32 @@ int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, doubl
 	a.flags   = d_flags;
 	bool const smem_tab = a.K <= kTabSmem;
 	bool const narrow   = a.block_log2 <= 16;
-	auto const kernel   = smem_tab ? (narrow ? fp_fast_tiles<true, unsigned short> : fp_fast_tiles<true, int>)
-	                               : (narrow ? fp_fast_tiles<false, unsigned short> : fp_fast_tiles<false, int>);
-	size_t const smem   = (narrow ? 2 : 4) * static_cast<size_t>(kTileWarps * kUnitCap) + (smem_tab ? sizeof(uint2) * static_cast<size_t>(a.K) : 0);
-	GEN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-	int dev = 0, sms = 148, per_sm = 1;
+	// the pipelined kernel (two buffers per warp, a ninth warp places the tiles) unless SPICE_GEN_PIPELINED=0; its buffers hold
+	// mean + 8 sigma, a unit beyond that sends the generation back to the one-buffer kernel (mean + 16 sigma)
+	char const* const pe = std::getenv("SPICE_GEN_PIPELINED");
+	bool piped           = !(pe && pe[0] == '0') && a.experiment == 0;
+	int dev = 0, sms = 148;
 	GEN_CUDA(cudaGetDevice(&dev));
 	GEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	GEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTileWarps * 32, smem));
-	int const grid = static_cast<int>(std::min<long long>(a.tiles, static_cast<long long>(sms) * std::max(per_sm, 1)));
-	for (int attempt = 0; attempt < 2; attempt++) {
-		GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(a.cap + 8)));
+	for (int attempt = 0; attempt < 4; attempt++) {
+		int const threads = (kTileWarps + (piped ? 1 : 0)) * 32;
+		auto const kernel = piped ? (smem_tab ? (narrow ? fp_fast_tiles_piped<true, unsigned short> : fp_fast_tiles_piped<true, int>)
+		                                      : (narrow ? fp_fast_tiles_piped<false, unsigned short> : fp_fast_tiles_piped<false, int>))
+		                          : (smem_tab ? (narrow ? fp_fast_tiles<true, unsigned short> : fp_fast_tiles<true, int>)
+		                                      : (narrow ? fp_fast_tiles<false, unsigned short> : fp_fast_tiles<false, int>));
+		size_t const smem = (narrow ? 2 : 4) * static_cast<size_t>(kTileWarps) * (piped ? 2 * kPipedCap : kUnitCap) +
+		                    (smem_tab ? sizeof(uint2) * static_cast<size_t>(a.K) : 0);
+		int per_sm = 1;
+		GEN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		GEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+		int const grid = static_cast<int>(std::min<long long>(a.tiles, static_cast<long long>(sms) * std::max(per_sm, 1)));
+		if (!out->neighbors)
+			GEN_CUDA(cudaMalloc(&out->neighbors, sizeof(int) * static_cast<size_t>(a.cap + 8)));
 		a.neighbors = out->neighbors;
 		GEN_CUDA(cudaEventRecord(ev0, stream));
 		GEN_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (static_cast<size_t>(a.tiles) + 1), stream));
 		GEN_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream));
-		kernel<<<grid, kTileWarps * 32, smem, stream>>>(a);
+		kernel<<<grid, threads, smem, stream>>>(a);
 		GEN_CUDA(cudaGetLastError());
 		GEN_CUDA(cudaEventRecord(ev1, stream));
 		long long edges = 0;
@@ -1612,6 +1731,12 @@ int generate_fast_tiles(cudaStream_t stream, long long src, long long dst, doubl
 		out->launches += 1;
 		cudaEventElapsedTime(&out->total_ms, ev0, ev1);
 		out->rows_ms = out->total_ms;
+		if (piped && std::getenv("SPICE_GEN_FORCE_FALLBACK")) // tests: take the path below
+			flags |= 1;
+		if ((flags & 1) && piped) { // a unit beyond mean + 8 sigma: once more with the larger buffers
+			piped = false;
+			continue;
+		}
 		if (flags & 1) {
 			if (err)
 				*err = "counter-based generator: a unit exceeded its capacity (mean + 16 sigma)";

@@ -218,6 +218,13 @@ def test_fast_generator_matches_its_restatement(sp, orc, monkeypatch):
         r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
         off, nb = _fast_rows_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
         assert np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (s, d, p)
+    for knob in ("SPICE_GEN_FORCE_FALLBACK", "SPICE_GEN_PIPELINED"):  # the one-buffer kernel: as the fallback, and on its own ("0")
+        monkeypatch.setenv(knob, "1" if knob.endswith("FALLBACK") else "0")
+        for (s, d, p, lo, hi, il) in cases[:4] + cases[-1:]:
+            r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
+            off, nb = _fast_tiles_restated(orc, orc.seed_seq(list(il)), s, d, p, lo, hi)
+            assert np.array_equal(r["offsets"], off) and np.array_equal(r["neighbors"], nb), (knob, s, d, p)
+        monkeypatch.delenv(knob)
     monkeypatch.setenv("SPICE_GEN_FAST_LOG_PATH", "1")  # the log path at ordinary p
     for (s, d, p, lo, hi, il) in [(40, 700, 0.1, 0, 700, (1337,)), (30, 500, 0.75, 100, 320, (5,)), (9, 100, 1.0, 0, 100, (1,))]:
         r = sp.generate_fixed_probability(s, d, p, il, 0, col_lo=lo, col_hi=hi, fast=True)
