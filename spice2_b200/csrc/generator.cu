@@ -1246,7 +1246,8 @@ int generate_adj_list(void* stream_, int const* edges_src, int const* edges_dst,
 //     order from a ticket and get their place in the output by decoupled look-back over (status, count) words, so the
 //     neighbours are written once, coalesced, with no counting pass and no host round trip (the output is allocated at
 //     mean + 10 sigma entries; the run repeats with the exact size in the never-seen case that this is too small).
-//     A rank generates only the blocks that overlap its columns.
+//     A rank generates only the blocks that overlap its columns.  fp_fast_tiles_piped (the default) takes the look-back
+//     off the generators' path: two buffers per generator warp, a ninth warp claims the tickets and places the tiles.
 //  p <  2^-13  "log path" (fp_fast_rows, count + write passes): a warp per row, engines stream(r * 32 + lane),
 //     gap = 1 + floor(log(u) / log(1 - p)) in double with the glibc log restatement, 32 gaps per iteration.
 namespace {
