@@ -1905,10 +1905,10 @@ int spice_add_population(spice_ctx* ctx, spice_neuron_ops const* ops, int64_t si
 	p.ops    = ops;
 	p.size   = size;
 	if (!ctx->next_bounds.empty()) { // spice_set_next_partition: in-degree-balanced (or any other) target ranges
-		PRE(ctx, static_cast<int>(ctx->next_bounds.size()) == ctx->world + 1 && ctx->next_bounds.front() == 0 && ctx->next_bounds.back() == size &&
-		             std::is_sorted(ctx->next_bounds.begin(), ctx->next_bounds.end()));
-		p.bounds = std::move(ctx->next_bounds);
+		p.bounds = std::move(ctx->next_bounds); // consumed by this call whether or not it is valid
 		ctx->next_bounds.clear();
+		PRE(ctx, static_cast<int>(p.bounds.size()) == ctx->world + 1 && p.bounds.front() == 0 && p.bounds.back() == size &&
+		             std::is_sorted(p.bounds.begin(), p.bounds.end()));
 	} else {
 		p.bounds.resize(static_cast<size_t>(ctx->world) + 1);
 		for (int r = 0; r <= ctx->world; r++)
