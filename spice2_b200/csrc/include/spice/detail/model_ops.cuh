@@ -494,9 +494,8 @@ __global__ void __launch_bounds__(256) update_stateless_kernel(update_args a) {
 			}
 			rng.g = util::xoroshiro64_128p(s0, s1);
 		}
-		for (int q = 0; q < kRngChunk; q++) {
-			if (first + q >= a.n_local)
-				break;
+		int const nq = static_cast<int>(min(static_cast<std::int64_t>(kRngChunk), a.n_local - first));
+		for (int q = 0; q < nq; q++) {
 			rng.used = 0;
 			bool spiked;
 			if constexpr (draws > 0)

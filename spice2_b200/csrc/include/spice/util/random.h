@@ -192,7 +192,11 @@ SPICE_HD constexpr Real generate_canonical(Rng& rng) {
 	UInt draw              = rng();
 	if constexpr (rng_bits < 8 * static_cast<int>(sizeof(Real)))
 		draw = (draw << rng_bits) | rng();
-	return static_cast<Real>((draw >> (width - digits)) + (LeftOpen ? 1u : 0u)) / static_cast<Real>(1_u64 << digits);
+	UInt const top = (draw >> (width - digits)) + (LeftOpen ? 1u : 0u);
+	if constexpr (digits < 32) // the same value through a 32-bit conversion (I2F.U32 instead of the slower I2F.U64 on the device)
+		return static_cast<Real>(static_cast<UInt32>(top)) / static_cast<Real>(1_u64 << digits);
+	else
+		return static_cast<Real>(top) / static_cast<Real>(1_u64 << digits);
 }
 
 template <class Real, bool LeftOpen = false>
