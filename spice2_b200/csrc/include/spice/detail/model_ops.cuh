@@ -451,93 +451,69 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 }
 
 // ---- stateless neurons: one thread per (step, 32 consecutive neurons) ----------------------------
-// grid = (chunks of 32 neurons / 256, steps of the window): a block works on ONE step, so its threads share the step's
-// lookup tables (staged in shared memory: 32 dependent-free LDS instead of four rounds of global loads) and a warp's lanes
-// share the ring slot: a lane notes its spikes in a bit mask while it walks its 32 neurons and the warp reserves room for
-// all of them with ONE atomic behind the loop instead of a returning atomic per spike taken by one lane while 31 wait (the
-// order of a step's spike list is arbitrary anyway, readers sort).  Measured 17.1 us against 17.6 us per 15-step window of
-// the bench's 353,555 Poisson neurons: neither latency was the bound — 52 instructions per neuron and step, most of them
-// the 64-bit engine on the half-rate integer pipe (ALU pipe 65 % busy at 0.73 waves), are.
+// A flat grid, the step's lookup tables read through L1, one returning atomic per spike.  A variant with one step per grid
+// row, the tables staged in shared memory and ONE atomic per warp for its spikes ran 3 % faster alone (17.1 against 17.6 us
+// per window of the bench's 353,555 Poisson neurons) and made the update phase 9 us SLOWER (81.8 against 72.9 us, A/B on one
+// box): this kernel shares the SMs with the stateful populations' update kernels on other streams, and what counts is how
+// its blocks pack beside theirs, not its own duration.  Removed.
 template <class Neur>
 __global__ void __launch_bounds__(256) update_stateless_kernel(update_args a) {
-	constexpr int draws = rng_draws_v<Neur>;
-	__shared__ ulonglong2 s_nib[draws > 0 ? 32 * 16 : 1];
-	int const s               = static_cast<int>(blockIdx.y);
-	std::int64_t const chunks = (a.n_local + kRngChunk - 1) / kRngChunk;
-	std::int64_t const chunk  = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	bool const active         = chunk < chunks; // nobody leaves early: whole warps take part in the reservation below
-	std::int64_t const t      = a.t0 + s;
-	Neur const neur           = *static_cast<Neur const*>(a.functor);
-	float const dt            = a.dt[s];
+	constexpr int draws        = rng_draws_v<Neur>;
+	std::int64_t const chunks  = (a.n_local + kRngChunk - 1) / kRngChunk;
+	std::int64_t const item    = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (item >= chunks * a.nsteps)
+		return;
+	int const s              = static_cast<int>(item / chunks);
+	std::int64_t const chunk = item % chunks;
+	std::int64_t const t     = a.t0 + s;
+	Neur const neur          = *static_cast<Neur const*>(a.functor);
+	float const dt           = a.dt[s];
+
+	counting_rng rng;
 	if constexpr (draws > 0) {
-		ulonglong2 const* nib = reinterpret_cast<ulonglong2 const*>(a.rng.nib + static_cast<std::int64_t>(s) * 32 * 16);
-		for (int k = threadIdx.x; k < 32 * 16; k += blockDim.x)
-			s_nib[k] = __ldg(nib + k);
-		__syncthreads();
+		// state at this chunk's offset in step t's stream: XOR of the basis states selected by
+		// the chunk's jump polynomial, 4 coefficients per lookup
+		u128 const poly = a.jump_poly[chunk];
+		u128 const* nib = a.rng.nib + static_cast<std::int64_t>(s) * 32 * 16;
+		UInt s0 = 0, s1 = 0;
+#pragma unroll 8
+		for (int g = 0; g < 32; g++) {
+			unsigned const v = static_cast<unsigned>(((g < 16 ? poly.lo : poly.hi) >> (4 * (g & 15))) & 15);
+			ulonglong2 const e = __ldg(reinterpret_cast<ulonglong2 const*>(nib + g * 16 + v));
+			s0 ^= e.x;
+			s1 ^= e.y;
+		}
+		rng.g = util::xoroshiro64_128p(s0, s1);
 	}
 
 	std::int64_t const first = chunk * kRngChunk;
-	unsigned mask            = 0; // bit q: neuron first + q spiked
-	if (active) {
-		counting_rng rng;
+	std::int64_t const slot  = t % a.ring;
+	for (int q = 0; q < kRngChunk; q++) {
+		std::int64_t const i = first + q;
+		if (i >= a.n_local)
+			break;
+		rng.used = 0;
+		bool spiked;
+		if constexpr (draws > 0)
+			spiked = neur.update(dt, rng);
+		else {
+			null_rng none;
+			spiked = neur.update(dt, none);
+		}
 		if constexpr (draws > 0) {
-			// state at this chunk's offset in step t's stream: XOR of the basis states selected by
-			// the chunk's jump polynomial, 4 coefficients per lookup
-			u128 const poly = a.jump_poly[chunk];
-			UInt s0 = 0, s1 = 0;
-#pragma unroll
-			for (int g = 0; g < 32; g++) {
-				unsigned const v   = static_cast<unsigned>(((g < 16 ? poly.lo : poly.hi) >> (4 * (g & 15))) & 15);
-				ulonglong2 const e = s_nib[g * 16 + v];
-				s0 ^= e.x;
-				s1 ^= e.y;
-			}
-			rng.g = util::xoroshiro64_128p(s0, s1);
+			// fewer draws than declared: skip the rest so the next neuron starts at its own position.  More: every neuron
+			// behind this one in the chunk would read the wrong part of the stream — reported, not papered over
+			if (rng.used > draws)
+				atomicOr(a.error, 64);
+			for (; rng.used < draws; rng.used++)
+				rng.g.advance();
 		}
-		int const nq = static_cast<int>(min(static_cast<std::int64_t>(kRngChunk), a.n_local - first));
-		for (int q = 0; q < nq; q++) {
-			rng.used = 0;
-			bool spiked;
-			if constexpr (draws > 0)
-				spiked = neur.update(dt, rng);
-			else {
-				null_rng none;
-				spiked = neur.update(dt, none);
-			}
-			if constexpr (draws > 0) {
-				// fewer draws than declared: skip the rest so the next neuron starts at its own position.  More: every neuron
-				// behind this one in the chunk would read the wrong part of the stream — reported, not papered over
-				if (rng.used > draws)
-					atomicOr(a.error, 64);
-				for (; rng.used < draws; rng.used++)
-					rng.g.advance();
-			}
-			mask |= (spiked ? 1u : 0u) << q;
+		if (spiked) {
+			unsigned const pos    = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], 1u);
+			std::int64_t const at = slot * a.ring_cap + a.lo + pos;
+			for (int r = 0; r < a.world; r++)
+				a.ring_ids[r][at] = static_cast<std::int32_t>(a.lo + i);
 		}
-	}
-	int const mine = __popc(mask);
-	int incl       = mine;
-#pragma unroll
-	for (int off = 1; off < 32; off <<= 1) {
-		int const o = __shfl_up_sync(0xffffffffu, incl, off);
-		if (static_cast<int>(threadIdx.x & 31) >= off)
-			incl += o;
-	}
-	int const total = __shfl_sync(0xffffffffu, incl, 31);
-	if (total == 0)
-		return;
-	std::int64_t const slot = t % a.ring;
-	unsigned base           = 0;
-	if ((threadIdx.x & 31) == 0)
-		base = atomicAdd(&a.ring_cnt[slot * a.world + a.rank], static_cast<unsigned>(total));
-	base              = __shfl_sync(0xffffffffu, base, 0);
-	std::int64_t at   = slot * a.ring_cap + a.lo + base + (incl - mine);
-	while (mask) {
-		int const q = __ffs(mask) - 1;
-		mask &= mask - 1;
-		for (int r = 0; r < a.world; r++)
-			a.ring_ids[r][at] = static_cast<std::int32_t>(a.lo + first + q);
-		at++;
 	}
 }
 
@@ -629,7 +605,7 @@ struct neuron_ops_builder {
 		} else {
 			std::int64_t const chunks = (a->n_local + kRngChunk - 1) / kRngChunk;
 			if (chunks > 0 && a->nsteps > 0)
-				update_stateless_kernel<Neur><<<dim3(static_cast<unsigned>((chunks + 255) / 256), static_cast<unsigned>(a->nsteps)), 256, 0, stream>>>(*a);
+				update_stateless_kernel<Neur><<<grid_for(chunks * a->nsteps), 256, 0, stream>>>(*a);
 		}
 		return static_cast<int>(cudaGetLastError());
 	}
