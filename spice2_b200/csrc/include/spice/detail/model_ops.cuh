@@ -369,6 +369,22 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 			if (c < NIN)
 				fsyn.v[c] = *static_cast<FSyn const*>(a.in[c].functor);
 	}
+	// Two incoming connections in a row with the SAME synapse object (samples/brunel: P->E and E->E both carry w_exc): the k1
+	// deliveries of one followed by the k2 of the other are k1 + k2 calls of the same function — the same float operations in
+	// the same order, one loop instead of two.
+	bool same_as_next[C] = {};
+	if constexpr (!std::is_void_v<FSyn> && !Generic) {
+#pragma unroll
+		for (int c = 0; c + 1 < C; c++)
+			if (c + 1 < NIN) {
+				bool eq = !a.in[c].zero_after_read && !a.in[c + 1].zero_after_read;
+				unsigned char const* x = reinterpret_cast<unsigned char const*>(&fsyn.v[c]);
+				unsigned char const* y = reinterpret_cast<unsigned char const*>(&fsyn.v[c + 1]);
+				for (unsigned k = 0; k < sizeof(FSyn); k++)
+					eq = eq && x[k] == y[k];
+				same_as_next[c] = eq;
+			}
+	}
 
 	for (int s = 0; s < a.nsteps; s++) {
 		int const cnext = cslot + 1 == a.cring ? 0 : cslot + 1;
@@ -380,6 +396,14 @@ __global__ void __launch_bounds__(128, 8) update_stateful_kernel(update_args a) 
 				kn[c] = cp[c][static_cast<std::int64_t>(cnext) * a.in[c].cstride];
 		}
 		// fold in the events whose delivery the reference ran at the end of step t-1
+		if constexpr (!std::is_void_v<FSyn> && !Generic) {
+#pragma unroll
+			for (int c = 0; c + 1 < C; c++)
+				if (c + 1 < NIN && same_as_next[c]) {
+					kk[c + 1] += kk[c];
+					kk[c] = 0;
+				}
+		}
 #pragma unroll
 		for (int c = 0; c < C; c++) {
 			if (c < NIN && kk[c]) {
